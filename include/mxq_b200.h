@@ -1,0 +1,151 @@
+/*
+ * mxq_b200 -- C ABI of the B200-native (sm_100a) MXQ quantization hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types, no C++ exceptions.
+ * Every entry point replaces one reference interface (cited as file:line under /root/reference).
+ *
+ * Conventions
+ *   - all tensor pointers are DEVICE pointers on the current CUDA device, row-major, contiguous,
+ *     16-byte aligned; the caller owns every buffer (inputs, outputs, workspace) -- the library
+ *     never allocates, frees or synchronises;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - return value: 0 = launched; < 0 = argument error (MXQ_E_*); > 0 = cudaError_t of the launch;
+ *   - dtype: MXQ_F32 / MXQ_F16 / MXQ_BF16;
+ *   - group_bits: optional device uint8[cols/group]; low 7 bits = bit-width, bit 7 (0x80) = the
+ *     group belongs to the per-row pool.  NULL = the reference recipe
+ *     {low, low, low, 0x80|4} repeated (utils_quant.py:340-385, mxqgpt.py:404-419).
+ *   - re-entrant and thread-safe: no mutable globals.
+ */
+#ifndef MXQ_B200_H_
+#define MXQ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MXQ_VERSION 100
+
+#if defined(__GNUC__)
+#define MXQ_API __attribute__((visibility("default")))
+#else
+#define MXQ_API
+#endif
+
+enum { MXQ_F32 = 0, MXQ_F16 = 1, MXQ_BF16 = 2 };
+
+enum {
+  MXQ_OK = 0,
+  MXQ_E_NULL = -1,      /* required pointer is NULL */
+  MXQ_E_SHAPE = -2,     /* shape / divisibility requirement violated */
+  MXQ_E_DTYPE = -3,     /* unknown dtype */
+  MXQ_E_ALIGN = -4,     /* pointer not 16-byte aligned */
+  MXQ_E_UNSUPPORTED = -5,
+  MXQ_E_WORKSPACE = -6  /* workspace too small */
+};
+
+MXQ_API int mxq_version(void);
+MXQ_API const char* mxq_error_string(int code);
+
+/* ---- (a-1) MXAsymQuantizer.forward   LLM-QAT/models/utils_quant.py:315-462 -------------------
+ * out[r,c] = round(((x-beta)/(alpha+1e-8))*s)/s*(alpha+1e-8)+beta, every op rounded to `dtype`.
+ * codes (optional, uint8[rows*cols]) receives the integer codes round(...) for parity checks.
+ * Requires cols % group == 0, group a power of two with 16 bytes <= group*sizeof(dtype) <= 512.
+ * With group_bits == NULL also cols % (4*group) == 0. */
+MXQ_API int mxq_fakequant_fwd(const void* x, void* out, uint8_t* codes, int64_t rows, int64_t cols,
+                      int dtype, int group, int low_bits, const uint8_t* group_bits, void* stream);
+
+/* ---- (a-2) MXAsymQuantizer.backward   utils_quant.py:464-475 ---------------------------------
+ * grad_in = grad_out; grad_in[x >= hi] = 0; grad_in[x <= lo] = 0.   n = number of elements. */
+MXQ_API int mxq_ste_bwd(const void* grad_out, const void* x, void* grad_in, int64_t n, int dtype,
+                float lo, float hi, void* stream);
+
+/* ---- (a-5/a-8) calibration statistics --------------------------------------------------------
+ * sumsq[c] (+)= sum_t X[t,c]^2 in fp32.  This is the whole of what MXQGPT.add_batch's K x K
+ * Hessian is used for (diag(H)==0, mxqgpt.py:369-383,399-403) and the Wanda statistic of
+ * WrappedGPT.add_batch (layerwrapper.py:22-35: scaler_row = scaler_row*n/(n+b) + sumsq/(n+b)).
+ * out = prev_scale * out + add_scale * sumsq  when accumulate != 0, else out = add_scale*sumsq.
+ * `workspace` needs mxq_colsumsq_workspace_bytes(tokens, cols) bytes. */
+MXQ_API size_t mxq_colsumsq_workspace_bytes(int64_t tokens, int64_t cols);
+MXQ_API int mxq_colsumsq(const void* X, int64_t tokens, int64_t cols, int dtype, float* out,
+                 float prev_scale, float add_scale, int accumulate, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* Wanda metric |W| * sqrt(scaler_row)   mxq_quant/lib/prune.py:177.   W: dtype [rows, cols],
+ * scaler_row: fp32[cols], out: fp32 [rows, cols]. */
+MXQ_API int mxq_wanda_metric(const void* W, const float* scaler_row, float* out, int64_t rows,
+                     int64_t cols, int dtype, void* stream);
+
+/* ---- (a-6/a-7) MXQGPT.fasterquant(blocksize=16) + Quantizer ----------------------------------
+ * mxq_quant/lib/mxqgpt.py:387-448, mxq_quant/lib/quantizer.py:5-20,61-121,149-155.
+ * W (fp16 [rows, cols]) -> Wq (fp16 fake-quantized, may alias W).  colstat (optional fp32[cols]):
+ * columns with colstat == 0 are "dead" and zeroed first (mxqgpt.py:401-403).
+ * codes (optional uint8 [rows, cols]) receives the integer codes.  rows % 16 == 0 (second-level
+ * scale quantisation spans 16 consecutive rows, quantizer.py:115).
+ * workspace: mxq_ptq_workspace_bytes(rows, cols). */
+MXQ_API size_t mxq_ptq_workspace_bytes(int64_t rows, int64_t cols);
+MXQ_API int mxq_ptq_quant(const void* W, void* Wq, uint8_t* codes, const float* colstat, int64_t rows,
+                  int64_t cols, int group, int low_bits, const uint8_t* group_bits,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Generic Quantizer(bits, perchannel, asym, qq_scale_bits=4).find_params + quantize_dequantize on
+ * an fp32 matrix x[rows, cols] with one scale/zero per row (quantizer.py:61-121,149-155).
+ * y, codes, scale, zero are optional outputs (fp32[rows*cols], uint8[rows*cols], fp32[rows] x2). */
+MXQ_API int mxq_rowquant(const float* x, float* y, uint8_t* codes, float* scale, float* zero,
+                 int64_t rows, int64_t cols, int bits, int qq_scale_bits, void* stream);
+
+/* ---- (a-9) packed mixed 2/4-bit layout -------------------------------------------------------
+ * mxq_quant/cuda_kernel/csrc/quantization/gemv_mxq_cuda.cu:39-208 is the only consumer in the
+ * reference; shapes for [OC, IC]:
+ *   weight int32[OC, IC/16], weight_last int32[OC, IC/64], zeros_and_scales int32[OC, 32*nch],
+ *   zeros_2nd int32[OC/4, 32*nch], scales_2nd fp16[OC/4, 3*IC/64], scales_4b fp16[OC],
+ *   zeros_4b int32[OC/8];   nch = ceil(IC/4096).  IC % 64 == 0, OC % 8 == 0 (mxq_pack: OC % 16). */
+typedef struct {
+  int32_t* weight;
+  int32_t* weight_last;
+  int32_t* zeros_and_scales;
+  int32_t* zeros_2nd;
+  void* scales_2nd;   /* fp16 */
+  void* scales_4b;    /* fp16 */
+  int32_t* zeros_4b;
+} mxq_packed_t;
+
+/* Quantize fp16 W[OC, IC] into the packed layout (encode policy documented in DESIGN.md; the
+ * reference has no producer).  colstat as in mxq_ptq_quant.  Every word of every output tensor
+ * is written (no pre-zeroing needed). */
+MXQ_API size_t mxq_pack_workspace_bytes(int64_t OC, int64_t IC);
+MXQ_API int mxq_pack(const void* W, const float* colstat, int64_t OC, int64_t IC, mxq_packed_t out,
+             void* workspace, size_t workspace_bytes, void* stream);
+
+/* Dequantize the packed layout to fp16 or fp32 [OC, IC] (decode formula of
+ * gemv_mxq_cuda.cu:131-136,152-153,178-179,191-192). */
+MXQ_API int mxq_unpack(mxq_packed_t in, int64_t OC, int64_t IC, void* out, int out_dtype, void* stream);
+
+/* ---- (a-9) gemv_mxq_forward_cuda   gemv_mxq_cuda.cu:225-273, gemv_mxq_cuda.h:4-12 -------------
+ * y[b, oc] = sum_k dequant(W)[oc, k] * x[b, k]; x fp16 [B, IC], y fp16 [B, OC], fp32 accumulate.
+ * Any IC % 64 == 0 (the reference is hard-wired to 4096), any B >= 1. */
+MXQ_API int mxq_gemv(const void* x, mxq_packed_t w, void* y, int64_t B, int64_t IC, int64_t OC,
+             void* stream);
+
+/* ---- (a-10) gemv_forward_cuda (AWQ uniform 4-bit)   gemv_cuda.cu:346-399, gemv_cuda.h:4-9 ------
+ * kernel int32[OC, IC/8] (nibble j of word i = column 8i+j), zeros int32[OC, zw] (nibble g%8 of
+ * word g/8, g = col/G), scales fp16[OC, zw*8]; zw = ceil(IC/G/8) rounded up to 1/2/4 words for
+ * G = 128/64/32 (gemv_cuda.cu:200,129,56). */
+MXQ_API int mxq_awq_gemv(const void* x, const int32_t* kernel, const void* scales, const int32_t* zeros,
+                 void* y, int64_t B, int64_t IC, int64_t OC, int group_size, void* stream);
+
+/* ---- prefill: packed dequant-GEMM on tcgen05/TMEM (no reference kernel exists for the mixed
+ * layout; gemm_cuda_gen.cu:424-478 is the un-built AWQ 4-bit analogue) --------------------------
+ * y[m, oc] = sum_k x[m, k] * dequant(W)[oc, k]; x fp16 [M, IC], y fp16 [M, OC].
+ * workspace: mxq_gemm_workspace_bytes(M, IC, OC) (TMA descriptors live in kernel params; the
+ * workspace holds the tile scheduler counter). */
+MXQ_API size_t mxq_gemm_workspace_bytes(int64_t M, int64_t IC, int64_t OC);
+MXQ_API int mxq_gemm(const void* x, mxq_packed_t w, void* y, int64_t M, int64_t IC, int64_t OC,
+             void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MXQ_B200_H_ */

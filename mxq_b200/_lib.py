@@ -1,0 +1,110 @@
+"""ctypes loader for libmxq_b200.so (the C ABI declared in include/mxq_b200.h).
+
+There is no CPU fallback: if the library is missing or a call is made with non-CUDA tensors the
+wrappers raise.  Build with ``python -m mxq_b200.build`` (or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmxq_b200.so")
+
+MXQ_F32, MXQ_F16, MXQ_BF16 = 0, 1, 2
+POOL = 0x80
+
+_DTYPE = {torch.float32: MXQ_F32, torch.float16: MXQ_F16, torch.bfloat16: MXQ_BF16}
+
+# every symbol include/mxq_b200.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "mxq_version", "mxq_error_string", "mxq_fakequant_fwd", "mxq_ste_bwd",
+    "mxq_colsumsq_workspace_bytes", "mxq_colsumsq", "mxq_wanda_metric",
+    "mxq_ptq_workspace_bytes", "mxq_ptq_quant", "mxq_rowquant",
+    "mxq_pack_workspace_bytes", "mxq_pack", "mxq_unpack", "mxq_gemv", "mxq_awq_gemv",
+    "mxq_gemm_workspace_bytes", "mxq_gemm",
+]
+
+
+class PackedC(C.Structure):
+    """mxq_packed_t"""
+    _fields_ = [("weight", C.c_void_p), ("weight_last", C.c_void_p),
+                ("zeros_and_scales", C.c_void_p), ("zeros_2nd", C.c_void_p),
+                ("scales_2nd", C.c_void_p), ("scales_4b", C.c_void_p), ("zeros_4b", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the mxq_b200 CUDA library is not built and there is no CPU "
+            "fallback. Run `python -m mxq_b200.build`.")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32, f32, sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
+    L.mxq_version.restype = i32
+    L.mxq_error_string.restype = C.c_char_p
+    L.mxq_error_string.argtypes = [i32]
+    L.mxq_fakequant_fwd.argtypes = [vp, vp, vp, i64, i64, i32, i32, i32, vp, vp]
+    L.mxq_ste_bwd.argtypes = [vp, vp, vp, i64, i32, f32, f32, vp]
+    L.mxq_colsumsq_workspace_bytes.restype = sz
+    L.mxq_colsumsq_workspace_bytes.argtypes = [i64, i64]
+    L.mxq_colsumsq.argtypes = [vp, i64, i64, i32, vp, f32, f32, i32, vp, sz, vp]
+    L.mxq_wanda_metric.argtypes = [vp, vp, vp, i64, i64, i32, vp]
+    L.mxq_ptq_workspace_bytes.restype = sz
+    L.mxq_ptq_workspace_bytes.argtypes = [i64, i64]
+    L.mxq_ptq_quant.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, vp, vp, sz, vp]
+    L.mxq_rowquant.argtypes = [vp, vp, vp, vp, vp, i64, i64, i32, i32, vp]
+    L.mxq_pack_workspace_bytes.restype = sz
+    L.mxq_pack_workspace_bytes.argtypes = [i64, i64]
+    L.mxq_pack.argtypes = [vp, vp, i64, i64, PackedC, vp, sz, vp]
+    L.mxq_unpack.argtypes = [PackedC, i64, i64, vp, i32, vp]
+    L.mxq_gemv.argtypes = [vp, PackedC, vp, i64, i64, i64, vp]
+    L.mxq_awq_gemv.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i32, vp]
+    L.mxq_gemm_workspace_bytes.restype = sz
+    L.mxq_gemm_workspace_bytes.argtypes = [i64, i64, i64]
+    L.mxq_gemm.argtypes = [vp, PackedC, vp, i64, i64, i64, vp, sz, vp]
+    for name in SYMBOLS:
+        if getattr(L, name).restype is C.c_int:
+            pass
+    _lib = L
+    return L
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = lib().mxq_error_string(code).decode()
+        raise RuntimeError(f"{what} failed: {msg} (code {code})")
+
+
+def dtype_enum(t: torch.Tensor) -> int:
+    try:
+        return _DTYPE[t.dtype]
+    except KeyError:
+        raise TypeError(f"mxq_b200: unsupported dtype {t.dtype}") from None
+
+
+def require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mxq_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+def ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def packed_struct(p: dict) -> PackedC:
+    return PackedC(p["weight"].data_ptr(), p["weight_last"].data_ptr(),
+                   p["zeros_and_scales"].data_ptr(), p["zeros_2nd"].data_ptr(),
+                   p["scales_2nd"].data_ptr(), p["scales_4b"].data_ptr(), p["zeros_4b"].data_ptr())

@@ -1,0 +1,345 @@
+// Fused MXQ fake-quant forward and clipped-STE backward (sm_100a).
+//
+// Replaces LLM-QAT/models/utils_quant.py:315-475 (MXAsymQuantizer.forward/backward): the
+// reference runs ~2.3k tiny ATen kernels and 5 full-size temporaries per 4096-wide weight; here
+// the forward is ONE pass over HBM (read x once, write out once).
+//
+// Forward data path:  HBM --cp.async.bulk (TMA 1-D, mbarrier tx-count)--> shared-memory ring of
+// whole rows --LDS.128--> registers --STG.128 (streaming)--> HBM.  Rows must be CTA-resident
+// because all 4-bit columns of a row share one min/max (utils_quant.py:347,368-377).
+//   pass 1 (per row)  : min/max over the pooled (4-bit) chunks only, warp shuffle + 8 partials
+//   pass 2 (per chunk): 16-byte chunk per lane, group min/max by xor-shuffles across the
+//                       lanes of the group, quantize/dequantize op by op in the tensor dtype.
+// Bit-exactness: IEEE fp32 ops via __f*_rn intrinsics (never contracted), division by a
+// correctly-rounded reciprocal + one Markstein correction (common.cuh), round-half-even by the
+// magic-constant add.  Each intermediate is rounded to the tensor dtype like the reference's
+// separate ATen kernels do.
+#include "common.cuh"
+
+namespace mxq {
+
+struct FQParams {
+  const uint8_t* x;
+  uint8_t* out;
+  uint8_t* codes;
+  const uint8_t* group_bits;
+  int rows, cols;
+  int cpr;          // 16-byte chunks per row
+  int lpg;          // lanes (chunks) per group, power of two <= 32
+  int lpg_shift;
+  int low_bits, pool_bits;
+  int tw;           // warps cooperating on one row (power of two)
+  int tw_shift;
+  int teams;        // rows per stage = 8 / tw
+  int stages;
+  int row_bytes;
+  int stage_bytes;
+  int num_sets;     // ceil(rows / teams)
+};
+
+constexpr int kFQThreads = 256;
+
+template <typename T, bool kRef>
+__global__ void __launch_bounds__(kFQThreads) fakequant_fwd_kernel(const FQParams p) {
+  using D = DT<T>;
+  constexpr int EPC = D::EPC;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* bufs = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  float2* part = reinterpret_cast<float2*>(bars + 8);
+  uint8_t* gtab = reinterpret_cast<uint8_t*>(part + 8);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int team = warp >> p.tw_shift, tw = warp & (p.tw - 1);
+  const int tthreads = p.tw * 32;
+
+  if (!kRef) {
+    const int ng = p.cols / (p.lpg * EPC);
+    for (int g = tid; g < ng; g += kFQThreads) gtab[g] = p.group_bits[g];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int first = blockIdx.x, step = gridDim.x;
+  const int nmine = first < p.num_sets ? (p.num_sets - first + step - 1) / step : 0;
+
+  auto issue = [&](int it) {
+    const int set = first + it * step;
+    const int stage = it % p.stages;
+    const int row0 = set * p.teams;
+    const int nrows = min(p.teams, p.rows - row0);
+    const uint32_t bytes = (uint32_t)nrows * (uint32_t)p.row_bytes;
+    mbar_arrive_expect_tx(&bars[stage], bytes);
+    bulk_g2s(bufs + (size_t)stage * p.stage_bytes, p.x + (size_t)row0 * p.row_bytes, bytes,
+             &bars[stage]);
+  };
+  if (tid == 0) {
+    const int n0 = min(p.stages, nmine);
+    for (int s = 0; s < n0; ++s) issue(s);
+  }
+
+  const float s_low = (float)((1 << p.low_bits) - 1);
+  const float s_pool = (float)((1 << p.pool_bits) - 1);
+  const float rs_low = __frcp_rn(s_low), rs_pool = __frcp_rn(s_pool);
+
+  for (int it = 0; it < nmine; ++it) {
+    const int stage = it % p.stages;
+    const uint32_t parity = (it / p.stages) & 1;
+    const int row0 = (first + it * step) * p.teams;
+    const int nrows = min(p.teams, p.rows - row0);
+    const bool active = team < nrows;
+    const uint8_t* rowp = bufs + (size_t)stage * p.stage_bytes + (size_t)team * p.row_bytes;
+    mbar_wait(&bars[stage], parity);
+
+    // ---- pass 1: per-row min/max over the pooled chunks -----------------------------------
+    float pmin = INFINITY, pmax = -INFINITY;
+    if (active) {
+      if (kRef) {
+        const int npc = p.cpr >> 2;  // one group in four is pooled
+        for (int m = tw * 32 + lane; m < npc; m += tthreads) {
+          const int c = ((((m >> p.lpg_shift) << 2) + 3) << p.lpg_shift) + (m & (p.lpg - 1));
+          const uint4 ch = *reinterpret_cast<const uint4*>(rowp + (size_t)c * 16);
+          float f[EPC];
+          D::unpack(ch, f);
+#pragma unroll
+          for (int e = 0; e < EPC; ++e) { pmin = fminf(pmin, f[e]); pmax = fmaxf(pmax, f[e]); }
+        }
+      } else {
+        for (int c = tw * 32 + lane; c < p.cpr; c += tthreads) {
+          if (gtab[c >> p.lpg_shift] & MXQ_POOL_FLAG) {
+            const uint4 ch = *reinterpret_cast<const uint4*>(rowp + (size_t)c * 16);
+            float f[EPC];
+            D::unpack(ch, f);
+#pragma unroll
+            for (int e = 0; e < EPC; ++e) { pmin = fminf(pmin, f[e]); pmax = fmaxf(pmax, f[e]); }
+          }
+        }
+      }
+    }
+    pmin = warp_min(pmin);
+    pmax = warp_max(pmax);
+    if (lane == 0) part[warp] = make_float2(pmin, pmax);
+    __syncthreads();
+    pmin = INFINITY; pmax = -INFINITY;
+    for (int i = 0; i < p.tw; ++i) {
+      const float2 v = part[(team << p.tw_shift) + i];
+      pmin = fminf(pmin, v.x); pmax = fmaxf(pmax, v.y);
+    }
+    // utils_quant.py:369-377: fp32 subtract, cast to the tensor dtype on assignment (:383)
+    const float a_pool = D::rnd(__fadd_rn(D::rnd(__fsub_rn(pmax, pmin)), 1e-8f));
+    const float b_pool = pmin;
+    const float r_pool = __frcp_rn(a_pool);
+
+    // ---- pass 2: quantize / dequantize -----------------------------------------------------
+    if (active) {
+      uint8_t* orow = p.out + (size_t)(row0 + team) * p.row_bytes;
+      uint8_t* crow = p.codes ? p.codes + (size_t)(row0 + team) * p.cols : nullptr;
+      for (int c0 = tw * 32; c0 < p.cpr; c0 += tthreads) {
+        const int c = c0 + lane;
+        const bool valid = c < p.cpr;
+        float f[EPC];
+        float lmin = INFINITY, lmax = -INFINITY;
+        if (valid) {
+          const uint4 ch = *reinterpret_cast<const uint4*>(rowp + (size_t)c * 16);
+          D::unpack(ch, f);
+#pragma unroll
+          for (int e = 0; e < EPC; ++e) { lmin = fminf(lmin, f[e]); lmax = fmaxf(lmax, f[e]); }
+        }
+        for (int o = p.lpg >> 1; o > 0; o >>= 1) {
+          lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+          lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        }
+        if (!valid) continue;
+        const int g = c >> p.lpg_shift;
+        const bool pooled = kRef ? ((g & 3) == 3) : ((gtab[g] & MXQ_POOL_FLAG) != 0);
+        float a, b, r, s, rs;
+        if (pooled) {
+          a = a_pool; b = b_pool; r = r_pool; s = s_pool; rs = rs_pool;
+        } else {
+          a = D::rnd(__fadd_rn(D::rnd(__fsub_rn(lmax, lmin)), 1e-8f));  // alpha + 1e-8 (:456)
+          b = lmin;
+          r = __frcp_rn(a);
+          s = s_low; rs = rs_low;
+        }
+        float o[EPC];
+        uint32_t cw[EPC / 4] = {};
+#pragma unroll
+        for (int e = 0; e < EPC; ++e) {
+          float t = D::rnd(__fsub_rn(f[e], b));
+          t = D::rnd(div_rn_by(t, a, r));          // input_normalized (:456)
+          t = D::rnd(__fmul_rn(t, s));
+          int qi;
+          const float q = rint_magic(t, qi);       // torch.round (:458)
+          t = D::rnd(div_rn_by(q, s, rs));         // .div(s)
+          t = D::rnd(__fmul_rn(t, a));
+          o[e] = D::rnd(__fadd_rn(t, b));          // (:460)
+          cw[e >> 2] |= (uint32_t)(qi & 0xFF) << (8 * (e & 3));
+        }
+        st_stream(orow + (size_t)c * 16, D::pack(o));
+        if (crow) {
+          if (EPC == 4) {
+            *reinterpret_cast<uint32_t*>(crow + (size_t)c * 4) = cw[0];
+          } else {
+            *reinterpret_cast<uint2*>(crow + (size_t)c * 8) = make_uint2(cw[0], cw[EPC / 4 - 1]);
+          }
+        }
+      }
+    }
+    __syncthreads();  // every warp is done reading this stage (and `part`)
+    if (tid == 0 && it + p.stages < nmine) issue(it + p.stages);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// STE backward: pure streaming select, 3 tensors, 128-bit accesses, 4 chunks in flight / thread
+// -------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) ste_bwd_kernel(const uint4* __restrict__ g,
+                                                      const uint4* __restrict__ x,
+                                                      uint4* __restrict__ gi, int64_t nchunks,
+                                                      float lo, float hi) {
+  using D = DT<T>;
+  constexpr int EPC = D::EPC;
+  constexpr int U = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + (U - 1) * stride < nchunks; i += U * stride) {
+    uint4 gv[U], xv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { gv[u] = ld_stream(g + i + u * stride); xv[u] = ld_stream(x + i + u * stride); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float gf[EPC], xf[EPC];
+      D::unpack(gv[u], gf);
+      D::unpack(xv[u], xf);
+#pragma unroll
+      for (int e = 0; e < EPC; ++e) gf[e] = (xf[e] >= hi || xf[e] <= lo) ? 0.0f : gf[e];
+      st_stream(gi + i + u * stride, D::pack(gf));
+    }
+  }
+  for (; i < nchunks; i += stride) {
+    float gf[EPC], xf[EPC];
+    D::unpack(ld_stream(g + i), gf);
+    D::unpack(ld_stream(x + i), xf);
+#pragma unroll
+    for (int e = 0; e < EPC; ++e) gf[e] = (xf[e] >= hi || xf[e] <= lo) ? 0.0f : gf[e];
+    st_stream(gi + i, D::pack(gf));
+  }
+}
+
+template <typename T>
+__global__ void ste_bwd_tail_kernel(const T* g, const T* x, T* gi, int64_t start, int64_t n,
+                                    float lo, float hi) {
+  int64_t i = start + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float xf = (float)x[i];
+    gi[i] = (xf >= hi || xf <= lo) ? (T)0.0f : g[i];
+  }
+}
+
+template <typename T>
+static int launch_fq(const FQParams& p, bool ref, int smem, int grid, cudaStream_t st) {
+  auto k = ref ? fakequant_fwd_kernel<T, true> : fakequant_fwd_kernel<T, false>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  k<<<grid, kFQThreads, smem, st>>>(p);
+  MXQ_LAUNCH_RESULT();
+}
+
+template <typename T>
+static int launch_ste(const void* g, const void* x, void* gi, int64_t n, float lo, float hi,
+                      cudaStream_t st) {
+  constexpr int EPC = DT<T>::EPC;
+  const int64_t nchunks = n / EPC;
+  if (nchunks > 0) {
+    int64_t blocks = ceil_div(nchunks, 256 * 4);
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    ste_bwd_kernel<T><<<(int)blocks, 256, 0, st>>>((const uint4*)g, (const uint4*)x, (uint4*)gi,
+                                                   nchunks, lo, hi);
+  }
+  const int64_t done = nchunks * EPC;
+  if (done < n) {
+    ste_bwd_tail_kernel<T><<<1, 32, 0, st>>>((const T*)g, (const T*)x, (T*)gi, done, n, lo, hi);
+  }
+  MXQ_LAUNCH_RESULT();
+}
+
+}  // namespace mxq
+
+using namespace mxq;
+
+extern "C" int mxq_fakequant_fwd(const void* x, void* out, uint8_t* codes, int64_t rows,
+                                 int64_t cols, int dtype, int group, int low_bits,
+                                 const uint8_t* group_bits, void* stream) {
+  if (rows < 0 || cols < 0) return MXQ_E_SHAPE;
+  if (rows == 0 || cols == 0) return MXQ_OK;
+  MXQ_CHECK_PTR(x);
+  MXQ_CHECK_PTR(out);
+  if (dtype != MXQ_F32 && dtype != MXQ_F16 && dtype != MXQ_BF16) return MXQ_E_DTYPE;
+  const int esize = dtype == MXQ_F32 ? 4 : 2;
+  const int epc = 16 / esize;
+  if (group < epc || (group & (group - 1)) || group / epc > 32) return MXQ_E_SHAPE;
+  if (cols % group) return MXQ_E_SHAPE;
+  if (!group_bits && cols % (4 * group)) return MXQ_E_SHAPE;
+  if (low_bits < 1 || low_bits > 8) return MXQ_E_SHAPE;
+  if (rows > INT32_MAX || cols > (1 << 24)) return MXQ_E_SHAPE;
+
+  FQParams p{};
+  p.x = (const uint8_t*)x; p.out = (uint8_t*)out; p.codes = codes; p.group_bits = group_bits;
+  p.rows = (int)rows; p.cols = (int)cols;
+  p.row_bytes = (int)cols * esize;
+  p.cpr = p.row_bytes / 16;
+  p.lpg = group / epc;
+  p.lpg_shift = 0;
+  while ((1 << p.lpg_shift) < p.lpg) ++p.lpg_shift;
+  p.low_bits = low_bits; p.pool_bits = 4;
+  int teams = 8;
+  while (teams > 1 && (int64_t)teams * p.row_bytes > 16384) teams >>= 1;
+  p.teams = teams; p.tw = 8 / teams;
+  p.tw_shift = 0;
+  while ((1 << p.tw_shift) < p.tw) ++p.tw_shift;
+  p.stage_bytes = teams * p.row_bytes;
+  const int ng = (int)(cols / group);
+  const int tail = 8 * 8 + 8 * 8 + ((ng + 15) & ~15);
+  const int max_smem = 227 * 1024;
+  if (p.stage_bytes + tail > max_smem) return MXQ_E_UNSUPPORTED;
+  int stages = 98304 / p.stage_bytes;
+  if (stages < 1) stages = 1;
+  if (stages > 4) stages = 4;
+  while (stages < 2 && (stages + 1) * p.stage_bytes + tail <= max_smem) ++stages;
+  p.stages = stages;
+  p.num_sets = (int)ceil_div(rows, teams);
+  const int smem = stages * p.stage_bytes + tail;
+  int bps = (228 * 1024) / (smem + 1024);
+  if (bps < 1) bps = 1;
+  if (bps > 8) bps = 8;
+  int grid = kNumSMs * bps;
+  if (grid > p.num_sets) grid = p.num_sets;
+  cudaStream_t st = as_stream(stream);
+  const bool ref = group_bits == nullptr;
+  switch (dtype) {
+    case MXQ_F32: return launch_fq<float>(p, ref, smem, grid, st);
+    case MXQ_F16: return launch_fq<__half>(p, ref, smem, grid, st);
+    default: return launch_fq<__nv_bfloat16>(p, ref, smem, grid, st);
+  }
+}
+
+extern "C" int mxq_ste_bwd(const void* grad_out, const void* x, void* grad_in, int64_t n,
+                           int dtype, float lo, float hi, void* stream) {
+  if (n < 0) return MXQ_E_SHAPE;
+  if (n == 0) return MXQ_OK;
+  MXQ_CHECK_PTR(grad_out);
+  MXQ_CHECK_PTR(x);
+  MXQ_CHECK_PTR(grad_in);
+  cudaStream_t st = as_stream(stream);
+  switch (dtype) {
+    case MXQ_F32: return launch_ste<float>(grad_out, x, grad_in, n, lo, hi, st);
+    case MXQ_F16: return launch_ste<__half>(grad_out, x, grad_in, n, lo, hi, st);
+    case MXQ_BF16: return launch_ste<__nv_bfloat16>(grad_out, x, grad_in, n, lo, hi, st);
+    default: return MXQ_E_DTYPE;
+  }
+}

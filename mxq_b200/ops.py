@@ -1,0 +1,234 @@
+"""Tensor-level wrappers over the C ABI (include/mxq_b200.h).  torch is plumbing here: it owns the
+device memory and the stream; every computation happens in libmxq_b200.so."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+POOL = L.POOL
+
+
+def reference_group_bits(cols: int, group: int = 16, low_bits: int = 2, device=None) -> torch.Tensor:
+    """{low, low, low, POOL|4} repeated -- the reference's positional 2/4-bit recipe
+    (LLM-QAT/models/utils_quant.py:340-385; mxq_quant/lib/mxqgpt.py:404-419)."""
+    if cols % (4 * group):
+        raise ValueError(f"cols={cols} must be a multiple of 4*group={4 * group}")
+    gb = torch.full((cols // group,), low_bits, dtype=torch.uint8)
+    gb[3::4] = POOL | 4
+    return gb.to(device) if device is not None else gb
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def fakequant_fwd(x: torch.Tensor, num_bits: int = 2, group: int = 16, group_bits=None,
+                  return_codes: bool = False):
+    """MXAsymQuantizer.forward (utils_quant.py:315-462) for a 2-D tensor."""
+    if x.dim() != 2:
+        raise ValueError("MXAsymQuantizer fake-quant is defined for 2-D weights (utils_quant.py:630)")
+    L.require_cuda(x, group_bits)
+    x = x.contiguous()
+    rows, cols = x.shape
+    if cols % 64 and group_bits is None and group == 16:
+        # the reference itself fails here: W_4b has K/64*16 columns (utils_quant.py:347,368)
+        raise ValueError("in_features must be a multiple of 64 for the mixed 2/4-bit recipe")
+    out = torch.empty_like(x)
+    codes = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if return_codes else None
+    rc = L.lib().mxq_fakequant_fwd(L.ptr(x), L.ptr(out), L.ptr(codes), rows, cols, L.dtype_enum(x),
+                                   group, num_bits, L.ptr(group_bits), L.stream())
+    L.check(rc, "mxq_fakequant_fwd")
+    return (out, codes) if return_codes else out
+
+
+def ste_bwd(grad_out: torch.Tensor, x: torch.Tensor, lo: float, hi: float) -> torch.Tensor:
+    """MXAsymQuantizer.backward (utils_quant.py:464-475)."""
+    L.require_cuda(grad_out, x)
+    if grad_out.dtype != x.dtype or grad_out.shape != x.shape:
+        raise ValueError("grad_out and x must match in dtype and shape")
+    g = grad_out.contiguous()
+    xc = x.contiguous()
+    gi = torch.empty_like(g)
+    rc = L.lib().mxq_ste_bwd(L.ptr(g), L.ptr(xc), L.ptr(gi), g.numel(), L.dtype_enum(g),
+                             float(lo), float(hi), L.stream())
+    L.check(rc, "mxq_ste_bwd")
+    return gi
+
+
+def colsumsq(X: torch.Tensor, out: torch.Tensor | None = None, prev_scale: float = 0.0,
+             add_scale: float = 1.0, workspace: torch.Tensor | None = None) -> torch.Tensor:
+    """out = prev_scale*out + add_scale * sum_tokens X^2 (per column, fp32)."""
+    L.require_cuda(X, out)
+    X2 = X.reshape(-1, X.shape[-1]).contiguous()
+    tokens, cols = X2.shape
+    accumulate = out is not None
+    if out is None:
+        out = torch.empty(cols, dtype=torch.float32, device=X.device)
+    need = L.lib().mxq_colsumsq_workspace_bytes(tokens, cols)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = _ws(need, X.device)
+    rc = L.lib().mxq_colsumsq(L.ptr(X2), tokens, cols, L.dtype_enum(X2), L.ptr(out),
+                              float(prev_scale), float(add_scale), int(accumulate),
+                              L.ptr(workspace), workspace.numel() * workspace.element_size(),
+                              L.stream())
+    L.check(rc, "mxq_colsumsq")
+    return out
+
+
+def wanda_metric(W: torch.Tensor, scaler_row: torch.Tensor) -> torch.Tensor:
+    """|W| * sqrt(scaler_row) (mxq_quant/lib/prune.py:177)."""
+    L.require_cuda(W, scaler_row)
+    W = W.contiguous()
+    out = torch.empty(W.shape, dtype=torch.float32, device=W.device)
+    rc = L.lib().mxq_wanda_metric(L.ptr(W), L.ptr(scaler_row.contiguous().float()), L.ptr(out),
+                                  W.shape[0], W.shape[1], L.dtype_enum(W), L.stream())
+    L.check(rc, "mxq_wanda_metric")
+    return out
+
+
+def ptq_quant(W: torch.Tensor, colstat: torch.Tensor | None = None, low_bits: int = 2,
+              group: int = 16, group_bits=None, return_codes: bool = False, out=None,
+              workspace=None):
+    """MXQGPT.fasterquant(blocksize=16) (mxq_quant/lib/mxqgpt.py:387-448): fp16 in, fp16 out."""
+    L.require_cuda(W, colstat, group_bits)
+    if W.dtype != torch.float16:
+        raise TypeError("ptq_quant expects fp16 weights (the reference casts back to the weight dtype)")
+    W = W.contiguous()
+    rows, cols = W.shape
+    Wq = torch.empty_like(W) if out is None else out
+    codes = torch.empty(W.shape, dtype=torch.uint8, device=W.device) if return_codes else None
+    need = L.lib().mxq_ptq_workspace_bytes(rows, cols)
+    if workspace is None or workspace.numel() < need:
+        workspace = _ws(need, W.device)
+    rc = L.lib().mxq_ptq_quant(L.ptr(W), L.ptr(Wq), L.ptr(codes), L.ptr(colstat), rows, cols, group,
+                               low_bits, L.ptr(group_bits), L.ptr(workspace), workspace.numel(),
+                               L.stream())
+    L.check(rc, "mxq_ptq_quant")
+    return (Wq, codes) if return_codes else Wq
+
+
+def rowquant(x: torch.Tensor, bits: int, qq_scale_bits: int | None = 4):
+    """Quantizer.find_params + quantize_dequantize / quantize (quantizer.py:61-121,149-173) on an
+    fp32 [rows, cols] matrix.  Returns (y, codes, scale, zero)."""
+    L.require_cuda(x)
+    x = x.contiguous().float()
+    rows, cols = x.shape
+    y = torch.empty_like(x)
+    codes = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    scale = torch.empty(rows, dtype=torch.float32, device=x.device)
+    zero = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rc = L.lib().mxq_rowquant(L.ptr(x), L.ptr(y), L.ptr(codes), L.ptr(scale), L.ptr(zero), rows,
+                              cols, bits, qq_scale_bits or 0, L.stream())
+    L.check(rc, "mxq_rowquant")
+    return y, codes, scale, zero
+
+
+def packed_shapes(OC: int, IC: int) -> dict:
+    if IC % 64 or OC % 8:
+        raise ValueError("IC must be a multiple of 64 and OC a multiple of 8")
+    nblk = IC // 64
+    nch = (nblk + 63) // 64
+    return dict(weight=((OC, nblk * 4), torch.int32), weight_last=((OC, nblk), torch.int32),
+                zeros_and_scales=((OC, 32 * nch), torch.int32),
+                zeros_2nd=((OC // 4, 32 * nch), torch.int32),
+                scales_2nd=((OC // 4, 3 * nblk), torch.float16),
+                scales_4b=((OC,), torch.float16), zeros_4b=((OC // 8,), torch.int32))
+
+
+def alloc_packed(OC: int, IC: int, device) -> dict:
+    return {k: torch.empty(s, dtype=d, device=device) for k, (s, d) in packed_shapes(OC, IC).items()}
+
+
+def pack(W: torch.Tensor, colstat: torch.Tensor | None = None, out: dict | None = None,
+         workspace=None) -> dict:
+    """fp16 W[OC, IC] -> packed mixed 2/4-bit tensors (layout of gemv_mxq_cuda.cu:39-208)."""
+    L.require_cuda(W, colstat)
+    if W.dtype != torch.float16:
+        raise TypeError("pack expects fp16 weights")
+    W = W.contiguous()
+    OC, IC = W.shape
+    if out is None:
+        out = alloc_packed(OC, IC, W.device)
+    need = L.lib().mxq_pack_workspace_bytes(OC, IC)
+    if workspace is None or workspace.numel() < need:
+        workspace = _ws(need, W.device)
+    rc = L.lib().mxq_pack(L.ptr(W), L.ptr(colstat), OC, IC, L.packed_struct(out), L.ptr(workspace),
+                          workspace.numel(), L.stream())
+    L.check(rc, "mxq_pack")
+    return out
+
+
+def _packed_dims(p: dict):
+    OC = p["weight"].shape[0]
+    IC = p["weight"].shape[1] * 16
+    return OC, IC
+
+
+def _check_packed(p: dict):
+    OC, IC = _packed_dims(p)
+    for k, (shape, dt) in packed_shapes(OC, IC).items():
+        t = p[k]
+        if tuple(t.shape) != tuple(shape) or t.dtype != dt or not t.is_contiguous():
+            raise ValueError(f"packed tensor '{k}' must be contiguous {dt} {tuple(shape)}, got "
+                             f"{t.dtype} {tuple(t.shape)}")
+        L.require_cuda(t)
+    return OC, IC
+
+
+def unpack(p: dict, dtype=torch.float32) -> torch.Tensor:
+    OC, IC = _check_packed(p)
+    out = torch.empty((OC, IC), dtype=dtype, device=p["weight"].device)
+    rc = L.lib().mxq_unpack(L.packed_struct(p), OC, IC, L.ptr(out), L.dtype_enum(out), L.stream())
+    L.check(rc, "mxq_unpack")
+    return out
+
+
+def gemv(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, validate: bool = True):
+    """y[B, OC] = x[B, IC] @ dequant(W)^T, fp16."""
+    OC, IC = _check_packed(p) if validate else _packed_dims(p)
+    L.require_cuda(x)
+    if x.dtype != torch.float16 or x.dim() != 2 or x.shape[1] != IC:
+        raise ValueError(f"x must be fp16 [B, {IC}]")
+    x = x.contiguous()
+    B = x.shape[0]
+    if out is None:
+        out = torch.empty((B, OC), dtype=torch.float16, device=x.device)
+    rc = L.lib().mxq_gemv(L.ptr(x), L.packed_struct(p), L.ptr(out), B, IC, OC, L.stream())
+    L.check(rc, "mxq_gemv")
+    return out
+
+
+def gemm(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, workspace=None,
+         validate: bool = True):
+    """Prefill: y[M, OC] = x[M, IC] @ dequant(W)^T on tcgen05/TMEM, fp16 in/out, fp32 accumulate."""
+    OC, IC = _check_packed(p) if validate else _packed_dims(p)
+    L.require_cuda(x)
+    if x.dtype != torch.float16 or x.dim() != 2 or x.shape[1] != IC:
+        raise ValueError(f"x must be fp16 [M, {IC}]")
+    x = x.contiguous()
+    M = x.shape[0]
+    if out is None:
+        out = torch.empty((M, OC), dtype=torch.float16, device=x.device)
+    need = L.lib().mxq_gemm_workspace_bytes(M, IC, OC)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.zeros(max(int(need), 16), dtype=torch.uint8, device=x.device)
+    rc = L.lib().mxq_gemm(L.ptr(x), L.packed_struct(p), L.ptr(out), M, IC, OC, L.ptr(workspace),
+                          workspace.numel(), L.stream())
+    L.check(rc, "mxq_gemm")
+    return out
+
+
+def awq_gemv(x: torch.Tensor, kernel: torch.Tensor, scales: torch.Tensor, zeros: torch.Tensor,
+             group_size: int) -> torch.Tensor:
+    """AWQ uniform 4-bit GEMV (gemv_cuda.cu:346-399)."""
+    L.require_cuda(x, kernel, scales, zeros)
+    x = x.contiguous()
+    B, IC = x.shape
+    OC = kernel.shape[0]
+    out = torch.empty((B, OC), dtype=torch.float16, device=x.device)
+    rc = L.lib().mxq_awq_gemv(L.ptr(x), L.ptr(kernel.contiguous()), L.ptr(scales.contiguous()),
+                              L.ptr(zeros.contiguous()), L.ptr(out), B, IC, OC, group_size,
+                              L.stream())
+    L.check(rc, "mxq_awq_gemv")
+    return out

@@ -1,0 +1,142 @@
+"""Drop-in for ``nas_quant`` / ``find_layers`` (mxq_quant/lib/prune.py:17-36,326-425), the driver
+behind ``python main.py --prune_method mxq``, plus ``quantize_linears``: the same per-layer work
+(statistics -> fasterquant -> pack) driven directly by calibration tensors, which is what the
+benchmark and the layer-sharded multi-GPU pass use."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .mxqgpt import MXQGPT
+
+dataset = "wikitext2"  # prune.py:13
+
+
+def find_layers(module, layers=(nn.Linear,), name=''):
+    """prune.py:17-36 -- recursively collect layers of the given types."""
+    if type(module) in layers or any(isinstance(module, t) for t in layers):
+        return {name: module}
+    res = {}
+    for name1, child in module.named_children():
+        res.update(find_layers(child, layers=layers, name=name + '.' + name1 if name != '' else name1))
+    return res
+
+
+@torch.no_grad()
+def nas_quant(args, model, tokenizer, dev, dataloader=None):
+    """prune.py:326-425.  ``dataloader`` (extension): iterable of (input_ids, ...) batches; when
+    omitted the reference's wikitext2 loader is needed, which requires the `datasets` package and
+    network access (prune.py:329)."""
+    print('Starting ...')
+    if dataloader is None:
+        try:
+            from lib.data import get_loaders  # the reference's own loader, if importable
+        except Exception as e:  # pragma: no cover - offline
+            raise RuntimeError("nas_quant needs a calibration dataloader (pass dataloader=...)") from e
+        dataloader, _ = get_loaders(dataset, nsamples=args.nsamples, seed=args.seed, seqlen=2048,
+                                    tokenizer=tokenizer)
+    use_cache = model.config.use_cache
+    model.config.use_cache = False
+    layers = model.model.layers
+    device_map = getattr(model, "hf_device_map", {})
+    if "model.embed_tokens" in device_map:
+        dev = device_map["model.embed_tokens"]
+    dtype = next(iter(model.parameters())).dtype
+    inps = torch.zeros((args.nsamples, model.seqlen, model.config.hidden_size), dtype=dtype, device=dev)
+    cache = {'i': 0, 'kwargs': {}}
+
+    class Catcher(nn.Module):
+        def __init__(self, module):
+            super().__init__()
+            self.module = module
+
+        def forward(self, inp, **kwargs):
+            inps[cache['i']] = inp
+            cache['i'] += 1
+            cache['kwargs'] = kwargs
+            raise ValueError
+
+    layers[0] = Catcher(layers[0])
+    for batch in dataloader:
+        try:
+            model(batch[0].to(dev))
+        except ValueError:
+            pass
+    layers[0] = layers[0].module
+    torch.cuda.empty_cache()
+    outs = torch.zeros_like(inps)
+    kwargs = {k: v for k, v in cache['kwargs'].items() if k in ("attention_mask", "position_ids", "position_embeddings")}
+    print('Ready.')
+
+    for i in range(len(layers)):
+        layer = layers[i]
+        if f"model.layers.{i}" in device_map:
+            dev = device_map[f"model.layers.{i}"]
+            kwargs = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in kwargs.items()}
+            inps, outs = inps.to(dev), outs.to(dev)
+        subset = find_layers(layer)
+        gpts = {name: MXQGPT(subset[name]) for name in subset}
+
+        def add_batch(name):
+            def tmp(_, inp, out):
+                gpts[name].add_batch(inp[0].data, out.data)
+            return tmp
+
+        handles = [subset[name].register_forward_hook(add_batch(name)) for name in gpts]
+        for j in range(args.nsamples):
+            outs[j] = layer(inps[j].unsqueeze(0), **kwargs)[0]
+        for h in handles:
+            h.remove()
+        for name in gpts:
+            print(i, name)
+            print('Pruning ...')
+            gpts[name].fasterquant(percdamp=0.01, blocksize=16,
+                                   pack=bool(getattr(args, "pack", False)))
+            if getattr(args, "pack", False):
+                subset[name].mxq_packed = gpts[name].packed
+            gpts[name].free()
+        for j in range(args.nsamples):
+            outs[j] = layer(inps[j].unsqueeze(0), **kwargs)[0]
+        layers[i] = layer
+        torch.cuda.empty_cache()
+        inps, outs = outs, inps
+
+    model.config.use_cache = use_cache
+    torch.cuda.empty_cache()
+
+
+class LinearQuantJob:
+    """Pre-allocated buffers for quantizing linears of one shape [OC, IC] repeatedly (no
+    allocation inside the timed region)."""
+
+    def __init__(self, OC: int, IC: int, device, tokens: int = 0):
+        self.OC, self.IC = OC, IC
+        self.Wq = torch.empty((OC, IC), dtype=torch.float16, device=device)
+        self.packed = ops.alloc_packed(OC, IC, device)
+        lib = ops.L.lib()
+        n = max(lib.mxq_ptq_workspace_bytes(OC, IC), lib.mxq_pack_workspace_bytes(OC, IC))
+        self.ws = torch.empty(int(n), dtype=torch.uint8, device=device)
+
+
+def calib_stat(X: torch.Tensor, nsamples: int, out=None, workspace=None) -> torch.Tensor:
+    """diag(H) of MXQGPT after all samples: (2/nsamples) * sum_tokens X^2 (mxqgpt.py:377-383)."""
+    return ops.colsumsq(X, out=None, add_scale=2.0 / nsamples, workspace=workspace) if out is None \
+        else _colsumsq_into(X, nsamples, out, workspace)
+
+
+def _colsumsq_into(X, nsamples, out, workspace):
+    X2 = X.reshape(-1, X.shape[-1])
+    lib = ops.L.lib()
+    rc = lib.mxq_colsumsq(ops.L.ptr(X2), X2.shape[0], X2.shape[1], ops.L.dtype_enum(X2),
+                          ops.L.ptr(out), 0.0, 2.0 / nsamples, 0, ops.L.ptr(workspace),
+                          workspace.numel(), ops.L.stream())
+    ops.L.check(rc, "mxq_colsumsq")
+    return out
+
+
+def quantize_linear(W: torch.Tensor, colstat: torch.Tensor, job: LinearQuantJob):
+    """fasterquant + pack for one linear into the job's buffers (W is left untouched)."""
+    ops.pack(W, colstat, out=job.packed, workspace=job.ws)
+    ops.ptq_quant(W, colstat, out=job.Wq, workspace=job.ws)
+    return job.Wq, job.packed

@@ -1,0 +1,112 @@
+"""CPU: the C-ABI library loads without a GPU, exports every symbol include/mxq_b200.h declares,
+and rejects bad arguments before touching the device; the host mirrors fail loudly off-GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from mxq_b200 import _lib, ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mxq_b200.h")).read()
+    return sorted(set(re.findall(r"MXQ_API[^;(]*?\b(mxq_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_loader_agree():
+    assert _declared_symbols() == sorted(_lib.SYMBOLS)
+
+
+def test_library_exports_every_symbol():
+    L = _lib.lib()
+    for name in _declared_symbols():
+        assert hasattr(L, name), name
+    assert L.mxq_version() == 100
+    assert b"shape" in L.mxq_error_string(-2)
+
+
+def test_argument_errors_without_gpu():
+    L = _lib.lib()
+    buf = (C.c_char * 4096)()
+    p = C.addressof(buf)
+    p16 = (p + 15) & ~15
+    # NULL pointer, unknown dtype, bad divisibility, misaligned pointer: all rejected up front
+    assert L.mxq_fakequant_fwd(None, p16, None, 4, 64, 0, 16, 2, None, None) == -1
+    assert L.mxq_fakequant_fwd(p16, p16, None, 4, 64, 7, 16, 2, None, None) == -3
+    assert L.mxq_fakequant_fwd(p16, p16, None, 4, 48, 0, 16, 2, None, None) == -2
+    assert L.mxq_fakequant_fwd(p16 + 4, p16, None, 4, 64, 0, 16, 2, None, None) == -4
+    assert L.mxq_fakequant_fwd(p16, p16, None, 4, 64, 0, 24, 2, None, None) == -2   # group not 2^k
+    assert L.mxq_fakequant_fwd(p16, p16, None, 0, 64, 0, 16, 2, None, None) == 0    # empty is a no-op
+    assert L.mxq_ste_bwd(None, p16, p16, 16, 0, -2.0, 2.0, None) == -1
+    assert L.mxq_ste_bwd(p16, p16, p16, 16, 9, -2.0, 2.0, None) == -3
+    assert L.mxq_ptq_quant(p16, p16, None, None, 8, 64, 16, 2, None, p16, 4096, None) == -2   # rows % 16
+    assert L.mxq_ptq_quant(p16, p16, None, None, 16, 64, 32, 2, None, p16, 4096, None) == -5  # group != 16
+    assert L.mxq_ptq_quant(p16, p16, None, None, 16, 64, 16, 2, None, p16, 8, None) == -6     # workspace
+    assert L.mxq_rowquant(p16, None, None, None, None, 8, 16, 2, 4, None) == -2               # rows % 16 w/ qq
+    pk = _lib.PackedC(p16, p16, p16, p16, p16, p16, p16)
+    assert L.mxq_gemv(p16, pk, p16, 1, 100, 64, None) == -2
+    assert L.mxq_pack(p16, None, 8, 64, pk, p16, 4096, None) == -2                            # OC % 16
+    assert L.mxq_awq_gemv(p16, p16, p16, p16, p16, 1, 128, 8, 48, None) == -5
+    assert L.mxq_ptq_workspace_bytes(4096, 4096) >= 4096 + 4096 * 8
+    assert L.mxq_colsumsq_workspace_bytes(262144, 4096) > 0
+
+
+def test_no_cpu_fallback():
+    x = torch.zeros(4, 64)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.fakequant_fwd(x)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.ste_bwd(x, x, -2, 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.colsumsq(x)
+    from mxq_b200 import MXAsymQuantizer
+    with pytest.raises(RuntimeError, match="CUDA"):
+        MXAsymQuantizer.apply(x, torch.tensor([-2.0, 2.0]), 2, False)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libmxq_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.lib()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "mxq_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_reference_recipe_mask():
+    gb = ops.reference_group_bits(128, 16, 2)
+    assert gb.tolist() == [2, 2, 2, 0x84] * 2
+    with pytest.raises(ValueError):
+        ops.reference_group_bits(96, 16, 2)
+
+
+def test_mirror_signatures_match_reference():
+    import inspect
+    from mxq_b200 import QuantizeLinear, MXQGPT, WrappedGPT
+    from mxq_b200 import engine
+    sig = inspect.signature(QuantizeLinear.__init__)
+    for kw, default in dict(symmetric=True, bias=False, w_bits=32, a_bits=32, act_layerwise=False,
+                            weight_layerwise=False, is_qk=False).items():
+        assert sig.parameters[kw].default == default
+    assert list(inspect.signature(MXQGPT.fasterquant).parameters)[:3] == ["self", "blocksize", "percdamp"]
+    assert inspect.signature(MXQGPT.fasterquant).parameters["blocksize"].default == 128
+    assert list(inspect.signature(MXQGPT.add_batch).parameters)[:3] == ["self", "inp", "out"]
+    assert list(inspect.signature(WrappedGPT.__init__).parameters) == ["self", "layer", "layer_id", "layer_name"]
+    assert list(inspect.signature(engine.gemv_mxq_forward_cuda).parameters) == [
+        "in_feats", "kernel", "kernel_last", "zeros_and_scales", "scales_2nd", "zeros_2nd",
+        "scales_4b", "zeros_4b", "group_size"]
+    lin = QuantizeLinear(64, 32, w_bits=2)
+    assert list(lin.state_dict().keys()) == ["weight"]
+    with pytest.raises(NotImplementedError):
+        QuantizeLinear(64, 32, w_bits=2, a_bits=8)

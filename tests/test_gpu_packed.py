@@ -1,0 +1,116 @@
+"""GPU parity for the packed mixed 2/4-bit layout: packer codes bit-exact vs the oracle's packer,
+decode bit-exact vs the reference decode formula, GEMV vs dequantize-then-matmul within
+max|err| <= 1e-3 * max|y| (fp16 output), and the reference's known-answer test."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mxq_oracle as O
+from tests.gpu_util import packed_to_dev, packed_to_np
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+def _rel_err(got, ref):
+    ref = np.asarray(ref, dtype=np.float64)
+    return np.abs(np.asarray(got, dtype=np.float64) - ref).max() / max(np.abs(ref).max(), 1e-30)
+
+
+def test_reference_known_answer(cuda):
+    # cuda_kernel/test_correct_gemv.py:19-53 through the mxq_inference_engine-compatible binding
+    from mxq_b200 import engine
+    p = packed_to_dev(O.kat_constant_fill(4096, 4096), cuda)
+    x = torch.ones((1, 4096), dtype=torch.float16, device=cuda)
+    C = engine.gemv_mxq_forward_cuda(x, p["weight"], p["weight_last"], p["zeros_and_scales"],
+                                     p["scales_2nd"], p["zeros_2nd"], p["scales_4b"], p["zeros_4b"], 16)
+    assert C.shape == (1, 4096) and C.dtype == torch.float16
+    assert torch.equal(C.int(), torch.full((1, 4096), 4096, dtype=torch.int32, device=cuda))
+    with pytest.raises(ValueError):
+        engine.gemv_mxq_forward_cuda(x, p["weight"], p["weight_last"], p["zeros_and_scales"],
+                                     p["scales_2nd"], p["zeros_2nd"], p["scales_4b"], p["zeros_4b"], 32)
+
+
+@pytest.mark.parametrize("shape", [(16, 64), (64, 256), (32, 4096 + 128), (48, 11008)])
+def test_pack_bit_exact_vs_oracle(cuda, shape):
+    from mxq_b200 import ops
+    rng = np.random.default_rng(shape[1])
+    W = (rng.standard_normal(shape) * 0.02).astype(np.float16)
+    W[3] = 0
+    W[5, :16] = 0.031
+    dead = np.zeros(shape[1], bool)
+    dead[[1, shape[1] - 2]] = True
+    stat = torch.from_numpy((~dead).astype(np.float32)).to(cuda)
+    want = O.pack_mxq(W, dead)
+    got = packed_to_np(ops.pack(torch.from_numpy(W).to(cuda), stat))
+    for k in want:
+        a = got[k].view(np.uint16) if got[k].dtype == np.float16 else got[k]
+        b = want[k].view(np.uint16) if want[k].dtype == np.float16 else want[k]
+        assert np.array_equal(a, b), k
+    # decode(pack(W)) on the GPU == oracle decode, exactly
+    Wd = ops.unpack(ops.pack(torch.from_numpy(W).to(cuda), stat)).cpu().numpy()
+    assert np.array_equal(Wd, O.decode_mxq(want))
+    assert (Wd[:, dead] == 0).all()
+
+
+@pytest.mark.parametrize("shape", [(8, 64), (64, 4096), (32, 11008)])
+def test_unpack_random_bits_exact(cuda, shape):
+    from mxq_b200 import ops
+    p = O.random_packed(*shape, seed=shape[1])
+    want = O.decode_mxq(p)
+    got = ops.unpack(packed_to_dev(p, cuda), torch.float32).cpu().numpy()
+    assert np.array_equal(got, want)
+    got16 = ops.unpack(packed_to_dev(p, cuda), torch.float16).cpu().numpy()
+    assert np.array_equal(got16, want.astype(np.float16))
+
+
+@pytest.mark.parametrize("OC,IC", [(64, 64), (256, 4096), (128, 11008), (4096, 4096), (512, 8192)])
+@pytest.mark.parametrize("B", [1, 2, 3, 8])
+def test_gemv_random_bits(cuda, OC, IC, B):
+    from mxq_b200 import ops
+    if OC == 4096 and B not in (1, 8):
+        pytest.skip("full-size case runs for B=1 and B=8")
+    p = O.random_packed(OC, IC, seed=OC + IC)
+    rng = np.random.default_rng(B)
+    x = rng.standard_normal((B, IC)).astype(np.float16)
+    ref = O.gemm_mxq_f32(x, p)
+    y = ops.gemv(torch.from_numpy(x).to(cuda), packed_to_dev(p, cuda)).cpu().numpy()
+    assert y.shape == (B, OC)
+    assert _rel_err(y, ref) <= TOL
+
+
+def test_gemv_packed_weights_end_to_end(cuda):
+    """weights -> mxq_pack -> mxq_gemv equals x @ decode(pack(W))^T and approximates x @ W^T."""
+    from mxq_b200 import ops
+    torch.manual_seed(0)
+    W = (torch.randn(1024, 4096, device=cuda) * 0.02).half()
+    x = torch.randn(1, 4096, device=cuda).half()
+    p = ops.pack(W)
+    y = ops.gemv(x, p).float()
+    ref = x.float() @ ops.unpack(p).T
+    assert float((y - ref).abs().max() / ref.abs().max()) <= TOL
+    dense = x.float() @ W.float().T
+    assert float((y - dense).norm() / dense.norm()) < 0.5      # 3-bit-average RTN noise
+
+
+@pytest.mark.parametrize("G", [64, 128])
+def test_awq_gemv(cuda, G):
+    from mxq_b200 import engine
+    rng = np.random.default_rng(G)
+    OC, IC, B = 128, 4096, 2
+    ng = IC // G
+    zw = -(-ng // 8)
+    zw = zw if G == 128 else -(-zw // 2) * 2
+    kernel = rng.integers(0, 2 ** 32, (OC, IC // 8), dtype=np.uint64).astype(np.uint32)
+    zeros = rng.integers(0, 2 ** 32, (OC, zw), dtype=np.uint64).astype(np.uint32)
+    scales = rng.uniform(0.001, 0.01, (OC, zw * 8)).astype(np.float16)
+    x = rng.standard_normal((B, IC)).astype(np.float16)
+    q = ((kernel[:, :, None] >> (4 * np.arange(8, dtype=np.uint32))) & 0xF).reshape(OC, IC).astype(np.float64)
+    g = np.arange(IC) // G
+    z = ((zeros[:, g // 8] >> (4 * (g % 8)).astype(np.uint32)) & 0xF).astype(np.float64)
+    Wd = scales.astype(np.float64)[:, g] * (q - z)
+    ref = x.astype(np.float64) @ Wd.T
+    y = engine.gemv_forward_cuda(torch.from_numpy(x).to(cuda), torch.from_numpy(kernel.view(np.int32)).to(cuda),
+                                 torch.from_numpy(scales).to(cuda), torch.from_numpy(zeros.view(np.int32)).to(cuda), G)
+    assert _rel_err(y.cpu().numpy(), ref) <= TOL

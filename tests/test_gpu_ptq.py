@@ -1,0 +1,130 @@
+"""GPU parity: calibration statistics + fused fasterquant vs the reference's golden vectors and the
+oracle.  Bar: fake-quant fp16 weights and integer codes bit-exact; dead-column mask exact; running
+statistics within 1e-5 relative (different fp32 summation order than torch.norm / X^T X)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mxq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fqt(golden_dir):
+    return np.load(os.path.join(golden_dir, "fasterquant.npz"))
+
+
+def _linear(W16: np.ndarray, dev):
+    N, K = W16.shape
+    layer = torch.nn.Linear(K, N, bias=False)
+    layer.weight.data = torch.from_numpy(W16.copy())
+    return layer.to(dev)
+
+
+def test_golden_mxqgpt(cuda, fqt):
+    from mxq_b200 import MXQGPT, WrappedGPT
+    for key in sorted({k.split("/")[0] for k in fqt.files}):
+        W, X, Wq = fqt[key + "/W"], fqt[key + "/X"], fqt[key + "/Wq"]
+        layer = _linear(W, cuda)
+        gpt, wr = MXQGPT(layer), WrappedGPT(layer)
+        assert (gpt.rows, gpt.columns, gpt.nsamples) == (W.shape[0], W.shape[1], 0)
+        Xd = torch.from_numpy(X).to(cuda)
+        for j in range(X.shape[0]):
+            gpt.add_batch(Xd[j], None)
+            wr.add_batch(Xd[j], None)
+            ref = fqt[key + "/scaler_row"][j]
+            got = wr.scaler_row.cpu().numpy()
+            assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max(), key
+        dH = gpt.diagH.cpu().numpy()
+        assert np.array_equal(dH == 0, fqt[key + "/diagH"] == 0), "dead-column mask"
+        assert np.abs(dH - fqt[key + "/diagH"]).max() <= 1e-5 * np.abs(dH).max()
+        wm = wr.metric().cpu().numpy()
+        assert np.abs(wm - fqt[key + "/wanda"]).max() <= 1e-5 * np.abs(wm).max()
+        gpt.fasterquant(percdamp=0.01, blocksize=16)
+        got = layer.weight.data.cpu().numpy()
+        assert got.dtype == np.float16
+        assert np.array_equal(got.view(np.uint16), Wq.view(np.uint16)), f"fasterquant {key}"
+        gpt.free()
+
+
+def test_golden_quantizer(cuda, golden_dir):
+    from mxq_b200 import Quantizer
+    Q = np.load(os.path.join(golden_dir, "quantizer.npz"))
+    for key in sorted({k.split("/")[0] for k in Q.files}):
+        bits = int(key[1])
+        x = torch.from_numpy(Q[key + "/x"]).to(cuda)
+        q = Quantizer()
+        q.configure(bits=bits, perchannel=True, sym=False, qq_scale_bits=4)
+        q.find_params(x, weight=True)
+        assert np.array_equal(q.quantize_dequantize(x).cpu().numpy(), Q[key + "/y"]), key
+        assert np.array_equal(q.quantize(x).cpu().numpy().astype(np.uint8), Q[key + "/codes"])
+        assert np.array_equal(q.scale.reshape(-1).cpu().numpy(), Q[key + "/scale"])
+        assert np.array_equal(q.zero.reshape(-1).cpu().numpy(), Q[key + "/zero"])
+
+
+@pytest.mark.parametrize("shape", [(256, 1024), (48, 11008), (16, 64)])
+def test_seeded_vs_oracle_with_codes(cuda, shape):
+    from mxq_b200 import ops
+    rng = np.random.default_rng(shape[1])
+    W = (rng.standard_normal(shape) * 0.02).astype(np.float16)
+    W[0, :16] = 0.25
+    X = rng.standard_normal((64, shape[1])).astype(np.float16)
+    X[:, [5, shape[1] - 1]] = 0
+    X[:, 9] *= 20
+    want, aux = O.fasterquant(W, O.dead_columns(X), return_aux=True)
+    stat = ops.colsumsq(torch.from_numpy(X).to(cuda), add_scale=2.0 / 1)
+    ref = O.colsumsq(X) * 2
+    assert np.abs(stat.cpu().numpy() - ref).max() <= 1e-5 * ref.max()
+    Wq, codes = ops.ptq_quant(torch.from_numpy(W).to(cuda), stat, return_codes=True)
+    assert np.array_equal(codes.cpu().numpy(), aux["codes"]), "integer codes"
+    assert np.array_equal(Wq.cpu().numpy().view(np.uint16), want.view(np.uint16))
+    # no statistics -> nothing is dead
+    want2 = O.fasterquant(W, None)
+    got2 = ops.ptq_quant(torch.from_numpy(W).to(cuda), None)
+    assert np.array_equal(got2.cpu().numpy().view(np.uint16), want2.view(np.uint16))
+
+
+@pytest.mark.parametrize("shape", [(4096, 4096), (4096, 11008), (11008, 4096)])
+def test_full_size_properties(cuda, shape):
+    """Llama-2-7B shapes: oracle on sampled 16-row tiles, tile independence, idempotent dead columns."""
+    from mxq_b200 import ops
+    torch.manual_seed(shape[1])
+    W = (torch.randn(*shape, device=cuda) * 0.02).half()
+    stat = torch.ones(shape[1], device=cuda)
+    stat[7] = 0
+    Wq = ops.ptq_quant(W, stat)
+    assert int((Wq[:, 7] != 0).sum()) == 0
+    tiles = np.random.default_rng(0).choice(shape[0] // 16, 4, replace=False)
+    dead = np.zeros(shape[1], bool)
+    dead[7] = True
+    for t in tiles:
+        sl = slice(16 * t, 16 * t + 16)
+        want = O.fasterquant(W[sl].cpu().numpy(), dead)
+        assert np.array_equal(Wq[sl].cpu().numpy().view(np.uint16), want.view(np.uint16))
+    # 16-row tiles are independent: quantizing a slab alone reproduces the same rows
+    assert torch.equal(ops.ptq_quant(W[160:320].contiguous(), stat), Wq[160:320])
+    # at most 4 distinct values per (row, 2-bit group) and 16 per row pool
+    g = Wq[:64].view(64, -1, 4, 16)[:, :, :3].float().cpu().numpy()
+    assert max(len(np.unique(r)) for r in g.reshape(-1, 16)[:2000]) <= 4
+    pool = Wq[:64].view(64, -1, 4, 16)[:, :, 3].reshape(64, -1).float().cpu().numpy()
+    assert max(len(np.unique(r)) for r in pool) <= 16
+
+
+def test_colsumsq_shapes_and_dtypes(cuda):
+    from mxq_b200 import ops
+    rng = np.random.default_rng(0)
+    for dt, tol in ((torch.float16, 1e-5), (torch.bfloat16, 1e-5), (torch.float32, 1e-5)):
+        for shape in ((3000, 4096), (777, 11008), (1, 64), (130, 8)):
+            X = torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).to(dt)
+            got = ops.colsumsq(X.to(cuda)).cpu().numpy()
+            ref = O.colsumsq(X.float().numpy())
+            assert np.abs(got - ref).max() <= tol * max(ref.max(), 1e-30), (dt, shape)
+    # running update: out = prev*out + add*sumsq
+    X = torch.randn(100, 256, device=cuda).half()
+    a = ops.colsumsq(X)
+    b = a.clone()
+    ops.colsumsq(X, out=b, prev_scale=0.5, add_scale=0.25)
+    assert torch.allclose(b, 0.75 * a, rtol=1e-6)
