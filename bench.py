@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py -- MXQ quantization hot path on B200 (contract in the task statement / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ptq] [--impl ours|reference]
+
+Default workload (BASELINE.json configs[1]): the full mxq quantization pass over a random-init
+Llama-2-7B (32 decoder layers x 7 linears) with synthetic 128 x 2048-token calibration
+activations, decoder layers sharded `layer % world` over the GPUs, no data-path collective.
+One step = one pass over all layers: per layer 4 activation statistics (what MXQGPT.add_batch is
+used for) + fasterquant + pack of the 7 linears.  `value` = algorithmic GB/s of
+the whole job with inputs resident in HBM; `e2e` = the same with HOST (pinned) calibration
+tensors and weights copied in and the quantized + packed weights copied out inside the timed
+region.  `components` carries the other BASELINE configs measured on rank 0 in the same run
+(fake-quant fwd/bwd GB/s, decode GEMV GB/s, prefill dequant-GEMM TFLOP/s).
+
+Under torchrun (N > 1) every rank runs its shard; rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HIDDEN, INTER, LAYERS = 4096, 11008, 32       # Llama-2-7B (configuration_llama.py:85-88)
+NSAMPLES, SEQLEN = 128, 2048                   # main.py:26,33 ; prune.py:329
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (NVML), runs during the timed region
+# ---------------------------------------------------------------------------------------------
+class Clocks:
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80, "sync_boost": 0x10,
+                 "applications_clocks_setting": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the CPU oracle port on a bounded sample of the same workload
+# ---------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_baseline as cb
+    tokens = 8192
+    cores = os.cpu_count() or 1
+    times, nbytes, desc = [], 0, ""
+    for i in range(args.warmup + args.steps):
+        dt, nbytes, desc = cb.ptq_layer_sample(HIDDEN, INTER, tokens, threads=cores, seed=i)
+        if i >= args.warmup:
+            times.append(dt)
+    tot = sum(times)
+    val = nbytes * len(times) / tot / 1e9
+    line = {
+        "impl": "reference", "metric": "mxq_quant_pass_hbm_GBps", "value": val, "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {"workload": "mxq PTQ pass (statistics + fasterquant + pack), Llama-2-7B shapes: 32 layers x 7 linears, "
+                        "synthetic 128x2048-token calibration per distinct linear input",
+            "hidden": HIDDEN, "intermediate": INTER, "layers": LAYERS, "nsamples": NSAMPLES, "seqlen": SEQLEN,
+            "sharding": f"layer % {n} (no data-path collective)",
+            "l2": "inputs larger than L2: 12.2 GB of calibration activations + 0.4 GB of weights stream per layer"}
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ptq", choices=["ptq"])
+    ap.add_argument("--no-components", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--layers", type=int, default=LAYERS, help="(debug) fewer layers; default is the named config")
+    ap.add_argument("--nsamples", type=int, default=NSAMPLES, help="(debug) fewer calibration samples")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        print(f"note: warmup {args.warmup} < 3 breaks the timing rules", file=sys.stderr)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from mxq_b200 import _lib
+    _lib.lib()                              # fail loudly if the CUDA library is missing
+    from mxq_b200 import prune
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    tokens = args.nsamples * SEQLEN
+    my_layers = [l for l in range(args.layers) if l % world == rank]
+    ptq = prune.LlamaLayerPTQ(HIDDEN, INTER, dev, tokens)
+    lin = prune.llama_linears(HIDDEN, INTER)
+
+    # ---- synthetic data, resident in HBM --------------------------------------------------
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000)
+    calib = {}
+    for key, d in (("attn_in", HIDDEN), ("o_in", HIDDEN), ("mlp_in", HIDDEN), ("down_in", INTER)):
+        X = torch.randn((tokens, d), generator=g, device=dev, dtype=torch.float16)
+        X[:, 7] = 0                          # dead column (mxqgpt.py:401)
+        X[:, 100:108] *= 20                  # LLM-like outlier channels
+        calib[key] = X
+    weights = {}
+    for l in my_layers:
+        g.manual_seed(l)
+        weights[l] = {name: (torch.randn((oc, ic), generator=g, device=dev, dtype=torch.float32) * 0.02).half()
+                      for name, (oc, ic, _) in lin.items()}
+    stat_b, quant_b = prune.algorithmic_bytes_per_layer(HIDDEN, INTER, tokens)
+    job_bytes = args.layers * (stat_b + quant_b)
+
+    # ---- dominant kernel (column sum-of-squares) timed with events on the launching stream --
+    n_stat_calls = 4 * len(my_layers) * args.steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_stat_calls)]
+    ev_bytes = []
+    cursor = {"i": 0, "on": False}
+
+    def on_stat(key, X2, before):
+        if not cursor["on"]:
+            return
+        a, b = ev[cursor["i"]]
+        if before:
+            a.record()
+        else:
+            b.record()
+            ev_bytes.append(X2.numel() * X2.element_size())
+            cursor["i"] += 1
+
+    def step():
+        for l in my_layers:
+            ptq.run(weights[l], calib, args.nsamples, on_stat=on_stat)
+
+    for _ in range(args.warmup):
+        step()
+    clocks = Clocks(local)
+    barrier()
+    clocks.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cursor["on"] = True
+    t0.record()
+    for _ in range(args.steps):
+        step()
+    t1.record()
+    barrier()
+    cursor["on"] = False
+    clk = clocks.stop()
+    ms_total = max_over_ranks(t0.elapsed_time(t1))
+    ms_step = ms_total / args.steps
+    value = job_bytes / (ms_step * 1e-3) / 1e9
+
+    pk = peaks()
+    stat_ms = [a.elapsed_time(b) for a, b in ev[:cursor["i"]]]
+    dom_bytes = sum(ev_bytes) / max(len(ev_bytes), 1)
+    dom_ms = sum(stat_ms) / max(len(stat_ms), 1)
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "colsumsq_partial_kernel<__half> (+ its 1-block-wide finalize, same event pair)",
+                "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
+                "peak_source": pk["src"] + " (burst copy bandwidth, MEASURED_PEAKS.json)" if pk["src"] == "measured" else "fallback 6.65 TB/s",
+                "traffic": None, "bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
+                "share_of_step": sum(stat_ms) / max(args.steps, 1) / ms_step if ms_step > 0 else None}
+
+    # ---- end to end: host (pinned) inputs, device->host results, copies inside the timing ---
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e = run_e2e(torch, dev, ptq, lin, calib, weights, my_layers, args, job_bytes, barrier, max_over_ranks)
+        except Exception as e:  # report, never fake
+            e2e = {"value": None, "unit": "GB/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                   "error": repr(e)[:300]}
+
+    # ---- other BASELINE configs, rank 0 only -------------------------------------------------
+    components = None
+    cpu = None
+    if rank == 0:
+        if not args.no_components:
+            del calib
+            torch.cuda.empty_cache()
+            components = run_components(torch, dev, pk)
+        if world == 1:
+            from oracle import cpu_baseline as cb
+            cores = os.cpu_count() or 1
+            dt, nb, desc = cb.ptq_layer_sample(HIDDEN, INTER, 8192, threads=cores)
+            cpu = {"value": nb / dt / 1e9, "unit": "GB/s", "cores": cores, "kind": "port", "sample": desc,
+                   "seconds": dt}
+
+    if rank == 0:
+        line = {
+            "metric": "mxq_quant_pass_hbm_GBps", "value": value, "unit": "GB/s", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world) if (args.layers == LAYERS and args.nsamples == NSAMPLES) else
+            dict(workload_config(world), layers=args.layers, nsamples=args.nsamples, note="REDUCED debug config"),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk,
+            "gpu_launches": prune.LlamaLayerPTQ.LAUNCHES_PER_LAYER * args.layers * args.steps,
+            "job_bytes_per_step": job_bytes, "layers_per_s": args.layers / (ms_step * 1e-3),
+            "components": components,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(torch, dev, ptq, lin, calib, weights, my_layers, args, job_bytes, barrier, max_over_ranks):
+    """Same pass through the public API with every input in pinned host memory."""
+    h_calib = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in calib.items()}
+    for k in calib:
+        h_calib[k].copy_(calib[k])
+    h_w = {l: {n: torch.empty(w.shape, dtype=w.dtype, pin_memory=True).copy_(w) for n, w in weights[l].items()}
+           for l in my_layers}
+    d_calib = calib                                   # the resident device tensors double as staging buffers
+    d_w = {n: torch.empty((oc, ic), dtype=torch.float16, device=dev) for n, (oc, ic, _) in lin.items()}
+    h_out = {}
+    for n, (oc, ic, _) in lin.items():
+        job = ptq.jobs[(oc, ic)]
+        h_out[n] = (torch.empty((oc, ic), dtype=torch.float16, pin_memory=True),
+                    {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in job.packed.items()})
+    h2d = sum(v.numel() * v.element_size() for v in h_calib.values()) + \
+        sum(w.numel() * 2 for w in h_w[my_layers[0]].values()) if my_layers else 0
+    d2h = sum(t.numel() * 2 + sum(v.numel() * v.element_size() for v in p.values()) for t, p in h_out.values())
+
+    def sink(name, Wq, packed):
+        ho, hp = h_out[name]
+        ho.copy_(Wq, non_blocking=True)
+        for k in packed:
+            hp[k].copy_(packed[k], non_blocking=True)
+
+    def step():
+        for l in my_layers:
+            for k in d_calib:
+                d_calib[k].copy_(h_calib[k], non_blocking=True)
+            ptq.statistics(d_calib, args.nsamples)
+            for n in d_w:
+                d_w[n].copy_(h_w[l][n], non_blocking=True)
+            ptq.quantize(d_w, sink)
+        torch.cuda.current_stream().synchronize()   # results are on the host
+
+    e_steps = max(1, min(args.steps, 2))
+    step()                                            # warm-up (page-locked paths, first touches)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    t0.record()
+    for _ in range(e_steps):
+        step()
+    t1.record()
+    barrier()
+    wall = time.perf_counter() - w0
+    ms = max_over_ranks(t0.elapsed_time(t1)) / e_steps
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return {"value": job_bytes / (ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms, "steps": e_steps,
+            "h2d_bytes_per_step": h2d * len(my_layers) * 1 if my_layers else 0,
+            "d2h_bytes_per_step": d2h * len(my_layers), "ranks_reported": "rank 0 bytes; every rank moves the same per layer",
+            "wall_s": wall, "api": "mxq_b200.prune.LlamaLayerPTQ.statistics/quantize with pinned host tensors"}
+
+
+def run_components(torch, dev, pk):
+    """The other BASELINE configs on one GPU: short, device-timed, inputs rotated beyond L2."""
+    from mxq_b200 import ops
+    out = {}
+
+    def timeit(fn, iters, warm=3):
+        for _ in range(warm):
+            fn(0)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(iters):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    # config 0: fake-quant fwd + STE bwd on a Llama-2-7B q_proj, fp32 and bf16; 6 rotating sets
+    for dt, name in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+        nset = 6
+        xs = [(torch.randn(4096, 4096, device=dev) * 0.02).to(dt) for _ in range(nset)]
+        gs = [torch.randn(4096, 4096, device=dev).to(dt) for _ in range(nset)]
+        esz = xs[0].element_size()
+        outs = [torch.empty_like(xs[0]) for _ in range(nset)]
+        lib = ops.L.lib()
+
+        def fwd(i):
+            k = i % nset
+            ops.L.check(lib.mxq_fakequant_fwd(xs[k].data_ptr(), outs[k].data_ptr(), None, 4096, 4096,
+                                              ops.L.dtype_enum(xs[k]), 16, 2, None, ops.L.stream()), "fq")
+
+        def bwd(i):
+            k = i % nset
+            ops.L.check(lib.mxq_ste_bwd(gs[k].data_ptr(), xs[k].data_ptr(), outs[k].data_ptr(), 4096 * 4096,
+                                        ops.L.dtype_enum(xs[k]), -2.0, 2.0, ops.L.stream()), "ste")
+        mf, mb = timeit(fwd, 30), timeit(bwd, 30)
+        nb = 4096 * 4096 * esz
+        out[f"fakequant_fwd_{name}"] = {"ms": mf, "GBps": 2 * nb / mf / 1e6, "frac_hbm": 2 * nb / mf / 1e6 / pk["hbm"]}
+        out[f"ste_bwd_{name}"] = {"ms": mb, "GBps": 3 * nb / mb / 1e6, "frac_hbm": 3 * nb / mb / 1e6 / pk["hbm"]}
+        del xs, gs, outs
+    # config 2: decode GEMV over the 7 linears of 8 layers of packed random-bit weights (> L2), CUDA graph
+    shapes = [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)]
+    nl = 8
+    packs = []
+    for _ in range(nl):
+        layer = []
+        for oc, ic in shapes:
+            p = {}
+            for k, (s, d) in ops.packed_shapes(oc, ic).items():
+                if d == torch.float16:
+                    p[k] = (torch.rand(s, device=dev) * 0.009 + 0.001).half()
+                else:
+                    p[k] = torch.randint(-2 ** 31, 2 ** 31 - 1, s, device=dev, dtype=torch.int64).to(torch.int32)
+            layer.append(p)
+        packs.append(layer)
+    xin = {4096: torch.randn(1, 4096, device=dev).half(), 11008: torch.randn(1, 11008, device=dev).half()}
+    yout = {4096: torch.empty(1, 4096, device=dev, dtype=torch.float16),
+            11008: torch.empty(1, 11008, device=dev, dtype=torch.float16)}
+    from mxq_b200.prune import packed_nbytes
+    gbytes = nl * sum(packed_nbytes(oc, ic) + 2 * (oc + ic) for oc, ic in shapes)
+
+    def gemv_all():
+        for layer in packs:
+            for (oc, ic), p in zip(shapes, layer):
+                ops.gemv(xin[ic], p, out=yout[oc], validate=False)
+    try:
+        gemv_all()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            gemv_all()
+        ms = timeit(lambda i: graph.replay(), 20)
+        out["gemv_decode_b1"] = {"ms_per_8_layers": ms, "GBps": gbytes / ms / 1e6, "frac_hbm": gbytes / ms / 1e6 / pk["hbm"],
+                                 "launches": nl * len(shapes), "note": "CUDA graph of 56 GEMVs, 0.6 GB of packed weights"}
+    except Exception as e:
+        out["gemv_decode_b1"] = {"error": repr(e)[:200]}
+    # config 2: prefill dequant-GEMM, M = 2048
+    try:
+        M = 2048
+        res = {}
+        for (oc, ic), p in zip(shapes[3:6:2] + shapes[6:], (packs[0][3], packs[0][5], packs[0][6])):
+            x = torch.randn(M, ic, device=dev).half()
+            y = torch.empty(M, oc, device=dev, dtype=torch.float16)
+            ws = torch.zeros(4096, dtype=torch.uint8, device=dev)
+            ms = timeit(lambda i: ops.gemm(x, p, out=y, workspace=ws, validate=False), 10)
+            tf = 2.0 * M * oc * ic / ms / 1e9
+            res[f"{oc}x{ic}"] = {"ms": ms, "TFLOPs": tf, "frac_tensor_burst": tf / pk["tf_burst"]}
+        out["gemm_prefill_m2048"] = res
+    except Exception as e:
+        out["gemm_prefill_m2048"] = {"error": repr(e)[:200]}
+    return out
+
+
+if __name__ == "__main__":
+    main()

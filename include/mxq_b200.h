@@ -145,6 +145,12 @@ MXQ_API size_t mxq_gemm_workspace_bytes(int64_t M, int64_t IC, int64_t OC);
 MXQ_API int mxq_gemm(const void* x, mxq_packed_t w, void* y, int64_t M, int64_t IC, int64_t OC,
              void* workspace, size_t workspace_bytes, void* stream);
 
+/* Diagnostic: the same tcgen05/TMA pipeline with a dense fp16 B operand W[OC, IC] loaded by TMA
+ * instead of dequantized in registers (y = x @ W^T).  Separates UMMA-descriptor errors from
+ * dequant/swizzle errors in tests; not part of the reference surface. */
+MXQ_API int mxq_gemm_dense(const void* x, const void* W, void* y, int64_t M, int64_t IC, int64_t OC,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

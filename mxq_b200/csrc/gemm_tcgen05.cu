@@ -1,10 +1,416 @@
-// Prefill dequant-GEMM on tcgen05/TMEM -- placeholder until the kernel lands (returns
-// MXQ_E_UNSUPPORTED so callers fail loudly).
+// Prefill dequant-GEMM for the packed mixed 2/4-bit layout on tcgen05 / TMEM / TMA (sm_100a).
+//
+//   y[m, oc] = sum_k x[m, k] * dequant(W)[oc, k]       x fp16 [M, IC], y fp16 [M, OC]
+//
+// The reference has no prefill kernel for the mixed layout (its AWQ mma.sync GEMM,
+// gemm_cuda_gen.cu:424-478, is neither built nor exported); decode formula as in
+// gemv_mxq_cuda.cu:131-136,152-153,178-179,191-192.
+//
+// CTA tile: 256 tokens x 256 weight rows, K block 64 (= one 64-column block of the packed
+// layout).  TMEM: two 128-lane x 256-column fp32 accumulators (all 512 columns).
+// Warp roles (320 threads):
+//   warp 0      : TMA producer -- activations [256 x 64] fp16 per stage, 128B-swizzled, mbarrier tx
+//   warp 1      : TMEM alloc + single-thread tcgen05.mma issue (2 accumulators x 4 UMMA_K per
+//                 K block), tcgen05.commit frees the stage / publishes the accumulators
+//   warps 2..9  : dequant producers -- thread = weight row; per K block: one 128-bit load of 48
+//                 two-bit + 8 four-bit codes, one 32-bit load of 8 four-bit codes, metadata;
+//                 LOP3 -> {1024+q} fp16 pairs, HSUB2 (1024+z), HMUL2 scale, eight 128-bit
+//                 st.shared into the canonical K-major SWIZZLE_128B UMMA layout; next K block's
+//                 packed words are prefetched into registers.  Afterwards the same warps run
+//                 the epilogue: tcgen05.ld 32x32b.x32 -> fp16 -> 128-bit global stores.
+// The dequantized operand never touches HBM: weights cost 0.3756 B each per M tile.
+#include <cuda.h>
+
 #include "common.cuh"
+
+namespace mxq {
+namespace gemm {
+
+constexpr int BM = 256;       // tokens per CTA (two UMMA M=128 halves)
+constexpr int BN = 256;       // weight rows per CTA (UMMA N)
+constexpr int BK = 64;        // K per stage = one packed block
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 3;
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 32 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
+constexpr int NUM_DEQ_WARPS = 8;
+constexpr int THREADS = 32 * (2 + NUM_DEQ_WARPS);
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle, 8-row atoms 1024 B apart (SBO); LBO unused for swizzled K-major.
+// Field layout: cute/arch/mma_sm100_desc.hpp UMMA::SmemDescriptor (version = 1, layout_type 2).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address  [0,14)
+  d |= (uint64_t)0 << 16;                               // leading byte offset [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset  [32,46)
+  d |= (uint64_t)1 << 46;                               // version [46,48) = 1 on sm_100
+  d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
+  return d;
+}
+// UMMA::InstrDescriptor: c=F32 (bit 4), a=b=F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t mask, uint32_t orv) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(orv));
+  return d;
+}
+__device__ __forceinline__ uint32_t hsub2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t hmul2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ uint32_t h2_bcast(float v) {
+  const __half2 h = __float2half2_rn(v);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// 16 two-bit codes of one word -> 16 fp16 weights in column order (two 16-byte chunks).
+// (w >> 2j) & 0x00030003 yields codes j (low half) and j+8 (high half); PRMT re-pairs
+// consecutive columns.
+__device__ __forceinline__ void dequant_2b(uint32_t w, uint32_t zmagic, uint32_t scale2, uint4& c0, uint4& c1) {
+  uint32_t h[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    h[j] = hmul2(hsub2(lop3_and_or(w >> (2 * j), 0x00030003u, 0x64006400u), zmagic), scale2);
+  // h[j] = {col j, col j+8}.  cols (2i, 2i+1) = low halves of h[2i], h[2i+1]; cols (8+2i, 9+2i) = high halves
+  c0 = make_uint4(prmt(h[0], h[1], 0x5410), prmt(h[2], h[3], 0x5410), prmt(h[4], h[5], 0x5410), prmt(h[6], h[7], 0x5410));
+  c1 = make_uint4(prmt(h[0], h[1], 0x7632), prmt(h[2], h[3], 0x7632), prmt(h[4], h[5], 0x7632), prmt(h[6], h[7], 0x7632));
+}
+// 8 four-bit codes of one word -> 8 fp16 weights (one 16-byte chunk); (w >> 4j) & 0x000F000F = nibbles j, j+4
+__device__ __forceinline__ uint4 dequant_4b(uint32_t w, uint32_t zmagic, uint32_t scale2) {
+  uint32_t h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    h[j] = hmul2(hsub2(lop3_and_or(w >> (4 * j), 0x000F000Fu, 0x64006400u), zmagic), scale2);
+  // h[j] = {col j, col j+4}: cols (0,1)=lo(h0,h1) (2,3)=lo(h2,h3) (4,5)=hi(h0,h1) (6,7)=hi(h2,h3)
+  return make_uint4(prmt(h[0], h[1], 0x5410), prmt(h[2], h[3], 0x5410), prmt(h[0], h[1], 0x7632), prmt(h[2], h[3], 0x7632));
+}
+
+struct Params {
+  mxq_packed_t w;
+  const __half* wdense;   // dense-B debug path only
+  __half* y;
+  int M, IC, OC;
+};
+
+template <bool kDenseB>
+__global__ void __launch_bounds__(THREADS, 1) gemm_mxq_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                              const __grid_constant__ CUtensorMap tmap_w,
+                                                              const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint64_t* full_a = bars;                 // [STAGES]
+  uint64_t* full_b = bars + STAGES;        // [STAGES]
+  uint64_t* empty = bars + 2 * STAGES;     // [STAGES]
+  uint64_t* tmem_full = bars + 3 * STAGES; // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int num_kb = p.IC / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    if (kDenseB) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_a[s], 1);
+      mbar_init(&full_b[s], kDenseB ? 1 : NUM_DEQ_WARPS);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (activations; dense-B debug path also loads the weights) =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_a[s], A_STAGE_BYTES);
+        tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_x, kb * BK, m0, &full_a[s]);
+        if (kDenseB) {
+          mbar_arrive_expect_tx(&full_b[s], B_STAGE_BYTES);
+          tma_load_2d(smem_b + s * B_STAGE_BYTES, &tmap_w, kb * BK, n0, &full_b[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_a[s], ph);
+        mbar_wait(&full_b[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_a + s * A_STAGE_BYTES);
+        const uint32_t b_addr = smem_u32(smem_b + s * B_STAGE_BYTES);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ad = make_smem_desc(a_addr + h * (128 * BK * 2) + k * (UMMA_K * 2));
+            const uint64_t bd = make_smem_desc(b_addr + k * (UMMA_K * 2));
+            umma_f16(tmem_base + h * BN, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[s]);        // frees the stage once these MMAs have read it
+      }
+      umma_commit(tmem_full);          // accumulators complete
+    }
+  } else {
+    // ===== dequant producers (thread = weight row), then epilogue =====
+    const int dw = warp - 2;                      // 0..7
+    const int row_local = dw * 32 + lane;         // 0..255
+    const int oc = n0 + row_local;
+    if (!kDenseB) {
+      const bool row_ok = oc < p.OC;
+      const int ocs = row_ok ? oc : 0;
+      const int nblk = num_kb;
+      const int nchunk = (nblk + 63) >> 6;
+      const uint4* wrow = reinterpret_cast<const uint4*>(p.w.weight + (size_t)ocs * nblk * 4);
+      const int32_t* wlrow = p.w.weight_last + (size_t)ocs * nblk;
+      const uint16_t* zsrow = reinterpret_cast<const uint16_t*>(p.w.zeros_and_scales) + (size_t)ocs * 64 * nchunk;
+      const uint8_t* z2row = reinterpret_cast<const uint8_t*>(p.w.zeros_2nd) + (size_t)(ocs >> 2) * 128 * nchunk;
+      const __half* s2row = reinterpret_cast<const __half*>(p.w.scales_2nd) + (size_t)(ocs >> 2) * nblk * 3;
+      const float s4 = __half2float(reinterpret_cast<const __half*>(p.w.scales_4b)[ocs]);
+      const uint32_t z4 = ((uint32_t)p.w.zeros_4b[ocs >> 3] >> (4 * (ocs & 7))) & 0xF;
+      const uint32_t z4magic = (0x6400u | z4) * 0x00010001u;
+      const uint32_t s4h2 = h2_bcast(row_ok ? s4 : 0.f);
+
+      auto meta_idx = [&](int kb, int& hw_idx, int& b_idx) {
+        const int chunk = kb >> 6, bp = kb & 63;
+        const int word = chunk * 32 + (bp & 31), ph = bp >> 5;
+        hw_idx = word * 2 + ph;
+        b_idx = word * 4 + ph;
+      };
+      // register prefetch of K block 0
+      uint4 wq = __ldg(wrow);
+      uint32_t wl = (uint32_t)__ldg(wlrow);
+      int hi, bi;
+      meta_idx(0, hi, bi);
+      uint32_t zs = __ldg(zsrow + hi);
+      uint32_t z2 = __ldg(z2row + bi);
+      float s2v[3] = {__half2float(__ldg(s2row)), __half2float(__ldg(s2row + 1)), __half2float(__ldg(s2row + 2))};
+
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        // current block's operands
+        const uint4 cwq = wq;
+        const uint32_t cwl = wl, czs = zs, cz2 = z2;
+        const float cs2[3] = {s2v[0], s2v[1], s2v[2]};
+        if (kb + 1 < num_kb) {   // prefetch next block
+          wq = __ldg(wrow + kb + 1);
+          wl = (uint32_t)__ldg(wlrow + kb + 1);
+          meta_idx(kb + 1, hi, bi);
+          zs = __ldg(zsrow + hi);
+          z2 = __ldg(z2row + bi);
+          const __half* sp = s2row + (size_t)(kb + 1) * 3;
+          s2v[0] = __half2float(__ldg(sp)); s2v[1] = __half2float(__ldg(sp + 1)); s2v[2] = __half2float(__ldg(sp + 2));
+        }
+        uint4 ch[8];
+        const uint32_t ws[3] = {cwq.x, cwq.y, cwq.z};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const uint32_t z1 = (czs >> (2 * k)) & 3;
+          const float c = (float)((czs >> (8 + 2 * k)) & 3);
+          const float zz = (float)((cz2 >> (2 * k)) & 3);
+          const float scale = row_ok ? cs2[k] * (c - zz) : 0.f;
+          dequant_2b(ws[k], (0x6400u | z1) * 0x00010001u, h2_bcast(scale), ch[2 * k], ch[2 * k + 1]);
+        }
+        ch[6] = dequant_4b(cwq.w, z4magic, s4h2);
+        ch[7] = dequant_4b(cwl, z4magic, s4h2);
+
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* brow = smem_b + s * B_STAGE_BYTES + row_local * 128;
+        const int sw = row_local & 7;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(brow + ((c ^ sw) << 4)) = ch[c];
+        fence_proxy_async();           // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_b[s]);
+      }
+    }
+    // ===== epilogue: TMEM -> registers -> fp16 -> global =====
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int half = dw >> 2;                 // accumulator (token half)
+    const int quad = warp & 3;                // TMEM lane quarter this warp may access
+    const int token = m0 + half * 128 + quad * 32 + lane;
+    __half* yrow = p.y + (size_t)token * p.OC + n0;
+#pragma unroll 1
+    for (int cb = 0; cb < BN / 32; ++cb) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + half * BN + cb * 32, v);
+      tmem_ld_wait();
+      if (token < p.M) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int col = n0 + cb * 32 + q * 8;
+          if (col + 8 <= p.OC) {
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              oh[e] = __floats2half2_rn(__uint_as_float(v[q * 8 + 2 * e]), __uint_as_float(v[q * 8 + 2 * e + 1]));
+            *reinterpret_cast<uint4*>(yrow + cb * 32 + q * 8) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  return reinterpret_cast<EncodeTiledFn>(fn);
+}
+
+// fp16 [rows, cols] row-major, box = [box_rows x 64 cols], 128B swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return MXQ_E_UNSUPPORTED;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MXQ_OK : MXQ_E_UNSUPPORTED;
+}
+
+template <bool kDenseB>
+static int launch(const void* x, const Params& p, cudaStream_t st) {
+  CUtensorMap mx, mw;
+  int rc = make_map(&mx, x, p.M, p.IC, BM);
+  if (rc) return rc;
+  if (kDenseB) {
+    rc = make_map(&mw, p.wdense, p.OC, p.IC, BN);
+    if (rc) return rc;
+  } else {
+    mw = mx;
+  }
+  auto k = gemm_mxq_kernel<kDenseB>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((unsigned)ceil_div(p.OC, BN), (unsigned)ceil_div(p.M, BM));
+  k<<<grid, THREADS, SMEM_BYTES, st>>>(mx, mw, p);
+  MXQ_LAUNCH_RESULT();
+}
+
+}  // namespace gemm
+}  // namespace mxq
+
+using namespace mxq;
 
 extern "C" size_t mxq_gemm_workspace_bytes(int64_t, int64_t, int64_t) { return 256; }
 
-extern "C" int mxq_gemm(const void*, mxq_packed_t, void*, int64_t, int64_t, int64_t, void*, size_t,
-                        void*) {
-  return MXQ_E_UNSUPPORTED;
+extern "C" int mxq_gemm(const void* x, mxq_packed_t w, void* y, int64_t M, int64_t IC, int64_t OC,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  if (M < 0 || IC < 0 || OC < 0) return MXQ_E_SHAPE;
+  if (M == 0 || OC == 0) return MXQ_OK;
+  MXQ_CHECK_PTR(x);
+  MXQ_CHECK_PTR(y);
+  MXQ_CHECK_PTR(w.weight);
+  if (!w.weight_last || !w.zeros_and_scales || !w.zeros_2nd || !w.scales_2nd || !w.scales_4b || !w.zeros_4b)
+    return MXQ_E_NULL;
+  if (IC % 64 || IC == 0 || OC % 8 || M > INT32_MAX || OC > INT32_MAX || IC > (1 << 24)) return MXQ_E_SHAPE;
+  gemm::Params p{w, nullptr, (__half*)y, (int)M, (int)IC, (int)OC};
+  return gemm::launch<false>(x, p, as_stream(stream));
+}
+
+extern "C" int mxq_gemm_dense(const void* x, const void* W, void* y, int64_t M, int64_t IC, int64_t OC,
+                              void* stream) {
+  if (M < 0 || IC < 0 || OC < 0) return MXQ_E_SHAPE;
+  if (M == 0 || OC == 0) return MXQ_OK;
+  MXQ_CHECK_PTR(x);
+  MXQ_CHECK_PTR(W);
+  MXQ_CHECK_PTR(y);
+  if (IC % 64 || IC == 0 || OC % 8) return MXQ_E_SHAPE;
+  mxq_packed_t none{};
+  gemm::Params p{none, (const __half*)W, (__half*)y, (int)M, (int)IC, (int)OC};
+  return gemm::launch<true>(x, p, as_stream(stream));
 }

@@ -219,6 +219,18 @@ def gemm(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, workspace=No
     return out
 
 
+def gemm_dense(x: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
+    """Diagnostic: y = x @ W^T with dense fp16 W through the same tcgen05 pipeline as `gemm`."""
+    L.require_cuda(x, W)
+    x, W = x.contiguous(), W.contiguous()
+    M, IC = x.shape
+    OC = W.shape[0]
+    out = torch.empty((M, OC), dtype=torch.float16, device=x.device)
+    rc = L.lib().mxq_gemm_dense(L.ptr(x), L.ptr(W), L.ptr(out), M, IC, OC, L.stream())
+    L.check(rc, "mxq_gemm_dense")
+    return out
+
+
 def awq_gemv(x: torch.Tensor, kernel: torch.Tensor, scales: torch.Tensor, zeros: torch.Tensor,
              group_size: int) -> torch.Tensor:
     """AWQ uniform 4-bit GEMV (gemv_cuda.cu:346-399)."""

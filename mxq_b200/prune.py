@@ -107,10 +107,10 @@ def nas_quant(args, model, tokenizer, dev, dataloader=None):
 
 
 class LinearQuantJob:
-    """Pre-allocated buffers for quantizing linears of one shape [OC, IC] repeatedly (no
-    allocation inside the timed region)."""
+    """Pre-allocated output buffers for quantizing linears of one shape [OC, IC] repeatedly (no
+    allocation inside a timed region)."""
 
-    def __init__(self, OC: int, IC: int, device, tokens: int = 0):
+    def __init__(self, OC: int, IC: int, device):
         self.OC, self.IC = OC, IC
         self.Wq = torch.empty((OC, IC), dtype=torch.float16, device=device)
         self.packed = ops.alloc_packed(OC, IC, device)
@@ -118,25 +118,77 @@ class LinearQuantJob:
         n = max(lib.mxq_ptq_workspace_bytes(OC, IC), lib.mxq_pack_workspace_bytes(OC, IC))
         self.ws = torch.empty(int(n), dtype=torch.uint8, device=device)
 
-
-def calib_stat(X: torch.Tensor, nsamples: int, out=None, workspace=None) -> torch.Tensor:
-    """diag(H) of MXQGPT after all samples: (2/nsamples) * sum_tokens X^2 (mxqgpt.py:377-383)."""
-    return ops.colsumsq(X, out=None, add_scale=2.0 / nsamples, workspace=workspace) if out is None \
-        else _colsumsq_into(X, nsamples, out, workspace)
-
-
-def _colsumsq_into(X, nsamples, out, workspace):
-    X2 = X.reshape(-1, X.shape[-1])
-    lib = ops.L.lib()
-    rc = lib.mxq_colsumsq(ops.L.ptr(X2), X2.shape[0], X2.shape[1], ops.L.dtype_enum(X2),
-                          ops.L.ptr(out), 0.0, 2.0 / nsamples, 0, ops.L.ptr(workspace),
-                          workspace.numel(), ops.L.stream())
-    ops.L.check(rc, "mxq_colsumsq")
-    return out
+    def run(self, W: torch.Tensor, colstat: torch.Tensor):
+        """fasterquant + pack of one linear into this job's buffers (W is left untouched)."""
+        ops.pack(W, colstat, out=self.packed, workspace=self.ws)
+        ops.ptq_quant(W, colstat, out=self.Wq, workspace=self.ws)
+        return self.Wq, self.packed
 
 
-def quantize_linear(W: torch.Tensor, colstat: torch.Tensor, job: LinearQuantJob):
-    """fasterquant + pack for one linear into the job's buffers (W is left untouched)."""
-    ops.pack(W, colstat, out=job.packed, workspace=job.ws)
-    ops.ptq_quant(W, colstat, out=job.Wq, workspace=job.ws)
-    return job.Wq, job.packed
+# Llama decoder layer: linear name -> (out dim, in dim, which captured input feeds it)
+def llama_linears(hidden: int, inter: int, kv_hidden: int | None = None):
+    kv = hidden if kv_hidden is None else kv_hidden
+    return {
+        "self_attn.q_proj": (hidden, hidden, "attn_in"), "self_attn.k_proj": (kv, hidden, "attn_in"),
+        "self_attn.v_proj": (kv, hidden, "attn_in"), "self_attn.o_proj": (hidden, hidden, "o_in"),
+        "mlp.gate_proj": (inter, hidden, "mlp_in"), "mlp.up_proj": (inter, hidden, "mlp_in"),
+        "mlp.down_proj": (hidden, inter, "down_in"),
+    }
+
+
+class LlamaLayerPTQ:
+    """The mxq work of one decoder layer given its captured linear inputs: 4 activation statistics
+    (what the 7 MXQGPT.add_batch hooks compute, prune.py:389-402) + fasterquant + pack of the 7
+    linears (prune.py:404-414).  Kernels launched per layer: 4 x 2 (statistics) + 7 x 6."""
+
+    LAUNCHES_PER_LAYER = 4 * 2 + 7 * 6
+
+    def __init__(self, hidden: int, inter: int, device, max_tokens: int, kv_hidden=None):
+        self.linears = llama_linears(hidden, inter, kv_hidden)
+        self.device = device
+        self.jobs = {}
+        for name, (oc, ic, _) in self.linears.items():
+            if (oc, ic) not in self.jobs:
+                self.jobs[(oc, ic)] = LinearQuantJob(oc, ic, device)
+        self.stats = {k: torch.empty(d, dtype=torch.float32, device=device)
+                      for k, d in (("attn_in", hidden), ("o_in", hidden), ("mlp_in", hidden), ("down_in", inter))}
+        n = ops.L.lib().mxq_colsumsq_workspace_bytes(max_tokens, hidden)
+        n = max(n, ops.L.lib().mxq_colsumsq_workspace_bytes(max_tokens, inter))
+        self.stat_ws = torch.empty(int(n), dtype=torch.uint8, device=device)
+
+    def statistics(self, calib: dict, nsamples: int, on_stat=None):
+        for key, X in calib.items():
+            X2 = X.reshape(-1, X.shape[-1])
+            if on_stat is not None:
+                on_stat(key, X2, True)
+            rc = ops.L.lib().mxq_colsumsq(ops.L.ptr(X2), X2.shape[0], X2.shape[1], ops.L.dtype_enum(X2),
+                                          ops.L.ptr(self.stats[key]), 0.0, 2.0 / nsamples, 0,
+                                          ops.L.ptr(self.stat_ws), self.stat_ws.numel(), ops.L.stream())
+            ops.L.check(rc, "mxq_colsumsq")
+            if on_stat is not None:
+                on_stat(key, X2, False)
+
+    def quantize(self, weights: dict, sink=None):
+        for name, (oc, ic, key) in self.linears.items():
+            Wq, packed = self.jobs[(oc, ic)].run(weights[name], self.stats[key])
+            if sink is not None:
+                sink(name, Wq, packed)
+
+    def run(self, weights: dict, calib: dict, nsamples: int, sink=None, on_stat=None):
+        self.statistics(calib, nsamples, on_stat)
+        self.quantize(weights, sink)
+
+
+def algorithmic_bytes_per_layer(hidden: int, inter: int, tokens: int, kv_hidden=None):
+    """statistics read each distinct linear input once (2 B/elt); quantize+pack read
+    fp16 W, write fp16 Wq and the 3.0-bit packed tensors (4 + 0.3756 B per weight)."""
+    lin = llama_linears(hidden, inter, kv_hidden)
+    stats = tokens * (3 * hidden + inter) * 2
+    weights = sum(oc * ic for oc, ic, _ in lin.values())
+    packed = sum(packed_nbytes(oc, ic) for oc, ic, _ in lin.values())
+    return stats, weights * 4 + packed
+
+
+def packed_nbytes(OC: int, IC: int) -> int:
+    return sum(int(torch.Size(s).numel()) * (2 if d == torch.float16 else 4)
+               for s, d in ops.packed_shapes(OC, IC).values())

@@ -14,9 +14,16 @@ def to_np(t: torch.Tensor) -> np.ndarray:
 
 
 def bits_equal(a: np.ndarray, b: np.ndarray) -> bool:
+    """Bit-for-bit equality; NaNs must sit in the same places (payload/sign of a NaN is not part
+    of the contract: 0/0 in a constant fp16 group is NaN in the reference too)."""
     a = np.ascontiguousarray(a, dtype=np.float32)
     b = np.ascontiguousarray(b, dtype=np.float32)
-    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    if a.shape != b.shape:
+        return False
+    na, nb = np.isnan(a), np.isnan(b)
+    if not np.array_equal(na, nb):
+        return False
+    return np.array_equal(a.view(np.uint32)[~na], b.view(np.uint32)[~nb])
 
 
 def packed_to_dev(p: dict, dev):
