@@ -119,6 +119,13 @@ MXQ_API size_t mxq_pack_workspace_bytes(int64_t OC, int64_t IC);
 MXQ_API int mxq_pack(const void* W, const float* colstat, int64_t OC, int64_t IC, mxq_packed_t out,
              void* workspace, size_t workspace_bytes, void* stream);
 
+/* Both of the above in one pass over W (read once; writes Wq and the packed tensors): what
+ * MXQGPT.fasterquant does per linear plus the packing the reference leaves undone.
+ * workspace: mxq_ptq_workspace_bytes(rows, cols). */
+MXQ_API int mxq_ptq_quant_pack(const void* W, void* Wq, uint8_t* codes, const float* colstat,
+                               int64_t rows, int64_t cols, mxq_packed_t out, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 /* Dequantize the packed layout to fp16 or fp32 [OC, IC] (decode formula of
  * gemv_mxq_cuda.cu:131-136,152-153,178-179,191-192). */
 MXQ_API int mxq_unpack(mxq_packed_t in, int64_t OC, int64_t IC, void* out, int out_dtype, void* stream);

@@ -14,6 +14,8 @@
 // correctly-rounded reciprocal + one Markstein correction (common.cuh), round-half-even by the
 // magic-constant add.  Each intermediate is rounded to the tensor dtype like the reference's
 // separate ATen kernels do.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mxq {
@@ -39,9 +41,17 @@ struct FQParams {
 
 constexpr int kFQThreads = 256;
 
-template <typename T, bool kRef>
+// Template switches (all compile-time so that the hot loop carries no dead work):
+//   kRef    reference recipe {low,low,low,pool} generated arithmetically (no mask table)
+//   kFast16 fp16/bf16 tensors with the reference bit-widths (2-bit groups, 4-bit pool): the
+//           per-element chain runs on packed f16x2/bf16x2 instructions (common.cuh P16), only
+//           the division is done in fp32.  Otherwise: fp32 math + explicit rounding to T.
+//   LPG     lanes (16-byte chunks) per group if known at compile time, 0 = runtime (p.lpg)
+//   kCodes  also emit the integer codes
+template <typename T, bool kRef, bool kFast16, int LPG, bool kCodes>
 __global__ void __launch_bounds__(kFQThreads) fakequant_fwd_kernel(const FQParams p) {
   using D = DT<T>;
+  using P = P16<typename std::conditional<kFast16, T, __half>::type>;
   constexpr int EPC = D::EPC;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* bufs = smem;
@@ -52,9 +62,12 @@ __global__ void __launch_bounds__(kFQThreads) fakequant_fwd_kernel(const FQParam
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int team = warp >> p.tw_shift, tw = warp & (p.tw - 1);
   const int tthreads = p.tw * 32;
+  const int lpg = LPG ? LPG : p.lpg;
+  const int lpg_shift = LPG ? (LPG == 1 ? 0 : LPG == 2 ? 1 : LPG == 4 ? 2 : LPG == 8 ? 3 : LPG == 16 ? 4 : 5)
+                            : p.lpg_shift;
 
   if (!kRef) {
-    const int ng = p.cols / (p.lpg * EPC);
+    const int ng = p.cols / (lpg * EPC);
     for (int g = tid; g < ng; g += kFQThreads) gtab[g] = p.group_bits[g];
   }
   if (tid == 0) {
@@ -97,11 +110,23 @@ __global__ void __launch_bounds__(kFQThreads) fakequant_fwd_kernel(const FQParam
     // ---- pass 1: per-row min/max over the pooled chunks -----------------------------------
     float pmin = INFINITY, pmax = -INFINITY;
     if (active) {
-      if (kRef) {
+      if (kRef && kFast16) {
         const int npc = p.cpr >> 2;  // one group in four is pooled
+        uint32_t mn2 = P::kPosInfNegInf & 0xFFFFu, mx2 = P::kPosInfNegInf >> 16;
+        mn2 |= mn2 << 16; mx2 |= mx2 << 16;
         for (int m = tw * 32 + lane; m < npc; m += tthreads) {
-          const int c = ((((m >> p.lpg_shift) << 2) + 3) << p.lpg_shift) + (m & (p.lpg - 1));
-          const uint4 ch = *reinterpret_cast<const uint4*>(rowp + (size_t)c * 16);
+          const int c = ((((m >> lpg_shift) << 2) + 3) << lpg_shift) + (m & (lpg - 1));
+          const uint4 ch = *reinterpret_cast<const uint4*>(rowp + c * 16);
+          mn2 = P::vmin(P::vmin(mn2, P::vmin(ch.x, ch.y)), P::vmin(ch.z, ch.w));
+          mx2 = P::vmax(P::vmax(mx2, P::vmax(ch.x, ch.y)), P::vmax(ch.z, ch.w));
+        }
+        pmin = fminf(P::lo(mn2), P::hi(mn2));
+        pmax = fmaxf(P::lo(mx2), P::hi(mx2));
+      } else if (kRef) {
+        const int npc = p.cpr >> 2;
+        for (int m = tw * 32 + lane; m < npc; m += tthreads) {
+          const int c = ((((m >> lpg_shift) << 2) + 3) << lpg_shift) + (m & (lpg - 1));
+          const uint4 ch = *reinterpret_cast<const uint4*>(rowp + c * 16);
           float f[EPC];
           D::unpack(ch, f);
 #pragma unroll
@@ -109,8 +134,8 @@ __global__ void __launch_bounds__(kFQThreads) fakequant_fwd_kernel(const FQParam
         }
       } else {
         for (int c = tw * 32 + lane; c < p.cpr; c += tthreads) {
-          if (gtab[c >> p.lpg_shift] & MXQ_POOL_FLAG) {
-            const uint4 ch = *reinterpret_cast<const uint4*>(rowp + (size_t)c * 16);
+          if (gtab[c >> lpg_shift] & MXQ_POOL_FLAG) {
+            const uint4 ch = *reinterpret_cast<const uint4*>(rowp + c * 16);
             float f[EPC];
             D::unpack(ch, f);
 #pragma unroll
@@ -136,54 +161,105 @@ __global__ void __launch_bounds__(kFQThreads) fakequant_fwd_kernel(const FQParam
     // ---- pass 2: quantize / dequantize -----------------------------------------------------
     if (active) {
       uint8_t* orow = p.out + (size_t)(row0 + team) * p.row_bytes;
-      uint8_t* crow = p.codes ? p.codes + (size_t)(row0 + team) * p.cols : nullptr;
-      for (int c0 = tw * 32; c0 < p.cpr; c0 += tthreads) {
-        const int c = c0 + lane;
-        const bool valid = c < p.cpr;
-        float f[EPC];
-        float lmin = INFINITY, lmax = -INFINITY;
-        if (valid) {
-          const uint4 ch = *reinterpret_cast<const uint4*>(rowp + (size_t)c * 16);
-          D::unpack(ch, f);
+      uint8_t* crow = kCodes ? p.codes + (size_t)(row0 + team) * p.cols : nullptr;
+      if (kFast16) {
+        const uint32_t a2_pool = P::pack(a_pool, a_pool), b2_pool = P::pack(b_pool, b_pool);
+        for (int c0 = tw * 32; c0 < p.cpr; c0 += tthreads) {
+          const int c = c0 + lane;
+          const bool valid = c < p.cpr;
+          uint4 ch = make_uint4(0, 0, 0, 0);
+          uint32_t mm = P::kPosInfNegInf;            // lo half: running min, hi half: running max
+          if (valid) {
+            ch = *reinterpret_cast<const uint4*>(rowp + c * 16);
+            uint32_t mn = P::vmin(P::vmin(ch.x, ch.y), P::vmin(ch.z, ch.w));
+            uint32_t mx = P::vmax(P::vmax(ch.x, ch.y), P::vmax(ch.z, ch.w));
+            mn = P::vmin(mn, prmt_b32(mn, mn, 0x1032));
+            mx = P::vmax(mx, prmt_b32(mx, mx, 0x1032));
+            mm = prmt_b32(mn, mx, 0x5410);
+          }
 #pragma unroll
-          for (int e = 0; e < EPC; ++e) { lmin = fminf(lmin, f[e]); lmax = fmaxf(lmax, f[e]); }
-        }
-        for (int o = p.lpg >> 1; o > 0; o >>= 1) {
-          lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
-          lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-        }
-        if (!valid) continue;
-        const int g = c >> p.lpg_shift;
-        const bool pooled = kRef ? ((g & 3) == 3) : ((gtab[g] & MXQ_POOL_FLAG) != 0);
-        float a, b, r, s, rs;
-        if (pooled) {
-          a = a_pool; b = b_pool; r = r_pool; s = s_pool; rs = rs_pool;
-        } else {
-          a = D::rnd(__fadd_rn(D::rnd(__fsub_rn(lmax, lmin)), 1e-8f));  // alpha + 1e-8 (:456)
-          b = lmin;
-          r = __frcp_rn(a);
-          s = s_low; rs = rs_low;
-        }
-        float o[EPC];
-        uint32_t cw[EPC / 4] = {};
+          for (int o = lpg >> 1; o > 0; o >>= 1) {
+            const uint32_t other = __shfl_xor_sync(0xffffffffu, mm, o);
+            mm = prmt_b32(P::vmin(mm, other), P::vmax(mm, other), 0x7610);
+          }
+          if (!valid) continue;
+          const int g = c >> lpg_shift;
+          const bool pooled = kRef ? ((g & 3) == 3) : ((gtab[g] & MXQ_POOL_FLAG) != 0);
+          uint32_t b2 = prmt_b32(mm, mm, 0x1010);
+          const uint32_t alpha2 = P::sub(prmt_b32(mm, mm, 0x3232), b2);      // max - min (:358-361)
+          const float ax = __fadd_rn(P::lo(alpha2), 1e-8f);                  // alpha + 1e-8 (:456)
+          uint32_t a2 = P::pack(ax, ax);                                     // rounded to the dtype
+          float a = P::lo(a2);
+          float r = rcp_rn_normal(a);
+          uint32_t s2 = P::kS3, ch2 = P::kC3, cl2 = 0u;
+          if (pooled) {
+            a = a_pool; r = r_pool; a2 = a2_pool; b2 = b2_pool;
+            s2 = P::kS15; ch2 = P::kC15hi; cl2 = P::kC15lo;
+          }
+          const uint32_t w[4] = {ch.x, ch.y, ch.z, ch.w};
+          uint32_t o[4], cw[4];
 #pragma unroll
-        for (int e = 0; e < EPC; ++e) {
-          float t = D::rnd(__fsub_rn(f[e], b));
-          t = D::rnd(div_rn_by(t, a, r));          // input_normalized (:456)
-          t = D::rnd(__fmul_rn(t, s));
-          int qi;
-          const float q = rint_magic(t, qi);       // torch.round (:458)
-          t = D::rnd(div_rn_by(q, s, rs));         // .div(s)
-          t = D::rnd(__fmul_rn(t, a));
-          o[e] = D::rnd(__fadd_rn(t, b));          // (:460)
-          cw[e >> 2] |= (uint32_t)(qi & 0xFF) << (8 * (e & 3));
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t t2 = P::sub(w[i], b2);                            // x - beta
+            const uint32_t n2 = P::pack(div_rn_by(P::lo(t2), a, r), div_rn_by(P::hi(t2), a, r));
+            const uint32_t m2 = P::add(P::mul(n2, s2), P::kMagic);           // round-half-even
+            const uint32_t q2 = P::sub(m2, P::kMagic);
+            const uint32_t v2 = P::fma(q2, ch2, P::mul(q2, cl2));            // == RN16(RN32(q / s))
+            o[i] = P::add(P::mul(v2, a2), b2);
+            cw[i] = m2 & P::kCodeMask;
+          }
+          st_stream(orow + c * 16, make_uint4(o[0], o[1], o[2], o[3]));
+          if (kCodes) {
+            *reinterpret_cast<uint2*>(crow + c * 8) =
+                make_uint2(prmt_b32(cw[0], cw[1], 0x6420), prmt_b32(cw[2], cw[3], 0x6420));
+          }
         }
-        st_stream(orow + (size_t)c * 16, D::pack(o));
-        if (crow) {
-          if (EPC == 4) {
-            *reinterpret_cast<uint32_t*>(crow + (size_t)c * 4) = cw[0];
-          } else {
-            *reinterpret_cast<uint2*>(crow + (size_t)c * 8) = make_uint2(cw[0], cw[EPC / 4 - 1]);
+      } else {
+        for (int c0 = tw * 32; c0 < p.cpr; c0 += tthreads) {
+          const int c = c0 + lane;
+          const bool valid = c < p.cpr;
+          float f[EPC];
+          float lmin = INFINITY, lmax = -INFINITY;
+          if (valid) {
+            const uint4 ch = *reinterpret_cast<const uint4*>(rowp + c * 16);
+            D::unpack(ch, f);
+#pragma unroll
+            for (int e = 0; e < EPC; ++e) { lmin = fminf(lmin, f[e]); lmax = fmaxf(lmax, f[e]); }
+          }
+#pragma unroll
+          for (int o = lpg >> 1; o > 0; o >>= 1) {
+            lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+            lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+          }
+          if (!valid) continue;
+          const int g = c >> lpg_shift;
+          const bool pooled = kRef ? ((g & 3) == 3) : ((gtab[g] & MXQ_POOL_FLAG) != 0);
+          float a = D::rnd(__fadd_rn(D::rnd(__fsub_rn(lmax, lmin)), 1e-8f));  // alpha + 1e-8 (:456)
+          float b = lmin;
+          float r = rcp_rn_normal(a);
+          float s = s_low, rs = rs_low;
+          if (pooled) { a = a_pool; b = b_pool; r = r_pool; s = s_pool; rs = rs_pool; }
+          float o[EPC];
+          uint32_t cw[EPC / 4] = {};
+#pragma unroll
+          for (int e = 0; e < EPC; ++e) {
+            float t = D::rnd(__fsub_rn(f[e], b));
+            t = D::rnd(div_rn_by(t, a, r));          // input_normalized (:456)
+            t = D::rnd(__fmul_rn(t, s));
+            int qi;
+            const float q = rint_magic(t, qi);       // torch.round (:458)
+            t = D::rnd(div_rn_by(q, s, rs));         // .div(s)
+            t = D::rnd(__fmul_rn(t, a));
+            o[e] = D::rnd(__fadd_rn(t, b));          // (:460)
+            if (kCodes) cw[e >> 2] |= (uint32_t)(qi & 0xFF) << (8 * (e & 3));
+          }
+          st_stream(orow + c * 16, D::pack(o));
+          if (kCodes) {
+            if (EPC == 4) {
+              *reinterpret_cast<uint32_t*>(crow + c * 4) = cw[0];
+            } else {
+              *reinterpret_cast<uint2*>(crow + c * 8) = make_uint2(cw[0], cw[EPC / 4 - 1]);
+            }
           }
         }
       }
@@ -240,13 +316,28 @@ __global__ void ste_bwd_tail_kernel(const T* g, const T* x, T* gi, int64_t start
   }
 }
 
-template <typename T>
-static int launch_fq(const FQParams& p, bool ref, int smem, int grid, cudaStream_t st) {
-  auto k = ref ? fakequant_fwd_kernel<T, true> : fakequant_fwd_kernel<T, false>;
+template <typename T, bool kRef, bool kFast16, int LPG>
+static int launch_fq3(const FQParams& p, int smem, int grid, cudaStream_t st) {
+  auto k = p.codes ? fakequant_fwd_kernel<T, kRef, kFast16, LPG, true>
+                   : fakequant_fwd_kernel<T, kRef, kFast16, LPG, false>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
   k<<<grid, kFQThreads, smem, st>>>(p);
   MXQ_LAUNCH_RESULT();
+}
+
+template <typename T>
+static int launch_fq(const FQParams& p, bool ref, int smem, int grid, cudaStream_t st) {
+  constexpr bool k16 = sizeof(T) == 2;
+  constexpr int kLpg16 = 16 / DT<T>::EPC;   // lanes per group at the reference group size 16
+  const bool fast = k16 && p.low_bits == 2 && p.pool_bits == 4;
+  const bool g16 = p.lpg == kLpg16;
+  if (ref) {
+    if (fast) return g16 ? launch_fq3<T, true, k16, kLpg16>(p, smem, grid, st) : launch_fq3<T, true, k16, 0>(p, smem, grid, st);
+    return g16 ? launch_fq3<T, true, false, kLpg16>(p, smem, grid, st) : launch_fq3<T, true, false, 0>(p, smem, grid, st);
+  }
+  if (fast) return launch_fq3<T, false, k16, 0>(p, smem, grid, st);
+  return launch_fq3<T, false, false, 0>(p, smem, grid, st);
 }
 
 template <typename T>

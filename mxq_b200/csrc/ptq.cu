@@ -1,21 +1,29 @@
-// Fused MXQGPT.fasterquant(blocksize=16) + Quantizer (sm_100a).
+// Fused MXQGPT.fasterquant(blocksize=16) + Quantizer + packer (sm_100a).
 //
-// Replaces mxq_quant/lib/mxqgpt.py:387-448 and mxq_quant/lib/quantizer.py:5-20,61-121,149-155:
-// 192 Quantizer() constructions and ~30 ATen calls per 64-column block become two kernels:
-//   (A) pool_minmax : per row min/max over the pooled (4-bit) columns of W with dead columns
-//                     zeroed (reads one 32-byte sector in four);
-//   (B) ptq_tile    : one warp per (16-row tile, 4-group block): lane = (row, half-group),
-//                     group min/max by one xor-shuffle, the 16-row second-level scale
-//                     quantisation (quantizer.py:114-121) by xor-shuffles 2,4,8,16, then
-//                     quantize/dequantize and 128-bit stores of the fp16 fake-quant weight.
-// HBM traffic: read W 1.25x, write Wq 1x (algorithmic 4 B / weight).
+// Replaces mxq_quant/lib/mxqgpt.py:387-448 and mxq_quant/lib/quantizer.py:5-20,61-121,149-155
+// (192 Quantizer() constructions and ~30 ATen calls per 64-column block) and produces the packed
+// mixed 2/4-bit layout consumed by gemv_mxq_cuda.cu:39-208 (the reference has no producer for it;
+// encode policy = oracle pack_mxq) -- in two kernels:
+//   (A) pool_prepass : one warp per row: min/max over the pooled (4-bit) columns with dead
+//                      columns zeroed; also the packer's per-row 4-bit scale / zero-point;
+//   (B) ptq_pack_tile: one warp per (16-row tile, 64-column block).  lane = (row pair, slot):
+//                      a thread owns the 16 columns of one group for rows r and r+8, so group
+//                      min/max, scale and zero need no shuffles and are computed exactly once;
+//                      the 16-row second-level scale quantisation (quantizer.py:114-121) is three
+//                      xor-shuffles, the packer's 4-row second level two.  W is read once and
+//                      both outputs (fp16 fake-quant weights, packed tensors) are written.
 // All arithmetic is op-by-op IEEE fp32 like the reference; x/scale uses a correctly-rounded
-// reciprocal + Markstein step (bit-identical to division, oracle/div_check.c).
+// reciprocal + one Markstein step (bit-identical to division, oracle/div_check.c); rounding is
+// clamp-then-magic-add (clamp and round-half-even commute because the bounds are integers).
 #include "common.cuh"
 
 namespace mxq {
 
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+__device__ __forceinline__ float rint_any(float v) {   // |v| < 2^22
+  return __fadd_rn(__fadd_rn(v, 12582912.0f), -12582912.0f);
+}
 
 // quantizer.py:81-99: scale, zero from (xmin, xmax) with the degenerate fix
 __device__ __forceinline__ void find_params(float xmin, float xmax, float maxq, float& scale,
@@ -25,140 +33,227 @@ __device__ __forceinline__ void find_params(float xmin, float xmax, float maxq, 
   zero = fdiv(-xmin, scale);
 }
 
-// quantizer.py:114-121 over 16 lanes that differ in lane bits 1..4 (same bit 0)
-__device__ __forceinline__ float qq_scale_16rows(float scale, int qq_maxq) {
-  float smin = scale, smax = scale;
-#pragma unroll
-  for (int o = 2; o <= 16; o <<= 1) {
-    smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
-    smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
-  }
-  float s2, z2;
-  find_params(smin, smax, (float)qq_maxq, s2, z2);
-  float q = rintf(__fadd_rn(fdiv(scale, fmaxf(s2, 1e-9f)), z2));
-  q = fminf(fmaxf(q, 0.f), (float)qq_maxq);
-  return __fmul_rn(s2, __fsub_rn(q, z2));
-}
-
 __global__ void dead_mask_kernel(const float* __restrict__ colstat, uint8_t* __restrict__ dead,
                                  int cols) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < cols) dead[c] = colstat ? (colstat[c] == 0.f) : 0;
 }
 
-__device__ __forceinline__ void load_chunk_f16(const __half* W, const uint8_t* dead, size_t row_off,
-                                               int col, float* f) {
-  const uint4 ch = *reinterpret_cast<const uint4*>(W + row_off + col);
-  DT<__half>::unpack(ch, f);
-  const uint2 dm = *reinterpret_cast<const uint2*>(dead + col);
-  if (dm.x | dm.y) {
+__device__ __forceinline__ void apply_dead8(uint32_t lo, uint32_t hi, float* f) {
+  if (lo | hi) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const uint32_t w = e < 4 ? dm.x : dm.y;
+      const uint32_t w = e < 4 ? lo : hi;
       if ((w >> (8 * (e & 3))) & 0xFF) f[e] = 0.f;
     }
   }
 }
 
-// (A) one warp per row
-template <bool kRef>
-__global__ void __launch_bounds__(256) pool_minmax_kernel(const __half* __restrict__ W,
-                                                          const uint8_t* __restrict__ dead,
-                                                          const uint8_t* __restrict__ gbits,
-                                                          float2* __restrict__ out, int rows,
-                                                          int cols, int group) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const int cpg = group / 8;  // 16-byte chunks per group
-  const int nchunks = cols / 8;
+// (A) one warp per row, 8 rows per CTA.  pool_mm[row] = (min, max) over pooled columns;
+//     pack_pool[row] = (s4f, z4) and scales_4b / zeros_4b of the packed layout when kPack.
+template <bool kRef, bool kPack>
+__global__ void __launch_bounds__(256) pool_prepass_kernel(const __half* __restrict__ W,
+                                                           const uint8_t* __restrict__ dead,
+                                                           const uint8_t* __restrict__ gbits,
+                                                           float2* __restrict__ pool_mm,
+                                                           float2* __restrict__ pack_pool,
+                                                           __half* __restrict__ scales_4b,
+                                                           uint32_t* __restrict__ zeros_4b,
+                                                           int rows, int cols) {
+  __shared__ uint32_t z4s[8];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + w;
+  const int nchunks = cols / 8;   // 16-byte chunks; group 16 = 2 chunks
   float mn = INFINITY, mx = -INFINITY;
-  const size_t roff = (size_t)row * cols;
-  if (kRef) {
-    const int npc = nchunks / 4;
+  if (row < rows) {
+    const size_t roff = (size_t)row * cols;
+    const int npc = kRef ? nchunks / 4 : nchunks;
     for (int m = lane; m < npc; m += 32) {
-      const int c = ((m / cpg) * 4 + 3) * cpg + (m % cpg);
+      const int c = kRef ? ((m >> 1) * 4 + 3) * 2 + (m & 1) : m;
+      if (!kRef && !(gbits[c >> 1] & MXQ_POOL_FLAG)) continue;
       float f[8];
-      load_chunk_f16(W, dead, roff, c * 8, f);
+      DT<__half>::unpack(*reinterpret_cast<const uint4*>(W + roff + c * 8), f);
+      const uint2 dm = *reinterpret_cast<const uint2*>(dead + c * 8);
+      apply_dead8(dm.x, dm.y, f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) { mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]); }
-    }
-  } else {
-    for (int c = lane; c < nchunks; c += 32) {
-      if (gbits[c / cpg] & MXQ_POOL_FLAG) {
-        float f[8];
-        load_chunk_f16(W, dead, roff, c * 8, f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]); }
-      }
     }
   }
   mn = warp_min(mn);
   mx = warp_max(mx);
-  if (lane == 0) out[row] = make_float2(mn, mx);
+  if (row < rows && lane == 0) pool_mm[row] = make_float2(mn, mx);
+  if (kPack) {
+    const float lo = fminf(mn, 0.f), hi = fmaxf(mx, 0.f);
+    __half s4h = __float2half_rn(fdiv(__fsub_rn(hi, lo), 15.f));
+    if (__half2float(s4h) == 0.f) s4h = __float2half_rn(1.f);
+    const float s4f = __half2float(s4h);
+    const float z4 = clampf(rintf(fdiv(-lo, s4f)), 0.f, 15.f);
+    if (lane == 0) {
+      z4s[w] = row < rows ? (uint32_t)z4 : 0u;
+      if (row < rows) {
+        pack_pool[row] = make_float2(s4f, z4);
+        scales_4b[row] = s4h;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) word |= z4s[i] << (4 * i);
+      zeros_4b[blockIdx.x] = word;
+    }
+  }
 }
 
-// (B) group == 16 (2 chunks per group): warp unit = 16 rows x 4 groups (64 columns)
-template <bool kRef>
-__global__ void __launch_bounds__(256) ptq_tile_kernel(const __half* __restrict__ W,
-                                                       __half* __restrict__ Wq,
-                                                       uint8_t* __restrict__ codes,
-                                                       const uint8_t* __restrict__ dead,
-                                                       const uint8_t* __restrict__ gbits,
-                                                       const float2* __restrict__ pool_mm,
-                                                       int rows, int cols, int low_bits,
-                                                       int pool_bits) {
+struct TileParams {
+  const __half* W;
+  __half* Wq;
+  uint8_t* codes;
+  const uint8_t* dead;
+  const uint8_t* gbits;
+  const float2* pool_mm;
+  const float2* pack_pool;
+  mxq_packed_t out;
+  int rows, cols, low_bits, pool_bits;
+};
+
+// (B)
+template <bool kRef, bool kQuant, bool kPack, bool kCodes>
+__global__ void __launch_bounds__(256) ptq_pack_tile_kernel(const TileParams p) {
   const int lane = threadIdx.x & 31;
-  const int r = lane >> 1, h = lane & 1;
-  const int nblk = cols / 64;
-  const int64_t units = (int64_t)(rows / 16) * nblk;
+  const int rr = lane >> 2, k = lane & 3;
+  const int nblk = p.cols / 64;
+  const int nchunk = (nblk + 63) / 64;
+  const int64_t units = (int64_t)(p.rows / 16) * nblk;
   const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int64_t wstride = (int64_t)gridDim.x * 8;
-  const float maxq_low = (float)((1 << low_bits) - 1);
-  const float maxq_pool = (float)((1 << pool_bits) - 1);
-  int cur_tile = -1;
-  float pool_scale = 0.f, pool_zero = 0.f;
+  const float maxq_low = (float)((1 << p.low_bits) - 1);
+  const float maxq_pool = (float)((1 << p.pool_bits) - 1);
+  uint16_t* zs16 = reinterpret_cast<uint16_t*>(p.out.zeros_and_scales);
+  uint8_t* z2b = reinterpret_cast<uint8_t*>(p.out.zeros_2nd);
+  __half* s2o = reinterpret_cast<__half*>(p.out.scales_2nd);
+
   for (int64_t u = warp0; u < units; u += wstride) {
     const int tile = (int)(u / nblk), blk = (int)(u % nblk);
-    const int row = tile * 16 + r;
-    const size_t roff = (size_t)row * cols;
-    if (tile != cur_tile) {  // per-row pool parameters + their 16-row second level
-      cur_tile = tile;
-      const float2 mm = pool_mm[row];
-      find_params(mm.x, mm.y, maxq_pool, pool_scale, pool_zero);
-      pool_scale = qq_scale_16rows(pool_scale, 15);
+    const int col0 = blk * 64 + k * 16;
+    const uint4 dm = *reinterpret_cast<const uint4*>(p.dead + col0);
+    float x[2][16];
+    float mn[2], mx[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const size_t off = (size_t)(tile * 16 + rr + 8 * i) * p.cols + col0;
+      const uint4 c0 = ld_stream(p.W + off), c1 = ld_stream(p.W + off + 8);
+      DT<__half>::unpack(c0, x[i]);
+      DT<__half>::unpack(c1, x[i] + 8);
+      apply_dead8(dm.x, dm.y, x[i]);
+      apply_dead8(dm.z, dm.w, x[i] + 8);
+      mn[i] = x[i][0]; mx[i] = x[i][0];
+#pragma unroll
+      for (int e = 1; e < 16; ++e) { mn[i] = fminf(mn[i], x[i][e]); mx[i] = fmaxf(mx[i], x[i][e]); }
     }
-    float f[4][8];
+
+    if (kQuant) {
+      // ---- MXQGPT.fasterquant semantics ----------------------------------------------------
+      const bool pooled = kRef ? (k == 3) : ((p.gbits[blk * 4 + k] & MXQ_POOL_FLAG) != 0);
+      const float maxq = pooled ? maxq_pool : maxq_low;
+      float scale[2], zero[2];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) load_chunk_f16(W, dead, roff, blk * 64 + k * 16 + h * 8, f[k]);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int g = blk * 4 + k;
-      const bool pooled = kRef ? (k == 3) : ((gbits[g] & MXQ_POOL_FLAG) != 0);
-      float mn = f[k][0], mx = f[k][0];
-#pragma unroll
-      for (int e = 1; e < 8; ++e) { mn = fminf(mn, f[k][e]); mx = fmaxf(mx, f[k][e]); }
-      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      float scale, zero, maxq;
-      find_params(mn, mx, maxq_low, scale, zero);
-      scale = qq_scale_16rows(scale, 15);  // executed by all lanes (shuffles), selected below
-      maxq = maxq_low;
-      if (pooled) { scale = pool_scale; zero = pool_zero; maxq = maxq_pool; }
-      const float sc = fmaxf(scale, 1e-9f);
-      const float rc = __frcp_rn(sc);
-      float o[8];
-      uint32_t cw[2] = {0, 0};
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float q = rintf(__fadd_rn(div_rn_by(f[k][e], sc, rc), zero));
-        q = fminf(fmaxf(q, 0.f), maxq);
-        o[e] = __fmul_rn(scale, __fsub_rn(q, zero));
-        cw[e >> 2] |= (uint32_t)q << (8 * (e & 3));
+      for (int i = 0; i < 2; ++i) {
+        float a = mn[i], b = mx[i];
+        if (pooled) {
+          const float2 mm = p.pool_mm[tile * 16 + rr + 8 * i];
+          a = mm.x; b = mm.y;
+        }
+        find_params(a, b, maxq, scale[i], zero[i]);
       }
-      const size_t off = roff + blk * 64 + k * 16 + h * 8;
-      *reinterpret_cast<uint4*>(Wq + off) = DT<__half>::pack(o);
-      if (codes) *reinterpret_cast<uint2*>(codes + off) = make_uint2(cw[0], cw[1]);
+      // second level over the 16 rows of the tile (quantizer.py:114-121)
+      float smin = fminf(scale[0], scale[1]), smax = fmaxf(scale[0], scale[1]);
+#pragma unroll
+      for (int o = 4; o <= 16; o <<= 1) {
+        smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+        smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+      }
+      float s2, z2;
+      find_params(smin, smax, 15.f, s2, z2);
+      const float s2c = fmaxf(s2, 1e-9f);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float qs = clampf(rintf(__fadd_rn(fdiv(scale[i], s2c), z2)), 0.f, 15.f);
+        const float sq = __fmul_rn(s2, __fsub_rn(qs, z2));       // dequantized scale
+        const float sc = fmaxf(sq, 1e-9f);
+        const float rc = __frcp_rn(sc);
+        float o[16];
+        uint32_t cw[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float v = clampf(__fadd_rn(div_rn_by(x[i][e], sc, rc), zero[i]), 0.f, maxq);
+          int qi;
+          const float q = rint_magic(v, qi);
+          o[e] = __fmul_rn(sq, __fsub_rn(q, zero[i]));
+          if (kCodes) cw[e >> 2] |= (uint32_t)(qi & 0xFF) << (8 * (e & 3));
+        }
+        const size_t off = (size_t)(tile * 16 + rr + 8 * i) * p.cols + col0;
+        *reinterpret_cast<uint4*>(p.Wq + off) = DT<__half>::pack(o);
+        *reinterpret_cast<uint4*>(p.Wq + off + 8) = DT<__half>::pack(o + 8);
+        if (kCodes) *reinterpret_cast<uint4*>(p.codes + off) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+      }
+    }
+
+    if (kPack) {
+      // ---- packed layout (encode policy: oracle pack_mxq) ----------------------------------
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int row = tile * 16 + rr + 8 * i;
+        uint32_t word = 0, word_last = 0, meta = 0;
+        __half s2h = __float2half_rn(0.f);
+        // 2-bit slots: every lane runs the shuffles, slot 3 ignores the result
+        const float lo = fminf(mn[i], 0.f), hi = fmaxf(mx[i], 0.f);
+        float s = fdiv(__fsub_rn(hi, lo), 3.f);
+        if (s == 0.f) s = 1.f;
+        float smax = s;
+        smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, 4));
+        smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, 8));
+        if (k < 3) {
+          s2h = __float2half_rn(fdiv(smax, 3.f));
+          const float s2f = __half2float(s2h);
+          const float c = clampf(rintf(fdiv(s, s2f)), 1.f, 3.f);
+          const float S = __fmul_rn(s2f, c);
+          const float z1 = clampf(rintf(fdiv(-lo, S)), 0.f, 3.f);
+          const float rS = __frcp_rn(S);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float q = clampf(__fadd_rn(rint_any(div_rn_by(x[i][e], S, rS)), z1), 0.f, 3.f);
+            word |= (__float_as_uint(__fadd_rn(q, 12582912.0f)) & 3u) << (2 * e);
+          }
+          meta = ((uint32_t)z1 | ((uint32_t)c << 8)) << (2 * k);
+        } else {
+          const float2 pz = p.pack_pool[row];
+          const float rS = __frcp_rn(pz.x);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float q = clampf(__fadd_rn(rint_any(div_rn_by(x[i][e], pz.x, rS)), pz.y), 0.f, 15.f);
+            const uint32_t code = __float_as_uint(__fadd_rn(q, 12582912.0f)) & 15u;
+            if (e < 8) word |= code << (4 * e); else word_last |= code << (4 * (e - 8));
+          }
+        }
+        // gather the block's four weight words and the metadata half-word into slot 0
+        const uint32_t w1 = __shfl_down_sync(0xffffffffu, word, 1);
+        const uint32_t w2 = __shfl_down_sync(0xffffffffu, word, 2);
+        const uint32_t w3 = __shfl_down_sync(0xffffffffu, word, 3);
+        const uint32_t m1 = __shfl_down_sync(0xffffffffu, meta, 1);
+        const uint32_t m2 = __shfl_down_sync(0xffffffffu, meta, 2);
+        const int chunk = blk >> 6, bp = blk & 63;
+        const int mword = chunk * 32 + (bp & 31), ph = bp >> 5;
+        if (k == 0) {
+          *reinterpret_cast<uint4*>(p.out.weight + (size_t)row * nblk * 4 + (size_t)blk * 4) =
+              make_uint4(word, w1, w2, w3);
+          zs16[((size_t)row * 32 * nchunk + mword) * 2 + ph] = (uint16_t)(meta | m1 | m2);
+          if ((row & 3) == 0) z2b[((size_t)(row >> 2) * 32 * nchunk + mword) * 4 + ph] = 0;  // z2 == 0 policy
+        } else if (k == 3) {
+          p.out.weight_last[(size_t)row * nblk + blk] = (int32_t)word_last;
+        }
+        if (k < 3 && (row & 3) == 0) s2o[(size_t)(row >> 2) * nblk * 3 + (size_t)blk * 3 + k] = s2h;
+      }
     }
   }
 }
@@ -218,44 +313,104 @@ using namespace mxq;
 
 static size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
-extern "C" size_t mxq_ptq_workspace_bytes(int64_t rows, int64_t cols) {
+// workspace: [dead mask: cols bytes][pool_mm: rows float2][pack_pool: rows float2]
+static size_t ws_bytes(int64_t rows, int64_t cols) {
   if (rows < 0 || cols < 0) return 0;
-  return align16((size_t)cols) + align16((size_t)rows * sizeof(float2)) + 16;
+  return align16((size_t)cols) + 2 * align16((size_t)rows * sizeof(float2)) + 16;
+}
+
+extern "C" size_t mxq_ptq_workspace_bytes(int64_t rows, int64_t cols) { return ws_bytes(rows, cols); }
+extern "C" size_t mxq_pack_workspace_bytes(int64_t OC, int64_t IC) { return ws_bytes(OC, IC); }
+
+static int check_packed_ptrs(const mxq_packed_t& p) {
+  MXQ_CHECK_PTR(p.weight);
+  MXQ_CHECK_PTR(p.weight_last);
+  MXQ_CHECK_PTR(p.zeros_and_scales);
+  MXQ_CHECK_PTR(p.zeros_2nd);
+  if (!p.scales_2nd || !p.scales_4b || !p.zeros_4b) return MXQ_E_NULL;
+  return MXQ_OK;
+}
+
+template <bool kRef, bool kQuant, bool kPack>
+static void launch_tile(const TileParams& tp, unsigned grid, cudaStream_t st) {
+  if (tp.codes) ptq_pack_tile_kernel<kRef, kQuant, kPack, true><<<grid, 256, 0, st>>>(tp);
+  else ptq_pack_tile_kernel<kRef, kQuant, kPack, false><<<grid, 256, 0, st>>>(tp);
+}
+
+static int run_ptq_pack(const void* W, void* Wq, uint8_t* codes, const float* colstat, int64_t rows,
+                        int64_t cols, int group, int low_bits, const uint8_t* group_bits,
+                        const mxq_packed_t* packed, void* workspace, size_t workspace_bytes,
+                        cudaStream_t st) {
+  const bool quant = Wq != nullptr, pack = packed != nullptr;
+  if (rows < 0 || cols < 0) return MXQ_E_SHAPE;
+  if (rows == 0 || cols == 0) return MXQ_OK;
+  MXQ_CHECK_PTR(W);
+  MXQ_CHECK_PTR(workspace);
+  if (quant) MXQ_CHECK_PTR(Wq);
+  if (pack) {
+    int rc = check_packed_ptrs(*packed);
+    if (rc) return rc;
+    if (group_bits) return MXQ_E_UNSUPPORTED;   // the packed layout is the reference recipe only
+  }
+  if (group != 16) return MXQ_E_UNSUPPORTED;    // fasterquant is only ever called with blocksize=16
+  if (rows % 16 || cols % 64) return MXQ_E_SHAPE;
+  if (low_bits < 1 || low_bits > 8) return MXQ_E_SHAPE;
+  if (rows > INT32_MAX || cols > (1 << 24)) return MXQ_E_SHAPE;
+  if (workspace_bytes < ws_bytes(rows, cols)) return MXQ_E_WORKSPACE;
+  uint8_t* dead = (uint8_t*)workspace;
+  float2* pool_mm = (float2*)((uint8_t*)workspace + align16((size_t)cols));
+  float2* pack_pool = (float2*)((uint8_t*)pool_mm + align16((size_t)rows * sizeof(float2)));
+  const int nblk = (int)(cols / 64);
+  const int nchunk = (nblk + 63) / 64;
+  if (pack && (nblk % 64)) {  // padding half-words of the last metadata chunk
+    cudaMemsetAsync(packed->zeros_and_scales, 0, (size_t)rows * 32 * nchunk * 4, st);
+    cudaMemsetAsync(packed->zeros_2nd, 0, (size_t)(rows / 4) * 32 * nchunk * 4, st);
+  }
+  dead_mask_kernel<<<(unsigned)ceil_div(cols, 256), 256, 0, st>>>(colstat, dead, (int)cols);
+  const unsigned gridA = (unsigned)ceil_div(rows, 8);
+  const __half* w = (const __half*)W;
+  __half* s4 = pack ? (__half*)packed->scales_4b : nullptr;
+  uint32_t* z4 = pack ? (uint32_t*)packed->zeros_4b : nullptr;
+  const bool ref = group_bits == nullptr;
+  if (ref && pack) pool_prepass_kernel<true, true><<<gridA, 256, 0, st>>>(w, dead, nullptr, pool_mm, pack_pool, s4, z4, (int)rows, (int)cols);
+  else if (ref) pool_prepass_kernel<true, false><<<gridA, 256, 0, st>>>(w, dead, nullptr, pool_mm, pack_pool, s4, z4, (int)rows, (int)cols);
+  else pool_prepass_kernel<false, false><<<gridA, 256, 0, st>>>(w, dead, group_bits, pool_mm, pack_pool, s4, z4, (int)rows, (int)cols);
+  TileParams tp{};
+  tp.W = w; tp.Wq = (__half*)Wq; tp.codes = codes; tp.dead = dead; tp.gbits = group_bits;
+  tp.pool_mm = pool_mm; tp.pack_pool = pack_pool;
+  if (pack) tp.out = *packed;
+  tp.rows = (int)rows; tp.cols = (int)cols; tp.low_bits = low_bits; tp.pool_bits = 4;
+  const int64_t units = (rows / 16) * (int64_t)nblk;
+  int64_t grid = ceil_div(units, 8);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  if (!ref) launch_tile<false, true, false>(tp, (unsigned)grid, st);
+  else if (quant && pack) launch_tile<true, true, true>(tp, (unsigned)grid, st);
+  else if (quant) launch_tile<true, true, false>(tp, (unsigned)grid, st);
+  else launch_tile<true, false, true>(tp, (unsigned)grid, st);
+  MXQ_LAUNCH_RESULT();
 }
 
 extern "C" int mxq_ptq_quant(const void* W, void* Wq, uint8_t* codes, const float* colstat,
                              int64_t rows, int64_t cols, int group, int low_bits,
                              const uint8_t* group_bits, void* workspace, size_t workspace_bytes,
                              void* stream) {
-  if (rows < 0 || cols < 0) return MXQ_E_SHAPE;
-  if (rows == 0 || cols == 0) return MXQ_OK;
-  MXQ_CHECK_PTR(W);
-  MXQ_CHECK_PTR(Wq);
-  MXQ_CHECK_PTR(workspace);
-  if (group != 16) return MXQ_E_UNSUPPORTED;  // fasterquant is only ever called with blocksize=16
-  if (rows % 16 || cols % 64) return MXQ_E_SHAPE;
-  if (low_bits < 1 || low_bits > 8) return MXQ_E_SHAPE;
-  if (rows > INT32_MAX || cols > (1 << 24)) return MXQ_E_SHAPE;
-  if (workspace_bytes < mxq_ptq_workspace_bytes(rows, cols)) return MXQ_E_WORKSPACE;
-  cudaStream_t st = as_stream(stream);
-  uint8_t* dead = (uint8_t*)workspace;
-  float2* pool_mm = (float2*)((uint8_t*)workspace + align16((size_t)cols));
-  dead_mask_kernel<<<(unsigned)ceil_div(cols, 256), 256, 0, st>>>(colstat, dead, (int)cols);
-  const unsigned gridA = (unsigned)ceil_div(rows, 8);
-  const int64_t units = (rows / 16) * (cols / 64);
-  int64_t gridB = ceil_div(units, 8);
-  if (gridB > kNumSMs * 8) gridB = kNumSMs * 8;
-  const __half* w = (const __half*)W;
-  if (group_bits == nullptr) {
-    pool_minmax_kernel<true><<<gridA, 256, 0, st>>>(w, dead, nullptr, pool_mm, (int)rows, (int)cols, group);
-    ptq_tile_kernel<true><<<(unsigned)gridB, 256, 0, st>>>(w, (__half*)Wq, codes, dead, nullptr, pool_mm,
-                                                           (int)rows, (int)cols, low_bits, 4);
-  } else {
-    pool_minmax_kernel<false><<<gridA, 256, 0, st>>>(w, dead, group_bits, pool_mm, (int)rows, (int)cols, group);
-    ptq_tile_kernel<false><<<(unsigned)gridB, 256, 0, st>>>(w, (__half*)Wq, codes, dead, group_bits, pool_mm,
-                                                            (int)rows, (int)cols, low_bits, 4);
-  }
-  MXQ_LAUNCH_RESULT();
+  if (!Wq && rows > 0 && cols > 0) return MXQ_E_NULL;
+  return run_ptq_pack(W, Wq, codes, colstat, rows, cols, group, low_bits, group_bits, nullptr,
+                      workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" int mxq_pack(const void* W, const float* colstat, int64_t OC, int64_t IC,
+                        mxq_packed_t out, void* workspace, size_t workspace_bytes, void* stream) {
+  return run_ptq_pack(W, nullptr, nullptr, colstat, OC, IC, 16, 2, nullptr, &out, workspace,
+                      workspace_bytes, as_stream(stream));
+}
+
+extern "C" int mxq_ptq_quant_pack(const void* W, void* Wq, uint8_t* codes, const float* colstat,
+                                  int64_t rows, int64_t cols, mxq_packed_t out, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  if (!Wq && rows > 0 && cols > 0) return MXQ_E_NULL;
+  return run_ptq_pack(W, Wq, codes, colstat, rows, cols, 16, 2, nullptr, &out, workspace,
+                      workspace_bytes, as_stream(stream));
 }
 
 extern "C" int mxq_rowquant(const float* x, float* y, uint8_t* codes, float* scale, float* zero,

@@ -62,8 +62,9 @@ class MXQGPT:
             raise TypeError("MXQGPT.fasterquant expects an fp16 layer (main.py loads the model in fp16)")
         colstat = self.diagH if self.nsamples > 0 else None
         if pack:
-            self.packed = ops.pack(W, colstat)
-        Wq = ops.ptq_quant(W, colstat, low_bits=2, group=16)
+            Wq, self.packed = ops.ptq_quant_pack(W, colstat)
+        else:
+            Wq = ops.ptq_quant(W, colstat, low_bits=2, group=16)
         self.layer.weight.data = Wq.reshape(self.layer.weight.shape).to(self.layer.weight.data.dtype)
 
     def free(self):

@@ -159,6 +159,28 @@ def pack(W: torch.Tensor, colstat: torch.Tensor | None = None, out: dict | None 
     return out
 
 
+def ptq_quant_pack(W: torch.Tensor, colstat: torch.Tensor | None = None, out=None, packed=None,
+                   workspace=None, return_codes: bool = False):
+    """fasterquant + pack in one pass over W: returns (Wq fp16, packed dict[, codes])."""
+    L.require_cuda(W, colstat)
+    if W.dtype != torch.float16:
+        raise TypeError("ptq_quant_pack expects fp16 weights")
+    W = W.contiguous()
+    rows, cols = W.shape
+    Wq = torch.empty_like(W) if out is None else out
+    if packed is None:
+        packed = alloc_packed(rows, cols, W.device)
+    codes = torch.empty(W.shape, dtype=torch.uint8, device=W.device) if return_codes else None
+    need = L.lib().mxq_ptq_workspace_bytes(rows, cols)
+    if workspace is None or workspace.numel() < need:
+        workspace = _ws(need, W.device)
+    rc = L.lib().mxq_ptq_quant_pack(L.ptr(W), L.ptr(Wq), L.ptr(codes), L.ptr(colstat), rows, cols,
+                                    L.packed_struct(packed), L.ptr(workspace), workspace.numel(),
+                                    L.stream())
+    L.check(rc, "mxq_ptq_quant_pack")
+    return (Wq, packed, codes) if return_codes else (Wq, packed)
+
+
 def _packed_dims(p: dict):
     OC = p["weight"].shape[0]
     IC = p["weight"].shape[1] * 16

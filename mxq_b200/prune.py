@@ -120,8 +120,7 @@ class LinearQuantJob:
 
     def run(self, W: torch.Tensor, colstat: torch.Tensor):
         """fasterquant + pack of one linear into this job's buffers (W is left untouched)."""
-        ops.pack(W, colstat, out=self.packed, workspace=self.ws)
-        ops.ptq_quant(W, colstat, out=self.Wq, workspace=self.ws)
+        ops.ptq_quant_pack(W, colstat, out=self.Wq, packed=self.packed, workspace=self.ws)
         return self.Wq, self.packed
 
 
@@ -139,9 +138,10 @@ def llama_linears(hidden: int, inter: int, kv_hidden: int | None = None):
 class LlamaLayerPTQ:
     """The mxq work of one decoder layer given its captured linear inputs: 4 activation statistics
     (what the 7 MXQGPT.add_batch hooks compute, prune.py:389-402) + fasterquant + pack of the 7
-    linears (prune.py:404-414).  Kernels launched per layer: 4 x 2 (statistics) + 7 x 6."""
+    linears (prune.py:404-414).  Kernels launched per layer: 4 x 2 (statistics) + 7 x 3 (dead
+    mask, pool pre-pass, fused quantize+pack tile kernel)."""
 
-    LAUNCHES_PER_LAYER = 4 * 2 + 7 * 6
+    LAUNCHES_PER_LAYER = 4 * 2 + 7 * 3
 
     def __init__(self, hidden: int, inter: int, device, max_tokens: int, kv_hidden=None):
         self.linears = llama_linears(hidden, inter, kv_hidden)

@@ -135,3 +135,22 @@ def test_error_behaviour(cuda):
     with pytest.raises(NotImplementedError):
         MXAsymQuantizer.apply(torch.zeros(2, 4, 64, device=cuda), clip, 2, False)
     assert ops.fakequant_fwd(torch.zeros(0, 64, device=cuda)).shape == (0, 64)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16", "fp16"])
+def test_wide_dynamic_range_rows(cuda, dtype):
+    """Row scales from 1e-6 to 1e2 (fp16: 1e-3..1e2): exercises the reciprocal/division path over
+    many exponents, alpha comparable to the 1e-8 epsilon, and exact ties."""
+    from mxq_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    rows, cols = 512, 1024
+    lo = -3.0 if dtype == "fp16" else -6.0
+    scale = 10.0 ** (torch.rand(rows, 1, generator=g) * (2.0 - lo) + lo)
+    x = torch.randn(rows, cols, generator=g) * scale
+    x[::7] = torch.round(x[::7] / scale[::7] * 6) / 6 * scale[::7]      # many exact .5 ties after scaling
+    x = x.to(TD[dtype])
+    want, q, *_ = O.fakequant_fwd(x.float().numpy(), dtype, 2, return_aux=True)
+    out, codes = ops.fakequant_fwd(x.to(cuda), return_codes=True)
+    assert np.array_equal(codes.cpu().numpy(), q.astype(np.uint8))
+    assert bits_equal(to_np(out), want)
+    assert bits_equal(to_np(ops.fakequant_fwd(x.to(cuda))), want)        # no-codes kernel variant

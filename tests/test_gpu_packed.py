@@ -114,3 +114,19 @@ def test_awq_gemv(cuda, G):
     y = engine.gemv_forward_cuda(torch.from_numpy(x).to(cuda), torch.from_numpy(kernel.view(np.int32)).to(cuda),
                                  torch.from_numpy(scales).to(cuda), torch.from_numpy(zeros.view(np.int32)).to(cuda), G)
     assert _rel_err(y.cpu().numpy(), ref) <= TOL
+
+
+@pytest.mark.parametrize("shape", [(64, 256), (32, 4096 + 128), (4096, 4096)])
+def test_fused_quant_pack_equals_separate(cuda, shape):
+    """mxq_ptq_quant_pack (one pass over W) == mxq_ptq_quant + mxq_pack, bit for bit."""
+    from mxq_b200 import ops
+    torch.manual_seed(shape[1])
+    W = (torch.randn(*shape, device=cuda) * 0.02).half()
+    stat = torch.ones(shape[1], device=cuda)
+    stat[[3, shape[1] - 1]] = 0
+    Wq, p, codes = ops.ptq_quant_pack(W, stat, return_codes=True)
+    Wq2, codes2 = ops.ptq_quant(W, stat, return_codes=True)
+    p2 = ops.pack(W, stat)
+    assert torch.equal(Wq, Wq2) and torch.equal(codes, codes2)
+    for k in p:
+        assert torch.equal(p[k], p2[k]), k
