@@ -197,11 +197,14 @@ __global__ void __launch_bounds__(kFQThreads) fakequant_fwd_kernel(const FQParam
             s2 = P::kS15; ch2 = P::kC15hi; cl2 = P::kC15lo;
           }
           const uint32_t w[4] = {ch.x, ch.y, ch.z, ch.w};
+          const f32x2 na_2 = pk2(-a, -a), r_2 = pk2(r, r);
           uint32_t o[4], cw[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint32_t t2 = P::sub(w[i], b2);                            // x - beta
-            const uint32_t n2 = P::pack(div_rn_by(P::lo(t2), a, r), div_rn_by(P::hi(t2), a, r));
+            float n_lo, n_hi;
+            upk2(div2_rn_by(pk2(P::lo(t2), P::hi(t2)), na_2, r_2), n_lo, n_hi);
+            const uint32_t n2 = P::pack(n_lo, n_hi);
             const uint32_t m2 = P::add(P::mul(n2, s2), P::kMagic);           // round-half-even
             const uint32_t q2 = P::sub(m2, P::kMagic);
             const uint32_t v2 = P::fma(q2, ch2, P::mul(q2, cl2));            // == RN16(RN32(q / s))
@@ -239,6 +242,34 @@ __global__ void __launch_bounds__(kFQThreads) fakequant_fwd_kernel(const FQParam
           float r = rcp_rn_normal(a);
           float s = s_low, rs = rs_low;
           if (pooled) { a = a_pool; b = b_pool; r = r_pool; s = s_pool; rs = rs_pool; }
+          if (sizeof(T) == 4) {
+            // fp32: the chain on packed FADD2/FMUL2/FFMA2 (two elements per instruction)
+            const f32x2 b_2 = pk2(b, b), a_2 = pk2(a, a), na_2 = pk2(-a, -a), r_2 = pk2(r, r);
+            const f32x2 s_2 = pk2(s, s), ns_2 = pk2(-s, -s), rs_2 = pk2(rs, rs);
+            const f32x2 nm_2 = pk2(-12582912.0f, -12582912.0f);
+            float o4[4];
+            uint32_t cw4 = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const f32x2 t = sub2(pk2(f[2 * h], f[2 * h + 1]), b_2);
+              const f32x2 u = mul2(div2_rn_by(t, na_2, r_2), s_2);
+              float u0, u1;
+              upk2(u, u0, u1);
+              const float m0 = __fadd_rn(u0, 12582912.0f), m1 = __fadd_rn(u1, 12582912.0f);
+              const f32x2 q = add2(pk2(m0, m1), nm_2);
+              const f32x2 w = mul2(div2_rn_by(q, ns_2, rs_2), a_2);
+              float w0, w1;
+              upk2(w, w0, w1);
+              o4[2 * h] = __fadd_rn(w0, b);
+              o4[2 * h + 1] = __fadd_rn(w1, b);
+              if (kCodes)
+                cw4 |= ((__float_as_uint(m0) & 0xFFu) | ((__float_as_uint(m1) & 0xFFu) << 8)) << (16 * h);
+            }
+            st_stream(orow + c * 16, make_uint4(__float_as_uint(o4[0]), __float_as_uint(o4[1]),
+                                                __float_as_uint(o4[2]), __float_as_uint(o4[3])));
+            if (kCodes) *reinterpret_cast<uint32_t*>(crow + c * 4) = cw4;
+            continue;
+          }
           float o[EPC];
           uint32_t cw[EPC / 4] = {};
 #pragma unroll
@@ -398,16 +429,16 @@ extern "C" int mxq_fakequant_fwd(const void* x, void* out, uint8_t* codes, int64
   const int tail = 8 * 8 + 8 * 8 + ((ng + 15) & ~15);
   const int max_smem = 227 * 1024;
   if (p.stage_bytes + tail > max_smem) return MXQ_E_UNSUPPORTED;
-  int stages = 98304 / p.stage_bytes;
-  if (stages < 1) stages = 1;
-  if (stages > 4) stages = 4;
-  while (stages < 2 && (stages + 1) * p.stage_bytes + tail <= max_smem) ++stages;
+  // two stages per CTA (one being consumed, one in flight) and as many CTAs per SM as registers
+  // allow: the kernel is issue-bound, so resident warps matter more than pipeline depth
+  int stages = 2;
+  if (stages * p.stage_bytes + tail > max_smem) stages = 1;
   p.stages = stages;
   p.num_sets = (int)ceil_div(rows, teams);
   const int smem = stages * p.stage_bytes + tail;
   int bps = (228 * 1024) / (smem + 1024);
   if (bps < 1) bps = 1;
-  if (bps > 8) bps = 8;
+  if (bps > 5) bps = 5;   // 48 regs x 256 threads -> 5 CTAs per SM
   int grid = kNumSMs * bps;
   if (grid > p.num_sets) grid = p.num_sets;
   cudaStream_t st = as_stream(stream);

@@ -36,7 +36,9 @@ constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr int NUM_DEQ_WARPS = 8;
 constexpr int THREADS = 32 * (2 + NUM_DEQ_WARPS);
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int STG_PITCH = 80;                 // bytes per row of the per-warp transpose buffer (4 x 16 B + pad)
+constexpr int STG_BYTES = NUM_DEQ_WARPS * 32 * STG_PITCH;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + STG_BYTES;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_mxq_kernel(const __grid_const
   uint64_t* empty = bars + 2 * STAGES;     // [STAGES]
   uint64_t* tmem_full = bars + 3 * STAGES; // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+  uint8_t* stage_base = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -247,39 +250,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_mxq_kernel(const __grid_const
       const uint32_t z4magic = (0x6400u | z4) * 0x00010001u;
       const uint32_t s4h2 = h2_bcast(row_ok ? s4 : 0.f);
 
-      auto meta_idx = [&](int kb, int& hw_idx, int& b_idx) {
-        const int chunk = kb >> 6, bp = kb & 63;
-        const int word = chunk * 32 + (bp & 31), ph = bp >> 5;
-        hw_idx = word * 2 + ph;
-        b_idx = word * 4 + ph;
-      };
-      // register prefetch of K block 0
-      uint4 wq = __ldg(wrow);
-      uint32_t wl = (uint32_t)__ldg(wlrow);
-      int hi, bi;
-      meta_idx(0, hi, bi);
-      uint32_t zs = __ldg(zsrow + hi);
-      uint32_t z2 = __ldg(z2row + bi);
-      float s2v[3] = {__half2float(__ldg(s2row)), __half2float(__ldg(s2row + 1)), __half2float(__ldg(s2row + 2))};
-
-      for (int kb = 0; kb < num_kb; ++kb) {
+      // dequantize one K block of this thread's row and publish it to the MMA warp
+      auto produce = [&](int kb, const uint4& cwq, uint32_t cwl, uint32_t czs, uint32_t cz2,
+                         float s20, float s21, float s22) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
-        // current block's operands
-        const uint4 cwq = wq;
-        const uint32_t cwl = wl, czs = zs, cz2 = z2;
-        const float cs2[3] = {s2v[0], s2v[1], s2v[2]};
-        if (kb + 1 < num_kb) {   // prefetch next block
-          wq = __ldg(wrow + kb + 1);
-          wl = (uint32_t)__ldg(wlrow + kb + 1);
-          meta_idx(kb + 1, hi, bi);
-          zs = __ldg(zsrow + hi);
-          z2 = __ldg(z2row + bi);
-          const __half* sp = s2row + (size_t)(kb + 1) * 3;
-          s2v[0] = __half2float(__ldg(sp)); s2v[1] = __half2float(__ldg(sp + 1)); s2v[2] = __half2float(__ldg(sp + 2));
-        }
         uint4 ch[8];
         const uint32_t ws[3] = {cwq.x, cwq.y, cwq.z};
+        const float cs2[3] = {s20, s21, s22};
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const uint32_t z1 = (czs >> (2 * k)) & 3;
@@ -290,7 +268,6 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_mxq_kernel(const __grid_const
         }
         ch[6] = dequant_4b(cwq.w, z4magic, s4h2);
         ch[7] = dequant_4b(cwl, z4magic, s4h2);
-
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* brow = smem_b + s * B_STAGE_BYTES + row_local * 128;
         const int sw = row_local & 7;
@@ -299,6 +276,104 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_mxq_kernel(const __grid_const
         fence_proxy_async();           // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_b[s]);
+      };
+
+      if ((nblk & 3) == 0) {
+        // ---- cooperative loads: 4 K blocks per group.  The 128-bit weight words are fetched with
+        // 4 lanes per row (64 contiguous bytes per row, 8 rows per request instead of 32 scattered
+        // rows) and transposed through a warp-private staging buffer; the per-row tail words and
+        // metadata are fetched as one 16-byte vector per lane per group.  Next group's loads are
+        // in flight while the current group is dequantized.
+        uint8_t* stg = stage_base + dw * (32 * STG_PITCH);
+        const int ngroups = nblk >> 2;
+        const int q = lane & 3, r8 = lane >> 2;
+        const uint4* wbase[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int orow = n0 + dw * 32 + 8 * i + r8;
+          orow = orow < p.OC ? orow : 0;
+          wbase[i] = reinterpret_cast<const uint4*>(p.w.weight + (size_t)orow * nblk * 4) + q;
+        }
+        const uint4* wl4 = reinterpret_cast<const uint4*>(wlrow);
+        const uint32_t* zsw = reinterpret_cast<const uint32_t*>(p.w.zeros_and_scales) + (size_t)ocs * 32 * nchunk;
+        const uint32_t* z2w = reinterpret_cast<const uint32_t*>(p.w.zeros_2nd) + (size_t)(ocs >> 2) * 32 * nchunk;
+        const uint2* s2v2 = reinterpret_cast<const uint2*>(s2row);
+        uint4 pw[4], pwl, pzs, pz2;
+        uint2 ps2[3];
+        auto fetch = [&](int g) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pw[i] = __ldg(wbase[i] + 4 * g);
+          pwl = __ldg(wl4 + g);
+          const int kb0 = 4 * g;
+          const int mword = (kb0 >> 6) * 32 + (kb0 & 31);
+          pzs = __ldg(reinterpret_cast<const uint4*>(zsw + mword));
+          pz2 = __ldg(reinterpret_cast<const uint4*>(z2w + mword));
+#pragma unroll
+          for (int i = 0; i < 3; ++i) ps2[i] = __ldg(s2v2 + 3 * g + i);
+        };
+        fetch(0);
+        for (int g = 0; g < ngroups; ++g) {
+          // transpose the weight words: lane (r8, q) holds rows 8i + r8, K block q
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(stg + (8 * i + r8) * STG_PITCH + q * 16) = pw[i];
+          const uint4 cwl = pwl, czs = pzs, cz2 = pz2;
+          const uint2 cs2[3] = {ps2[0], ps2[1], ps2[2]};
+          __syncwarp();
+          uint4 wq[4];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) wq[kk] = *reinterpret_cast<const uint4*>(stg + lane * STG_PITCH + kk * 16);
+          __syncwarp();
+          if (g + 1 < ngroups) fetch(g + 1);
+          const int hsh = (((4 * g) & 63) >> 5) * 16;   // metadata half-word of these 4 K blocks
+          const uint32_t wlw[4] = {cwl.x, cwl.y, cwl.z, cwl.w};
+          const uint32_t zsv[4] = {czs.x, czs.y, czs.z, czs.w};
+          const uint32_t z2v[4] = {cz2.x, cz2.y, cz2.z, cz2.w};
+          const uint32_t s2w[6] = {cs2[0].x, cs2[0].y, cs2[1].x, cs2[1].y, cs2[2].x, cs2[2].y};
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            // scales_2nd halves 3*kk .. 3*kk+2 of the group's 12
+            float sv[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const int hidx = 3 * kk + k;
+              const uint32_t wsel = s2w[hidx >> 1];
+              sv[k] = __half2float(__ushort_as_half((unsigned short)((hidx & 1) ? (wsel >> 16) : (wsel & 0xFFFF))));
+            }
+            produce(4 * g + kk, wq[kk], wlw[kk], (zsv[kk] >> hsh) & 0xFFFF, (z2v[kk] >> (hsh >> 1)) & 0xFF,
+                    sv[0], sv[1], sv[2]);
+          }
+        }
+      } else {
+        // ---- generic K (IC % 256 != 0): per-block scalar loads, one block of register prefetch
+        auto meta_idx = [&](int kb, int& hw_idx, int& b_idx) {
+          const int chunk = kb >> 6, bp = kb & 63;
+          const int word = chunk * 32 + (bp & 31), ph = bp >> 5;
+          hw_idx = word * 2 + ph;
+          b_idx = word * 4 + ph;
+        };
+        uint4 wq = __ldg(wrow);
+        uint32_t wl = (uint32_t)__ldg(wlrow);
+        int hi, bi;
+        meta_idx(0, hi, bi);
+        uint32_t zs = __ldg(zsrow + hi);
+        uint32_t z2 = __ldg(z2row + bi);
+        float s2v[3] = {__half2float(__ldg(s2row)), __half2float(__ldg(s2row + 1)), __half2float(__ldg(s2row + 2))};
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const uint4 cwq = wq;
+          const uint32_t cwl = wl, czs = zs, cz2 = z2;
+          const float c0 = s2v[0], c1 = s2v[1], c2 = s2v[2];
+          if (kb + 1 < num_kb) {
+            wq = __ldg(wrow + kb + 1);
+            wl = (uint32_t)__ldg(wlrow + kb + 1);
+            meta_idx(kb + 1, hi, bi);
+            zs = __ldg(zsrow + hi);
+            z2 = __ldg(z2row + bi);
+            const __half* sp = s2row + (size_t)(kb + 1) * 3;
+            s2v[0] = __half2float(__ldg(sp)); s2v[1] = __half2float(__ldg(sp + 1)); s2v[2] = __half2float(__ldg(sp + 2));
+          }
+          produce(kb, cwq, cwl, czs, cz2, c0, c1, c2);
+        }
       }
     }
     // ===== epilogue: TMEM -> registers -> fp16 -> global =====

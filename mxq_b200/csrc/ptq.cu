@@ -130,7 +130,6 @@ __global__ void __launch_bounds__(256) ptq_pack_tile_kernel(const TileParams p) 
   const float maxq_low = (float)((1 << p.low_bits) - 1);
   const float maxq_pool = (float)((1 << p.pool_bits) - 1);
   uint16_t* zs16 = reinterpret_cast<uint16_t*>(p.out.zeros_and_scales);
-  uint8_t* z2b = reinterpret_cast<uint8_t*>(p.out.zeros_2nd);
   __half* s2o = reinterpret_cast<__half*>(p.out.scales_2nd);
 
   for (int64_t u = warp0; u < units; u += wstride) {
@@ -248,7 +247,6 @@ __global__ void __launch_bounds__(256) ptq_pack_tile_kernel(const TileParams p) 
           *reinterpret_cast<uint4*>(p.out.weight + (size_t)row * nblk * 4 + (size_t)blk * 4) =
               make_uint4(word, w1, w2, w3);
           zs16[((size_t)row * 32 * nchunk + mword) * 2 + ph] = (uint16_t)(meta | m1 | m2);
-          if ((row & 3) == 0) z2b[((size_t)(row >> 2) * 32 * nchunk + mword) * 4 + ph] = 0;  // z2 == 0 policy
         } else if (k == 3) {
           p.out.weight_last[(size_t)row * nblk + blk] = (int32_t)word_last;
         }
@@ -362,9 +360,11 @@ static int run_ptq_pack(const void* W, void* Wq, uint8_t* codes, const float* co
   float2* pack_pool = (float2*)((uint8_t*)pool_mm + align16((size_t)rows * sizeof(float2)));
   const int nblk = (int)(cols / 64);
   const int nchunk = (nblk + 63) / 64;
-  if (pack && (nblk % 64)) {  // padding half-words of the last metadata chunk
-    cudaMemsetAsync(packed->zeros_and_scales, 0, (size_t)rows * 32 * nchunk * 4, st);
+  if (pack) {
+    // z2 == 0 policy: the whole zeros_2nd tensor is zero (its upper half-words are unused by the
+    // layout); zeros_and_scales only has padding half-words in a ragged last metadata chunk.
     cudaMemsetAsync(packed->zeros_2nd, 0, (size_t)(rows / 4) * 32 * nchunk * 4, st);
+    if (nblk % 64) cudaMemsetAsync(packed->zeros_and_scales, 0, (size_t)rows * 32 * nchunk * 4, st);
   }
   dead_mask_kernel<<<(unsigned)ceil_div(cols, 256), 256, 0, st>>>(colstat, dead, (int)cols);
   const unsigned gridA = (unsigned)ceil_div(rows, 8);

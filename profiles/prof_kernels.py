@@ -41,9 +41,8 @@ if "ptq" in which or "pack" in which:
         if "ptq" in which:
             ops.ptq_quant(W, stat)
         if "pack" in which:
-            ops.pack(W, stat)
-    ops.ptq_quant(W2, None)
-    ops.pack(W2, None)
+            ops.ptq_quant_pack(W, stat)
+    ops.ptq_quant_pack(W2, None)
 if "gemv" in which or "gemm" in which:
     def rand_packed(oc, ic):
         p = {}
