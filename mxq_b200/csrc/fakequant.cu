@@ -14,6 +14,7 @@
 // correctly-rounded reciprocal + one Markstein correction (common.cuh), round-half-even by the
 // magic-constant add.  Each intermediate is rounded to the tensor dtype like the reference's
 // separate ATen kernels do.
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -419,8 +420,12 @@ extern "C" int mxq_fakequant_fwd(const void* x, void* out, uint8_t* codes, int64
   p.lpg_shift = 0;
   while ((1 << p.lpg_shift) < p.lpg) ++p.lpg_shift;
   p.low_bits = low_bits; p.pool_bits = 4;
+  // rows per stage: measured best on B200 (profiles/sweep_fq.py): 32 KB sets for fp32, 16 KB for
+  // 16-bit tensors, 2 stages, up to 4 CTAs per SM
+  int team_bytes = esize == 4 ? 32768 : 16384;
+  if (const char* e = getenv("MXQ_FQ_TEAM_BYTES")) team_bytes = atoi(e);
   int teams = 8;
-  while (teams > 1 && (int64_t)teams * p.row_bytes > 16384) teams >>= 1;
+  while (teams > 1 && (int64_t)teams * p.row_bytes > team_bytes) teams >>= 1;
   p.teams = teams; p.tw = 8 / teams;
   p.tw_shift = 0;
   while ((1 << p.tw_shift) < p.tw) ++p.tw_shift;
@@ -432,13 +437,15 @@ extern "C" int mxq_fakequant_fwd(const void* x, void* out, uint8_t* codes, int64
   // two stages per CTA (one being consumed, one in flight) and as many CTAs per SM as registers
   // allow: the kernel is issue-bound, so resident warps matter more than pipeline depth
   int stages = 2;
-  if (stages * p.stage_bytes + tail > max_smem) stages = 1;
+  if (const char* e = getenv("MXQ_FQ_STAGES")) stages = atoi(e);   // tuning knob (profiles/sweep_fq.py)
+  while (stages > 1 && stages * p.stage_bytes + tail > max_smem) --stages;
   p.stages = stages;
   p.num_sets = (int)ceil_div(rows, teams);
   const int smem = stages * p.stage_bytes + tail;
   int bps = (228 * 1024) / (smem + 1024);
   if (bps < 1) bps = 1;
-  if (bps > 5) bps = 5;   // 48 regs x 256 threads -> 5 CTAs per SM
+  if (bps > 4) bps = 4;
+  if (const char* e = getenv("MXQ_FQ_BPS")) { const int v = atoi(e); if (v >= 1 && v < bps) bps = v; }
   int grid = kNumSMs * bps;
   if (grid > p.num_sets) grid = p.num_sets;
   cudaStream_t st = as_stream(stream);
