@@ -134,7 +134,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ptq", choices=["ptq"])
+    ap.add_argument("--workload", default="ptq", choices=["ptq", "gemm70b"])
     ap.add_argument("--no-components", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--layers", type=int, default=LAYERS, help="(debug) fewer layers; default is the named config")
@@ -144,6 +144,8 @@ def main():
         print(f"note: warmup {args.warmup} < 3 breaks the timing rules", file=sys.stderr)
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "gemm70b":
+        return run_gemm70b(args)
 
     import torch
     import torch.distributed as dist
@@ -282,6 +284,102 @@ def main():
             "job_bytes_per_step": job_bytes, "layers_per_s": args.layers / (ms_step * 1e-3),
             "components": components,
         }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_gemm70b(args):
+    """BASELINE configs[4]: Llama-2-70B-shape packed dequant-GEMM (M = 2048), output columns sharded
+    over the ranks, result all-gathered over NVLink -- GEMM only, GEMM + NCCL all-gather, and the
+    fused peer-store epilogue.  Device-timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from mxq_b200 import dist as mdist, ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    M = 2048
+    shapes = {"q/o_proj": (8192, 8192), "k/v_proj": (1024, 8192), "gate/up_proj": (28672, 8192), "down_proj": (8192, 28672)}
+    out = {}
+    tot_flops, tot_ms = 0.0, {"gemm": 0.0, "nccl": 0.0, "p2p": 0.0}
+
+    def rand_packed(oc, ic):
+        p = {}
+        for k, (s, d) in ops.packed_shapes(oc, ic).items():
+            if d == torch.float16:
+                p[k] = (torch.rand(s, device=dev) * 0.009 + 0.001).half()
+            else:
+                p[k] = torch.randint(-2 ** 31, 2 ** 31 - 1, s, device=dev, dtype=torch.int64).to(torch.int32)
+        return p
+
+    def timed(fn, iters):
+        for _ in range(max(3, args.warmup)):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / iters], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for name, (oc, ic) in shapes.items():
+        ocl = oc // world
+        p = rand_packed(ocl, ic)
+        x = torch.randn(M, ic, device=dev).half()
+        ws = torch.zeros(4096, dtype=torch.uint8, device=dev)
+        y = torch.empty(M, ocl, device=dev, dtype=torch.float16)
+        flops = 2.0 * M * oc * ic
+        r = {"flops": flops}
+        r["gemm_ms"] = timed(lambda: ops.gemm(x, p, out=y, workspace=ws, validate=False), args.steps)
+        modes = ["nccl", "p2p"] if world > 1 else []
+        for mode in modes:
+            try:
+                lin = mdist.ColumnShardedMXQLinear(p, oc, mode=mode)
+                lin(x)
+                r[mode + "_ms"] = timed(lambda: lin(x), args.steps)
+            except Exception as e:
+                r[mode + "_error"] = repr(e)[:200]
+        r["gemm_TFLOPs"] = flops / r["gemm_ms"] / 1e9
+        for mode in modes:
+            if mode + "_ms" in r:
+                r[mode + "_TFLOPs"] = flops / r[mode + "_ms"] / 1e9
+                tot_ms[mode] += r[mode + "_ms"]
+        tot_ms["gemm"] += r["gemm_ms"]
+        tot_flops += flops
+        out[name] = r
+        del p, x, y
+    best = "p2p" if tot_ms["p2p"] > 0 and (tot_ms["nccl"] == 0 or tot_ms["p2p"] <= tot_ms["nccl"]) else ("nccl" if tot_ms["nccl"] > 0 else "gemm")
+    if world > 1 and any((best + "_ms") not in r for r in out.values()):
+        best = "nccl"
+    value = tot_flops / tot_ms[best] / 1e9
+    if rank == 0:
+        line = {"metric": "mxq_dequant_gemm_70b_TFLOPs", "value": value, "unit": "TFLOP/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": tot_ms[best], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                "config": {"workload": "Llama-2-70B-shape packed mixed 2/4-bit dequant-GEMM, M=2048, output columns sharded + gathered",
+                           "exchange": best, "shapes": {k: list(v) for k, v in shapes.items()}},
+                "roofline": {"bound": "tensor", "achieved": tot_flops / tot_ms["gemm"] / 1e9 / world, "peak": pk["tf_burst"],
+                             "unit": "TFLOP/s", "frac": tot_flops / tot_ms["gemm"] / 1e9 / world / pk["tf_burst"],
+                             "traffic": None, "note": "per-GPU GEMM-only rate vs measured cuBLAS bf16 burst peak"},
+                "gemm_only_TFLOPs": tot_flops / tot_ms["gemm"] / 1e9,
+                "nccl_TFLOPs": tot_flops / tot_ms["nccl"] / 1e9 if tot_ms["nccl"] else None,
+                "p2p_TFLOPs": tot_flops / tot_ms["p2p"] / 1e9 if tot_ms["p2p"] else None,
+                "per_shape": out, "gpu_launches": args.steps * len(shapes)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

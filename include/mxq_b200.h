@@ -152,6 +152,15 @@ MXQ_API size_t mxq_gemm_workspace_bytes(int64_t M, int64_t IC, int64_t OC);
 MXQ_API int mxq_gemm(const void* x, mxq_packed_t w, void* y, int64_t M, int64_t IC, int64_t OC,
              void* workspace, size_t workspace_bytes, void* stream);
 
+/* Column-sharded GEMM fused with its all-gather: this rank owns output columns
+ * [col0, col0 + OC) of a [M, ldy] result; the epilogue stores every tile into each of the `npeers`
+ * output buffers in y_peers (host array of device pointers: the local buffer and the peers'
+ * buffers mapped into this process over NVLink, e.g. torch symmetric memory).  The caller
+ * synchronises the ranks afterwards (the library never does). */
+MXQ_API int mxq_gemm_scatter(const void* x, mxq_packed_t w, void* const* y_peers, int npeers,
+                             int64_t M, int64_t IC, int64_t OC, int64_t ldy, int64_t col0,
+                             void* stream);
+
 /* Diagnostic: the same tcgen05/TMA pipeline with a dense fp16 B operand W[OC, IC] loaded by TMA
  * instead of dequantized in registers (y = x @ W^T).  Separates UMMA-descriptor errors from
  * dequant/swizzle errors in tests; not part of the reference surface. */

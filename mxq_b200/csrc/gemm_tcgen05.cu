@@ -146,10 +146,13 @@ __device__ __forceinline__ uint4 dequant_4b(uint32_t w, uint32_t zmagic, uint32_
   return make_uint4(prmt(h[0], h[1], 0x5410), prmt(h[2], h[3], 0x5410), prmt(h[0], h[1], 0x7632), prmt(h[2], h[3], 0x7632));
 }
 
+constexpr int MAX_PEERS = 8;
 struct Params {
   mxq_packed_t w;
-  const __half* wdense;   // dense-B debug path only
-  __half* y;
+  const __half* wdense;      // dense-B debug path only
+  __half* y[MAX_PEERS];      // output base pointers: [0] local; > 1 entries = peers' buffers mapped
+  int npeers;                //   over NVLink (fused column all-gather: every tile is stored to all)
+  int ldy, col0;             // output row stride (elements) and first output column of this shard
   int M, IC, OC;
 };
 
@@ -382,7 +385,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_mxq_kernel(const __grid_const
     const int half = dw >> 2;                 // accumulator (token half)
     const int quad = warp & 3;                // TMEM lane quarter this warp may access
     const int token = m0 + half * 128 + quad * 32 + lane;
-    __half* yrow = p.y + (size_t)token * p.OC + n0;
+    const size_t yoff = (size_t)token * p.ldy + p.col0 + n0;
 #pragma unroll 1
     for (int cb = 0; cb < BN / 32; ++cb) {
       uint32_t v[32];
@@ -398,7 +401,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_mxq_kernel(const __grid_const
 #pragma unroll
             for (int e = 0; e < 4; ++e)
               oh[e] = __floats2half2_rn(__uint_as_float(v[q * 8 + 2 * e]), __uint_as_float(v[q * 8 + 2 * e + 1]));
-            *reinterpret_cast<uint4*>(yrow + cb * 32 + q * 8) = o;
+            // local store, or one store per peer buffer (st.global on NVLink-mapped addresses)
+            for (int pe = 0; pe < p.npeers; ++pe)
+              *reinterpret_cast<uint4*>(p.y[pe] + yoff + cb * 32 + q * 8) = o;
           }
         }
       }
@@ -473,7 +478,31 @@ extern "C" int mxq_gemm(const void* x, mxq_packed_t w, void* y, int64_t M, int64
   if (!w.weight_last || !w.zeros_and_scales || !w.zeros_2nd || !w.scales_2nd || !w.scales_4b || !w.zeros_4b)
     return MXQ_E_NULL;
   if (IC % 64 || IC == 0 || OC % 8 || M > INT32_MAX || OC > INT32_MAX || IC > (1 << 24)) return MXQ_E_SHAPE;
-  gemm::Params p{w, nullptr, (__half*)y, (int)M, (int)IC, (int)OC};
+  gemm::Params p{};
+  p.w = w; p.y[0] = (__half*)y; p.npeers = 1; p.ldy = (int)OC; p.col0 = 0;
+  p.M = (int)M; p.IC = (int)IC; p.OC = (int)OC;
+  return gemm::launch<false>(x, p, as_stream(stream));
+}
+
+extern "C" int mxq_gemm_scatter(const void* x, mxq_packed_t w, void* const* y_peers, int npeers,
+                                int64_t M, int64_t IC, int64_t OC, int64_t ldy, int64_t col0,
+                                void* stream) {
+  if (M < 0 || IC < 0 || OC < 0) return MXQ_E_SHAPE;
+  if (M == 0 || OC == 0) return MXQ_OK;
+  MXQ_CHECK_PTR(x);
+  MXQ_CHECK_PTR(w.weight);
+  if (!y_peers || !w.weight_last || !w.zeros_and_scales || !w.zeros_2nd || !w.scales_2nd || !w.scales_4b || !w.zeros_4b)
+    return MXQ_E_NULL;
+  if (npeers < 1 || npeers > gemm::MAX_PEERS) return MXQ_E_SHAPE;
+  if (IC % 64 || IC == 0 || OC % 8 || ldy % 8 || col0 % 8 || col0 + OC > ldy || ldy > INT32_MAX) return MXQ_E_SHAPE;
+  gemm::Params p{};
+  p.w = w;
+  for (int i = 0; i < npeers; ++i) {
+    MXQ_CHECK_PTR(y_peers[i]);
+    p.y[i] = (__half*)y_peers[i];
+  }
+  p.npeers = npeers; p.ldy = (int)ldy; p.col0 = (int)col0;
+  p.M = (int)M; p.IC = (int)IC; p.OC = (int)OC;
   return gemm::launch<false>(x, p, as_stream(stream));
 }
 
@@ -485,7 +514,8 @@ extern "C" int mxq_gemm_dense(const void* x, const void* W, void* y, int64_t M, 
   MXQ_CHECK_PTR(W);
   MXQ_CHECK_PTR(y);
   if (IC % 64 || IC == 0 || OC % 8) return MXQ_E_SHAPE;
-  mxq_packed_t none{};
-  gemm::Params p{none, (const __half*)W, (__half*)y, (int)M, (int)IC, (int)OC};
+  gemm::Params p{};
+  p.wdense = (const __half*)W; p.y[0] = (__half*)y; p.npeers = 1; p.ldy = (int)OC; p.col0 = 0;
+  p.M = (int)M; p.IC = (int)IC; p.OC = (int)OC;
   return gemm::launch<true>(x, p, as_stream(stream));
 }

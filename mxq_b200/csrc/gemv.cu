@@ -7,13 +7,17 @@
 //     a lane's 128-bit weight load, its 4-bit tail word and its metadata are issued up front for
 //     all 4 rows (>= 100 B in flight per lane) and the activations of the block are loaded once
 //     for the 4 rows;
-//   * dequant two codes per LOP3 into fp16 {1024+q} pairs, one HADD2 removes 1024+z1 exactly,
-//     and FHFMA (fma.rn.f32.f16, sm_100) accumulates in fp32 -- no int->float conversions;
+//   * dequant two codes per SHF+LOP3 into fp16 {bias+q} pairs (code in the top mantissa bits) that
+//     FHFMA (fma.rn.f32.f16, sm_100) multiplies straight into an fp32 accumulator -- no
+//     int->float conversions, no per-weight subtraction; bias and zero-point are removed once per
+//     (row, group) with the group's activation sum;
 //   * the scale s2*(c - z2) is applied once per (row, group) on the fp32 group sum;
 //   * K-slices of a row group are reduced through shared memory in a fixed order.
 // Any IC % 64 == 0 (metadata tiled in 4096-column chunks; identical to the reference at 4096);
 // the reference's activation-offset and batch-stride bugs (gemv_mxq_cuda.cu:50,119) are not
 // reproduced.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mxq {
@@ -40,26 +44,47 @@ __device__ __forceinline__ uint32_t hsub2_u32(uint32_t a, uint32_t b) {
 
 constexpr int kGemvWarps = 8;
 
-// x16: the 16 activations of one group as 8 half2 words (cols 0..15 in order).
-// 2-bit word: code j at bits [2j+1:2j]; pair extraction (w >> 2j) & 0x00030003 gives codes j, j+8.
-__device__ __forceinline__ float dot_group_2b(uint32_t w, uint32_t zmagic, const uint32_t* x16) {
+// Dequant without subtraction: a code is moved to the TOP mantissa bits of an fp16 whose exponent
+// makes one mantissa step equal to 1, so the register already holds the number bias + q
+// (bias 4 for 2-bit codes, 16 for 4-bit codes) and FHFMA consumes it directly.  The bias and the
+// zero-point are removed once per (row, group) on the fp32 group sum:
+//     sum_j (q_j - z) x_j = sum_j (bias + q_j) x_j - (bias + z) * sum_j x_j
+// (fp32 accumulation loses only log2(bias) bits to the cancellation).
+//
+// x16: 16 activations of one group as 8 half2 words (cols 0..15 in order).
+// 2-bit word: code j at bits [2j+1:2j]; shifting by 8-2j puts code j at bits [9:8] of the low
+// half and code j+8 at bits [9:8] of the high half.
+__device__ __forceinline__ float dot_group_2b(uint32_t w, const uint32_t* x16) {
   float p = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const uint32_t h = hsub2_u32(lop3_and_or(w >> (2 * j), 0x00030003u, 0x64006400u), zmagic);
-    p = fhfma_sel(h, 0, x16[j >> 1], j & 1, p);              // col j
-    p = fhfma_sel(h, 1, x16[(j + 8) >> 1], (j + 8) & 1, p);  // col j + 8
+    const uint32_t t = (8 - 2 * j) >= 0 ? (w << (8 - 2 * j)) : (w >> (2 * j - 8));
+    const uint32_t h = lop3_and_or(t, 0x03000300u, 0x44004400u);   // {4 + q_j, 4 + q_{j+8}}
+    p = fhfma_sel(h, 0, x16[j >> 1], j & 1, p);
+    p = fhfma_sel(h, 1, x16[(j + 8) >> 1], (j + 8) & 1, p);
   }
   return p;
 }
-// 4-bit word: nibble j at bits [4j+3:4j]; (w >> 4j) & 0x000F000F gives nibbles j, j+4.
-__device__ __forceinline__ float dot_word_4b(uint32_t w, uint32_t zmagic, const uint32_t* x8,
-                                             float p) {
+// 4-bit word: nibble j at bits [4j+3:4j]; shifting by 6-4j puts nibble j at bits [9:6] of the low
+// half and nibble j+4 at bits [9:6] of the high half: {16 + n_j, 16 + n_{j+4}}.
+__device__ __forceinline__ float dot_word_4b(uint32_t w, const uint32_t* x8, float p) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const uint32_t h = hsub2_u32(lop3_and_or(w >> (4 * j), 0x000F000Fu, 0x64006400u), zmagic);
+    const uint32_t t = (6 - 4 * j) >= 0 ? (w << (6 - 4 * j)) : (w >> (4 * j - 6));
+    const uint32_t h = lop3_and_or(t, 0x03C003C0u, 0x4C004C00u);
     p = fhfma_sel(h, 0, x8[j >> 1], j & 1, p);
     p = fhfma_sel(h, 1, x8[(j + 4) >> 1], (j + 4) & 1, p);
+  }
+  return p;
+}
+// sum of the 2n halves held in n words, fp32
+template <int N>
+__device__ __forceinline__ float sum_halves(const uint32_t* x) {
+  float p = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    p = fhfma_sel(0x3C003C00u, 0, x[i], 0, p);
+    p = fhfma_sel(0x3C003C00u, 0, x[i], 1, p);
   }
   return p;
 }
@@ -87,13 +112,11 @@ __global__ void __launch_bounds__(kGemvWarps * 32) gemv_mxq_kernel(
     const int oc0 = grp * 4;
     const __half* s4p = reinterpret_cast<const __half*>(w.scales_4b) + oc0;
     const uint32_t z4w = (uint32_t)w.zeros_4b[oc0 >> 3] >> (4 * (oc0 & 7));
-    float s4[4];
-    uint32_t z4magic[4];
+    float s4[4], z4b[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       s4[r] = __half2float(s4p[r]);
-      const uint32_t z = (z4w >> (4 * r)) & 0xF;
-      z4magic[r] = (0x6400u | z) * 0x00010001u;   // fp16 1024 + z in both halves
+      z4b[r] = __uint_as_float(0x41800000u + (((z4w >> (4 * r)) & 0xF) << 19));   // 16 + z4
     }
     const uint16_t* zs16 = reinterpret_cast<const uint16_t*>(w.zeros_and_scales);
     const uint8_t* z2b = reinterpret_cast<const uint8_t*>(w.zeros_2nd);
@@ -119,6 +142,7 @@ __global__ void __launch_bounds__(kGemvWarps * 32) gemv_mxq_kernel(
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         uint32_t xv[NB][8];
+        float xs[NB];
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
           const int bb = min(b0 + b, B - 1);
@@ -126,24 +150,26 @@ __global__ void __launch_bounds__(kGemvWarps * 32) gemv_mxq_kernel(
           const uint4 v0 = __ldg(xp), v1 = __ldg(xp + 1);
           xv[b][0] = v0.x; xv[b][1] = v0.y; xv[b][2] = v0.z; xv[b][3] = v0.w;
           xv[b][4] = v1.x; xv[b][5] = v1.y; xv[b][6] = v1.z; xv[b][7] = v1.w;
+          xs[b] = sum_halves<8>(xv[b]);
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           if (k < 3) {
             const uint32_t wk = k == 0 ? wq[r].x : (k == 1 ? wq[r].y : wq[r].z);
-            const uint32_t z1 = (zs[r] >> (2 * k)) & 3;
-            const float c = (float)((zs[r] >> (8 + 2 * k)) & 3);
-            const float zz = (float)((z2 >> (2 * k)) & 3);
-            const float scale = s2[k] * (c - zz);                   // gemv_mxq_cuda.cu:136
-            const uint32_t zmagic = (0x6400u | z1) * 0x00010001u;
+            const float zb = __uint_as_float(0x40800000u + (((zs[r] >> (2 * k)) & 3) << 21));   // 4 + z1
+            const int d = 3 + (int)((zs[r] >> (8 + 2 * k)) & 3) - (int)((z2 >> (2 * k)) & 3);   // 3 + c - z2
+            const float scale = s2[k] * (__uint_as_float(0x41000000u + ((uint32_t)d << 20)) - 11.0f);  // :136
 #pragma unroll
-            for (int b = 0; b < NB; ++b)
-              acc[r][b] = fmaf(scale, dot_group_2b(wk, zmagic, xv[b]), acc[r][b]);
+            for (int b = 0; b < NB; ++b) {
+              const float pz = fmaf(-zb, xs[b], dot_group_2b(wk, xv[b]));
+              acc[r][b] = fmaf(scale, pz, acc[r][b]);
+            }
           } else {
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-              float pz = dot_word_4b(wq[r].w, z4magic[r], xv[b], 0.f);
-              pz = dot_word_4b(wl[r], z4magic[r], xv[b] + 4, pz);
+              float pz = dot_word_4b(wq[r].w, xv[b], 0.f);
+              pz = dot_word_4b(wl[r], xv[b] + 4, pz);
+              pz = fmaf(-z4b[r], xs[b], pz);
               acc[r][b] = fmaf(s4[r], pz, acc[r][b]);               // :179,192
             }
           }
@@ -194,17 +220,18 @@ __global__ void __launch_bounds__(256) awq_gemv_kernel(const __half* __restrict_
     const int g = (c * 32) / G;
     const uint32_t z = (zeros[(size_t)oc * zw + (g >> 3)] >> (4 * (g & 7))) & 0xF;
     const float sc = __half2float(scales[(size_t)oc * zw * 8 + g]);
-    const uint32_t zmagic = (0x6400u | z) * 0x00010001u;
+    const float zb = __uint_as_float(0x41800000u + (z << 19));   // 16 + zero
     const uint4* xp = reinterpret_cast<const uint4*>(x + (size_t)b * IC + (size_t)c * 32);
     const uint32_t wd[4] = {wv.x, wv.y, wv.z, wv.w};
-    float p = 0.f;
+    float p = 0.f, xs = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const uint4 xv = __ldg(xp + i);
       const uint32_t xr[4] = {xv.x, xv.y, xv.z, xv.w};
-      p = dot_word_4b(wd[i], zmagic, xr, p);
+      p = dot_word_4b(wd[i], xr, p);
+      xs += sum_halves<4>(xr);
     }
-    acc = fmaf(sc, p, acc);
+    acc = fmaf(sc, fmaf(-zb, xs, p), acc);
   }
   acc = warp_sum(acc);
   if (lane == 0) y[(size_t)b * OC + oc] = __float2half_rn(acc);
@@ -229,6 +256,10 @@ extern "C" int mxq_gemv(const void* x, mxq_packed_t w, void* y, int64_t B, int64
   const int nblk = (int)(IC / 64);
   int KS = 1, ks_shift = 0;
   while (KS < kGemvWarps && nblk > 32 * KS) { KS <<= 1; ++ks_shift; }
+  if (const char* e = getenv("MXQ_GEMV_KS")) {   // tuning knob (profiles/sweep_gemv.py)
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8) { KS = v; ks_shift = v == 1 ? 0 : v == 2 ? 1 : v == 4 ? 2 : 3; }
+  }
   const int RG = kGemvWarps / KS;
   const unsigned gx = (unsigned)ceil_div(OC / 4, RG);
   cudaStream_t st = as_stream(stream);

@@ -1,0 +1,103 @@
+"""Multi-GPU plumbing for the sharded paths.  One process per GPU; torch.distributed
+(NCCL over NVLink on the GPU box, gloo in the CPU tests) carries the only exchange step.
+
+* PTQ pass            : decoder layers are independent -> `layer % world`, no data-path collective.
+* dequant-GEMM (70B)  : output columns (= weight rows with all their per-row / 4-row / 8-row
+                        metadata) are sharded, x is replicated, the [M, N/W] tiles are exchanged:
+                        either NCCL all-gather, or the GEMM epilogue stores its tile straight into
+                        every peer's output buffer over NVLink (symmetric memory, `mode="p2p"`).
+* QAT                 : data parallel, NCCL gradient all-reduce (torch DDP around QuantizeLinear).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+ROW_ALIGN = 16   # rows per shard must keep 4-row second-order groups, 8-row zeros_4b words and
+                 # 16-row packer tiles whole
+
+
+def layer_shard(n_layers: int, world: int, rank: int) -> list[int]:
+    """Layers owned by `rank` (round robin keeps the per-rank work within one layer of equal)."""
+    return [l for l in range(n_layers) if l % world == rank]
+
+
+def row_range(OC: int, world: int, rank: int) -> tuple[int, int]:
+    if OC % (world * ROW_ALIGN):
+        raise ValueError(f"out_features={OC} must be a multiple of world*{ROW_ALIGN}={world * ROW_ALIGN}")
+    n = OC // world
+    return rank * n, (rank + 1) * n
+
+
+def shard_packed_rows(p: dict, world: int, rank: int) -> dict:
+    """Slice a packed tensor set to the output rows of `rank` (contiguous copies)."""
+    OC = p["weight"].shape[0]
+    r0, r1 = row_range(OC, world, rank)
+    return dict(weight=p["weight"][r0:r1].contiguous(), weight_last=p["weight_last"][r0:r1].contiguous(),
+                zeros_and_scales=p["zeros_and_scales"][r0:r1].contiguous(),
+                zeros_2nd=p["zeros_2nd"][r0 // 4:r1 // 4].contiguous(),
+                scales_2nd=p["scales_2nd"][r0 // 4:r1 // 4].contiguous(),
+                scales_4b=p["scales_4b"][r0:r1].contiguous(), zeros_4b=p["zeros_4b"][r0 // 8:r1 // 8].contiguous())
+
+
+def gather_columns(y_local: torch.Tensor, group=None) -> torch.Tensor:
+    """[M, N/W] per rank -> [M, N] on every rank (all-gather along the column dimension)."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return y_local
+    M, n = y_local.shape
+    buf = torch.empty((world, M, n), dtype=y_local.dtype, device=y_local.device)
+    try:
+        dist.all_gather_into_tensor(buf, y_local.contiguous(), group=group)
+    except (RuntimeError, NotImplementedError):      # backends without the fused form
+        dist.all_gather(list(buf.unbind(0)), y_local.contiguous(), group=group)
+    return buf.permute(1, 0, 2).reshape(M, world * n)
+
+
+class ColumnShardedMXQLinear:
+    """y = x @ dequant(W)^T with W's output rows sharded over the process group."""
+
+    def __init__(self, packed_local: dict, OC_total: int, group=None, mode: str = "nccl"):
+        from . import ops
+        self.ops = ops
+        self.p = packed_local
+        self.OC_total = OC_total
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.OC_local, self.IC = ops._packed_dims(packed_local)
+        self.mode = mode
+        self._ws = None
+        self._symm = None
+
+    # -- fused path: the GEMM epilogue writes its tile into every peer's output over NVLink ------
+    def _symm_out(self, M: int, device):
+        if self._symm is not None and self._symm[0].shape[0] == M:
+            return self._symm
+        import torch.distributed._symmetric_memory as symm_mem
+        t = symm_mem.empty((M, self.OC_total), dtype=torch.float16, device=device)
+        grp = self.group if self.group is not None else dist.group.WORLD
+        try:
+            hdl = symm_mem.rendezvous(t, grp)
+        except TypeError:
+            hdl = symm_mem.rendezvous(t, grp.group_name)
+        self._symm = (t, hdl)
+        return self._symm
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        ops = self.ops
+        M = x.shape[0]
+        if self._ws is None:
+            self._ws = torch.zeros(4096, dtype=torch.uint8, device=x.device)
+        if self.world == 1:
+            return ops.gemm(x, self.p, workspace=self._ws, validate=False)
+        if self.mode == "p2p":
+            out, hdl = self._symm_out(M, x.device)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            ops.gemm_scatter(x, self.p, ptrs, ldy=self.OC_total, col0=self.rank * self.OC_local)
+            hdl.barrier(channel=0)          # all tiles have landed in every rank's buffer
+            return out
+        y_local = ops.gemm(x, self.p, workspace=self._ws, validate=False)
+        return gather_columns(y_local, self.group)
+
+    __call__ = forward

@@ -241,6 +241,19 @@ def gemm(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, workspace=No
     return out
 
 
+def gemm_scatter(x: torch.Tensor, p: dict, peer_ptrs: list, ldy: int, col0: int):
+    """Column-sharded GEMM whose epilogue stores the [M, OC_local] tile at column `col0` of every
+    [M, ldy] fp16 buffer in `peer_ptrs` (device addresses; peers mapped over NVLink)."""
+    import ctypes as C
+    OC, IC = _packed_dims(p)
+    L.require_cuda(x)
+    x = x.contiguous()
+    arr = (C.c_void_p * len(peer_ptrs))(*[int(a) for a in peer_ptrs])
+    rc = L.lib().mxq_gemm_scatter(L.ptr(x), L.packed_struct(p), arr, len(peer_ptrs), x.shape[0], IC, OC,
+                                  ldy, col0, L.stream())
+    L.check(rc, "mxq_gemm_scatter")
+
+
 def gemm_dense(x: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
     """Diagnostic: y = x @ W^T with dense fp16 W through the same tcgen05 pipeline as `gemm`."""
     L.require_cuda(x, W)

@@ -1,0 +1,67 @@
+"""GPU, world_size 2 (skipped on a 1-GPU box): column-sharded dequant-GEMM, NCCL all-gather and the
+fused peer-store epilogue, against the single-GPU GEMM on the unsharded tensors."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from mxq_b200 import dist as mdist, ops
+    from oracle import mxq_oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        OC, IC, M = 1024, 4096, 512
+        p = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in O.random_packed(OC, IC, seed=5).items()}
+        x = torch.from_numpy(np.random.default_rng(1).standard_normal((M, IC)).astype(np.float16)).to(dev)
+        ref = ops.gemm(x, p)
+        local = mdist.shard_packed_rows(p, world, rank)
+        res = {}
+        for mode in ("nccl", "p2p"):
+            try:
+                lin = mdist.ColumnShardedMXQLinear(local, OC, mode=mode)
+                y = lin(x)
+                torch.cuda.synchronize()
+                res[mode] = bool(torch.equal(y, ref))
+            except Exception as e:  # report, the parent decides
+                res[mode] = repr(e)[:300]
+        dist.barrier()
+        if rank == 0:
+            q.put(res)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_sharded_gemm(cuda):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert res["nccl"] is True, res
+    assert res["p2p"] is True, res

@@ -130,3 +130,36 @@ def test_fused_quant_pack_equals_separate(cuda, shape):
     assert torch.equal(Wq, Wq2) and torch.equal(codes, codes2)
     for k in p:
         assert torch.equal(p[k], p2[k]), k
+
+
+def _load_reference_ext():
+    import importlib.util
+    import os
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref",
+                      "mxq_inference_engine.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/mxq_inference_engine.so not built (python oracle/build_ref.py)")
+    spec = importlib.util.spec_from_file_location("mxq_inference_engine", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_matches_reference_cuda_kernel(cuda):
+    """The reference's own gemv_mxq kernel (compiled from its sources into oracle/_ref) on random
+    packed bits at IC = 4096, batch 1.  Its activation-offset bug (gemv_mxq_cuda.cu:119: the second
+    2048-column half re-reads x[0:2048]) is neutralised by an x whose two halves are equal; this pins
+    bit order, metadata positions and the decode formula against real reference code."""
+    from mxq_b200 import ops
+    ref = _load_reference_ext()
+    OC, IC = 512, 4096
+    p = packed_to_dev(O.random_packed(OC, IC, seed=7), cuda)
+    half = torch.randn(1, IC // 2, device=cuda).half()
+    x = torch.cat([half, half], dim=1).contiguous()
+    y_ref = ref.gemv_mxq_forward_cuda(x, p["weight"], p["weight_last"], p["zeros_and_scales"], p["scales_2nd"],
+                                      p["zeros_2nd"], p["scales_4b"], p["zeros_4b"], 16)
+    torch.cuda.synchronize()
+    y = ops.gemv(x, p)
+    assert y.shape == y_ref.shape
+    err = (y.float() - y_ref.float()).abs().max() / y_ref.float().abs().max()
+    assert float(err) <= TOL
