@@ -59,16 +59,34 @@ __global__ void __launch_bounds__(kCSThreads) colsumsq_partial_kernel(
     *reinterpret_cast<float4*>(dst + e) = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
 }
 
-__global__ void colsumsq_final_kernel(const float* __restrict__ partial, float* __restrict__ out,
-                                      int cols, int slabs, float prev_scale, float add_scale,
-                                      int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+// fold the slabs: block = 32 columns x 32 slab lanes (coalesced 128-byte rows of `partial`), fixed
+// summation order -> deterministic
+__global__ void __launch_bounds__(1024) colsumsq_final_kernel(const float* __restrict__ partial,
+                                                              float* __restrict__ out, int cols,
+                                                              int slabs, float prev_scale,
+                                                              float add_scale, int accumulate) {
+  __shared__ float red[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int k = 0; k < slabs; ++k) s += partial[(size_t)k * cols + c];
-  float v = add_scale * s;
-  if (accumulate) v = fmaf(prev_scale, out[c], v);
-  out[c] = v;
+  if (c < cols) {
+    int k = threadIdx.y;
+    for (; k + 96 < slabs; k += 128) {
+      const float a0 = partial[(size_t)k * cols + c], a1 = partial[(size_t)(k + 32) * cols + c];
+      const float a2 = partial[(size_t)(k + 64) * cols + c], a3 = partial[(size_t)(k + 96) * cols + c];
+      s += (a0 + a1) + (a2 + a3);
+    }
+    for (; k < slabs; k += 32) s += partial[(size_t)k * cols + c];
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
+    float v = add_scale * t;
+    if (accumulate) v = fmaf(prev_scale, out[c], v);
+    out[c] = v;
+  }
 }
 
 template <typename T>
@@ -129,7 +147,7 @@ extern "C" int mxq_colsumsq(const void* X, int64_t tokens, int64_t cols, int dty
     else
       colsumsq_partial_kernel<__nv_bfloat16><<<grid, kCSThreads, 0, st>>>(Xb, part, tokens, (int)cols, cpr, rows_per_slab);
   }
-  colsumsq_final_kernel<<<(unsigned)ceil_div(cols, 256), 256, 0, st>>>(
+  colsumsq_final_kernel<<<(unsigned)ceil_div(cols, 32), dim3(32, 32), 0, st>>>(
       (const float*)workspace, out, (int)cols, slabs, prev_scale, add_scale, accumulate);
   MXQ_LAUNCH_RESULT();
 }

@@ -200,41 +200,50 @@ __global__ void __launch_bounds__(256) ptq_pack_tile_kernel(const TileParams p) 
 
     if (kPack) {
       // ---- packed layout (encode policy: oracle pack_mxq) ----------------------------------
+      // One code path for the 2-bit slots (k < 3) and the 4-bit slot (k == 3): only the scale,
+      // zero-point, code range and code width differ per lane, so the warp never diverges.
+      const bool four = (k == 3);
+      const float maxq = four ? 15.f : 3.f;
+      // codes are assembled by Horner's rule on the raw float bits: m = 1.5*2^23 + code exactly, so
+      // bits(m) = 0x4B400000 + code and  word = sum_e code_e * radix^e = H - 0x4B400000 * sum_e radix^e
+      const uint32_t radix = four ? 16u : 4u;
+      const uint32_t horner_bias = 0x4B400000u * (four ? 0x11111111u : 0x00005555u);
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int row = tile * 16 + rr + 8 * i;
-        uint32_t word = 0, word_last = 0, meta = 0;
-        __half s2h = __float2half_rn(0.f);
-        // 2-bit slots: every lane runs the shuffles, slot 3 ignores the result
+        // second-order (4-row) scale of the 2-bit slots; slot 3 runs the shuffles but ignores them
         const float lo = fminf(mn[i], 0.f), hi = fmaxf(mx[i], 0.f);
         float s = fdiv(__fsub_rn(hi, lo), 3.f);
         if (s == 0.f) s = 1.f;
         float smax = s;
         smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, 4));
         smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, 8));
-        if (k < 3) {
-          s2h = __float2half_rn(fdiv(smax, 3.f));
-          const float s2f = __half2float(s2h);
-          const float c = clampf(rintf(fdiv(s, s2f)), 1.f, 3.f);
-          const float S = __fmul_rn(s2f, c);
-          const float z1 = clampf(rintf(fdiv(-lo, S)), 0.f, 3.f);
-          const float rS = __frcp_rn(S);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float q = clampf(__fadd_rn(rint_any(div_rn_by(x[i][e], S, rS)), z1), 0.f, 3.f);
-            word |= (__float_as_uint(__fadd_rn(q, 12582912.0f)) & 3u) << (2 * e);
-          }
-          meta = ((uint32_t)z1 | ((uint32_t)c << 8)) << (2 * k);
-        } else {
+        const __half s2h = __float2half_rn(fdiv(smax, 3.f));
+        const float s2f = __half2float(s2h);
+        const float c = clampf(rintf(fdiv(s, s2f)), 1.f, 3.f);
+        float S = __fmul_rn(s2f, c);
+        float z = clampf(rintf(fdiv(-lo, S)), 0.f, 3.f);
+        uint32_t meta = ((uint32_t)z | ((uint32_t)c << 8)) << (2 * k);
+        if (four) {
           const float2 pz = p.pack_pool[row];
-          const float rS = __frcp_rn(pz.x);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float q = clampf(__fadd_rn(rint_any(div_rn_by(x[i][e], pz.x, rS)), pz.y), 0.f, 15.f);
-            const uint32_t code = __float_as_uint(__fadd_rn(q, 12582912.0f)) & 15u;
-            if (e < 8) word |= code << (4 * e); else word_last |= code << (4 * (e - 8));
-          }
+          S = pz.x; z = pz.y; meta = 0;
         }
+        const float rS = __frcp_rn(S);
+        const float m_lo = 12582912.0f, m_hi = __fadd_rn(12582912.0f, maxq);
+        uint32_t acc_lo = 0, acc_hi = 0;                 // codes 0..7 and 8..15 of this slot
+#pragma unroll
+        for (int e = 7; e >= 0; --e) {
+          // code = clamp(rint(w / S) + z, 0, maxq), evaluated in the 1.5*2^23 "integer" domain:
+          // (v + M) holds rint(v) exactly, adding the integer z and clamping stay exact
+          const float ma = __fadd_rn(__fadd_rn(div_rn_by(x[i][e], S, rS), 12582912.0f), z);
+          const float mb = __fadd_rn(__fadd_rn(div_rn_by(x[i][e + 8], S, rS), 12582912.0f), z);
+          acc_lo = acc_lo * radix + __float_as_uint(fminf(fmaxf(ma, m_lo), m_hi));
+          acc_hi = acc_hi * radix + __float_as_uint(fminf(fmaxf(mb, m_lo), m_hi));
+        }
+        acc_lo -= horner_bias;
+        acc_hi -= horner_bias;
+        const uint32_t word = four ? acc_lo : (acc_lo | (acc_hi << 16));
+        const uint32_t word_last = acc_hi;
         // gather the block's four weight words and the metadata half-word into slot 0
         const uint32_t w1 = __shfl_down_sync(0xffffffffu, word, 1);
         const uint32_t w2 = __shfl_down_sync(0xffffffffu, word, 2);
