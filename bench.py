@@ -245,7 +245,11 @@ def main():
     roofline = {"bound": "hbm", "kernel": "colsumsq_partial_kernel<__half> (+ its 1-block-wide finalize, same event pair)",
                 "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
                 "peak_source": pk["src"] + " (burst copy bandwidth, MEASURED_PEAKS.json)" if pk["src"] == "measured" else "fallback 6.65 TB/s",
-                "traffic": None, "bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
+                # dram__bytes_read+write per launch from the ncu --set full capture in
+                # profiles/r1c_ncu_full_bench_kernels.csv (2.152 GB + 4.9 MB for the 2.147 GB input,
+                # 5.77 GB + 7.9 MB for the 5.771 GB one): no re-reads
+                "traffic": 1.0025 * dom_bytes, "traffic_source": "profiles/r1c_ncu_full_bench_kernels.csv",
+                "bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
                 "share_of_step": sum(stat_ms) / max(args.steps, 1) / ms_step if ms_step > 0 else None}
 
     # ---- end to end: host (pinned) inputs, device->host results, copies inside the timing ---
