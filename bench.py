@@ -134,7 +134,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ptq", choices=["ptq", "gemm70b"])
+    ap.add_argument("--workload", default="ptq", choices=["ptq", "gemm70b", "qat"])
     ap.add_argument("--no-components", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--layers", type=int, default=LAYERS, help="(debug) fewer layers; default is the named config")
@@ -146,6 +146,8 @@ def main():
         return run_reference(args)
     if args.workload == "gemm70b":
         return run_gemm70b(args)
+    if args.workload == "qat":
+        return run_qat(args)
 
     import torch
     import torch.distributed as dist
@@ -384,6 +386,103 @@ def run_gemm70b(args):
                 "nccl_TFLOPs": tot_flops / tot_ms["nccl"] / 1e9 if tot_ms["nccl"] else None,
                 "p2p_TFLOPs": tot_flops / tot_ms["p2p"] / 1e9 if tot_ms["p2p"] else None,
                 "per_shape": out, "gpu_launches": args.steps * len(shapes)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_qat(args):
+    """BASELINE configs[3]: one LLM-QAT `run_train.sh 2 32 32` optimisation step on a random-init
+    Llama-2-7B (bf16, batch 2 x 2048 tokens per GPU, gradient checkpointing, KD against a frozen
+    teacher, AdamW), fake-quant through the fused kernels, data parallel with NCCL all-reduce."""
+    import torch
+    import torch.distributed as dist
+    from mxq_b200 import ops, qat
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    layers = args.layers
+    cfg = qat.llama_config(layers=layers)
+    student, teacher, nq = qat.build_models(cfg, dev)
+    model = student
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(student, device_ids=[local], gradient_as_bucket_view=True)
+    opt = torch.optim.AdamW(student.parameters(), lr=2e-5, betas=(0.9, 0.95), weight_decay=0.0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(rank)
+    B, T = 2, 2048
+    ids = [torch.randint(0, 32000, (B, T), generator=g, device=dev) for _ in range(4)]
+    h_ids = [t.cpu().pin_memory() for t in ids]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    losses = []
+    for i in range(max(3, args.warmup)):
+        losses.append(qat.qat_step(model, teacher, ids[i % 4], opt))
+    clocks = Clocks(local)
+    barrier()
+    clocks.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        losses.append(qat.qat_step(model, teacher, ids[i % 4], opt))
+    t1.record()
+    barrier()
+    clk = clocks.stop()
+    ms = torch.tensor([t0.elapsed_time(t1) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    # e2e: token ids from pinned host memory in, loss value out, every step
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        x = h_ids[i % 4].to(dev, non_blocking=True)
+        float(qat.qat_step(model, teacher, x, opt).item())
+    e1.record()
+    barrier()
+    ems = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    ems = float(ems.item())
+    # the fake-quant share: all quantized weights, 2 forwards (checkpoint recompute) + 1 STE backward
+    ws = [m.weight.detach() for m in student.modules() if isinstance(m, qat.QuantizeLinear)]
+    gs = {w.shape: torch.randn_like(w) for w in ws}
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for w in ws:
+        ops.fakequant_fwd(w)
+        ops.fakequant_fwd(w)
+        ops.ste_bwd(gs[w.shape], w, -2.0, 2.0)
+    f1.record()
+    torch.cuda.synchronize()
+    fq_ms = f0.elapsed_time(f1)
+    fq_bytes = sum(w.numel() for w in ws) * 2 * (2 * 2 + 3)
+    tokens = B * T * world
+    if rank == 0:
+        line = {"metric": "qat_step_tokens_per_s", "value": tokens / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "LLM-QAT run_train.sh 2 32 32 step (KD vs frozen teacher, AdamW, gradient checkpointing)",
+                           "model": f"Llama-2-7B architecture, {layers} layers, random init", "per_gpu_batch": B, "seq_len": T,
+                           "parallelism": f"dp{world}", "quantized_linears": nq},
+                "roofline": {"bound": "hbm", "kernel": "fakequant_fwd_kernel<bf16> x2 + ste_bwd_kernel<bf16> over all quantized weights",
+                             "achieved": fq_bytes / (fq_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                             "frac": fq_bytes / (fq_ms * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
+                             "ms_per_step": fq_ms, "share_of_step": fq_ms / ms},
+                "e2e": {"value": tokens / (ems * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": B * T * 8, "d2h_bytes_per_step": 4},
+                "clocks": clk, "loss_first_last": [float(losses[0]), float(losses[-1])],
+                "gpu_launches": args.steps * nq * 3}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
