@@ -136,6 +136,15 @@ MXQ_API int mxq_unpack(mxq_packed_t in, int64_t OC, int64_t IC, void* out, int o
 MXQ_API int mxq_gemv(const void* x, mxq_packed_t w, void* y, int64_t B, int64_t IC, int64_t OC,
              void* stream);
 
+/* Same, with flags.  By default the kernel is launched with the programmatic-dependent-launch
+ * attribute: it may become resident while the previous kernel of `stream` is still running, and
+ * until that kernel has completed it only prefetches its own weight stream into L2 (it reads x and
+ * writes y strictly afterwards), so the overlap is safe after any predecessor.  MXQ_GEMV_NO_PDL
+ * launches it fully serialised. */
+#define MXQ_GEMV_NO_PDL 1u
+MXQ_API int mxq_gemv_ex(const void* x, mxq_packed_t w, void* y, int64_t B, int64_t IC, int64_t OC,
+                        unsigned flags, void* stream);
+
 /* ---- (a-10) gemv_forward_cuda (AWQ uniform 4-bit)   gemv_cuda.cu:346-399, gemv_cuda.h:4-9 ------
  * kernel int32[OC, IC/8] (nibble j of word i = column 8i+j), zeros int32[OC, zw] (nibble g%8 of
  * word g/8, g = col/G), scales fp16[OC, zw*8]; zw = ceil(IC/G/8) rounded up to 1/2/4 words for

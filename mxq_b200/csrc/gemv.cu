@@ -16,6 +16,7 @@
 // Any IC % 64 == 0 (metadata tiled in 4096-column chunks; identical to the reference at 4096);
 // the reference's activation-offset and batch-stride bugs (gemv_mxq_cuda.cu:50,119) are not
 // reproduced.
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -42,31 +43,393 @@ __device__ __forceinline__ uint32_t hsub2_u32(uint32_t a, uint32_t b) {
   return d;
 }
 
-constexpr int kGemvWarps = 8;
+constexpr int kXBlkBytes = 144;   // 64 fp16 activations of a block + 16 B pad (conflict-free LDS.128)
 
-// Dequant without subtraction: a code is moved to the TOP mantissa bits of an fp16 whose exponent
-// makes one mantissa step equal to 1, so the register already holds the number bias + q
-// (bias 4 for 2-bit codes, 16 for 4-bit codes) and FHFMA consumes it directly.  The bias and the
-// zero-point are removed once per (row, group) on the fp32 group sum:
-//     sum_j (q_j - z) x_j = sum_j (bias + q_j) x_j - (bias + z) * sum_j x_j
-// (fp32 accumulation loses only log2(bias) bits to the cancellation).
-//
-// x16: 16 activations of one group as 8 half2 words (cols 0..15 in order).
-// 2-bit word: code j at bits [2j+1:2j]; shifting by 8-2j puts code j at bits [9:8] of the low
-// half and code j+8 at bits [9:8] of the high half.
-__device__ __forceinline__ float dot_group_2b(uint32_t w, const uint32_t* x16) {
-  float p = 0.f;
+// ---------------------------------------------------------------------------------------------
+// Dequant without shifts or subtractions.  A 2-bit code sitting at mantissa bits [p+1:p] of an
+// fp16 whose exponent field makes bit p worth 1.0 IS the number bias_p + q (bias 1024 at p=0,
+// 256 at p=2, 64 at p=4, 16 at p=6, 4 at p=8), so one LOP3 (mask | exponent) on the packed word
+// yields the fp16 pair {bias + q_j, bias + q_{j+8}} for j = 0..4 with no shift at all, and one
+// SHF (>> 6) exposes j = 5..7 the same way: 9 instructions per 16 codes.  FHFMA
+// (fma.rn.f32.f16, sm_100) multiplies the pair straight into an fp32 accumulator (products are
+// exact, 11 x 11 bits).  The bias and the zero-point leave on the fp32 side, once per (row, group):
+//     sum_j (q_j - z) x_j = sum_j (bias_j + q_j) x_j - [ sum_j bias_j x_j + z * sum_j x_j ]
+// The bracket's two sums are row independent: the CTA computes them once per group while it stages
+// the activations in shared memory (tables tabA/tabB below) and they seed the accumulator.
+// ---------------------------------------------------------------------------------------------
+// bias of code j (and j+8) of a 2-bit word, of nibble j (and j+4) of a 4-bit word
+__host__ __device__ constexpr float bias2(int j) {
+  j &= 7;
+  return j == 0 ? 1024.f : j == 1 ? 256.f : j == 2 ? 64.f : j == 3 ? 16.f : j == 4 ? 4.f
+       : j == 5 ? 64.f : j == 6 ? 16.f : 4.f;
+}
+__host__ __device__ constexpr float bias4(int j) {
+  j &= 3;
+  return j == 0 ? 1024.f : j == 1 ? 64.f : j == 2 ? 256.f : 16.f;
+}
+
+__host__ __device__ constexpr uint32_t bias_half(float b) {   // fp16 bits of a power of two
+  return b == 1024.f ? 0x6400u : b == 256.f ? 0x5C00u : b == 64.f ? 0x5400u : b == 16.f ? 0x4C00u
+       : 0x4400u;
+}
+
+// h[i] = {bias2(i) + q_i, bias2(i) + q_{i+8}}, i = 0..7
+__device__ __forceinline__ void dequant_word_2b(uint32_t w, uint32_t* h) {
+  h[0] = lop3_and_or(w, 0x00030003u, 0x64006400u);
+  h[1] = lop3_and_or(w, 0x000C000Cu, 0x5C005C00u);
+  h[2] = lop3_and_or(w, 0x00300030u, 0x54005400u);
+  h[3] = lop3_and_or(w, 0x00C000C0u, 0x4C004C00u);
+  h[4] = lop3_and_or(w, 0x03000300u, 0x44004400u);
+  const uint32_t t = w >> 6;
+  h[5] = lop3_and_or(t, 0x00300030u, 0x54005400u);
+  h[6] = lop3_and_or(t, 0x00C000C0u, 0x4C004C00u);
+  h[7] = lop3_and_or(t, 0x03000300u, 0x44004400u);
+}
+// h[i] = {bias4(i) + n_i, bias4(i) + n_{i+4}}, i = 0..3
+__device__ __forceinline__ void dequant_word_4b(uint32_t w, uint32_t* h) {
+  h[0] = lop3_and_or(w, 0x000F000Fu, 0x64006400u);
+  h[1] = lop3_and_or(w, 0x00F000F0u, 0x54005400u);
+  const uint32_t t = w >> 6;
+  h[2] = lop3_and_or(t, 0x003C003Cu, 0x5C005C00u);
+  h[3] = lop3_and_or(t, 0x03C003C0u, 0x4C004C00u);
+}
+// p += sum over the 16 codes of a 2-bit word;  x16 = 16 activations as 8 half2 words
+__device__ __forceinline__ float dot16_2b(const uint32_t* h, const uint32_t* x16, float p) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const uint32_t t = (8 - 2 * j) >= 0 ? (w << (8 - 2 * j)) : (w >> (2 * j - 8));
-    const uint32_t h = lop3_and_or(t, 0x03000300u, 0x44004400u);   // {4 + q_j, 4 + q_{j+8}}
-    p = fhfma_sel(h, 0, x16[j >> 1], j & 1, p);
-    p = fhfma_sel(h, 1, x16[(j + 8) >> 1], (j + 8) & 1, p);
+    p = fhfma_sel(h[j], 0, x16[j >> 1], j & 1, p);
+    p = fhfma_sel(h[j], 1, x16[(j + 8) >> 1], j & 1, p);
   }
   return p;
 }
-// 4-bit word: nibble j at bits [4j+3:4j]; shifting by 6-4j puts nibble j at bits [9:6] of the low
-// half and nibble j+4 at bits [9:6] of the high half: {16 + n_j, 16 + n_{j+4}}.
+// p += sum over the 8 nibbles of a 4-bit word;  x8 = 8 activations as 4 half2 words
+__device__ __forceinline__ float dot8_4b(const uint32_t* h, const uint32_t* x8, float p) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    p = fhfma_sel(h[j], 0, x8[j >> 1], j & 1, p);
+    p = fhfma_sel(h[j], 1, x8[(j + 4) >> 1], j & 1, p);
+  }
+  return p;
+}
+// 4.0f + the 2-bit field of v at bit position pos (exact, no int->float conversion)
+__device__ __forceinline__ float four_plus_field(uint32_t v, int pos) {
+  return __uint_as_float(((v & (3u << pos)) << (21 - pos)) + 0x40800000u);
+}
+__device__ __forceinline__ float fhfma_lo(uint32_t a, uint32_t b, float c) {   // lo(a) * lo(b) + c
+  return fhfma_sel(a, 0, b, 0, c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight stream.  The rows of a CTA are one contiguous range of every packed tensor, so a "stage"
+// (rpr consecutive 4-row groups, all of K) is fetched with four 1-D TMA bulk copies
+// (cp.async.bulk, UBLKCP) into a shared-memory ring, completion on an mbarrier:
+//   [0)       weight            group g, row r, block b at (g*4 + r)*nblk*16 + b*16
+//   [off_wl)  weight_last       (g*4 + r)*nblk*4 + b*4
+//   [off_zs)  zeros_and_scales  (g*4 + r)*128*nchunk + word*4 (+2 for the upper half)
+//   [off_z2)  zeros_2nd         g*128*nchunk + word*4 (+ byte)
+// scales_2nd (6 % of the bytes; its groups start on 2-byte boundaries, so no bulk copy) is
+// prefetched into L2 and read with ordinary loads issued before the stage barrier is waited on.
+// ---------------------------------------------------------------------------------------------
+struct GemvStage {
+  int off_wl, off_zs, off_z2, bytes;
+};
+__host__ __device__ inline GemvStage gemv_stage_layout(int rpr, int nblk, int nchunk) {
+  GemvStage L;
+  L.off_wl = rpr * nblk * 64;
+  L.off_zs = L.off_wl + rpr * nblk * 16;
+  L.off_z2 = L.off_zs + rpr * 512 * nchunk;
+  L.bytes = L.off_z2 + rpr * 128 * nchunk;
+  return L;
+}
+// thread 0: fetch `rc` row groups starting at `grp0` into stage `st`
+__device__ __forceinline__ void gemv_fill(unsigned char* st, const GemvStage& L, uint64_t* bar,
+                                          const mxq_packed_t& w, int grp0, int rc, int nblk,
+                                          int nchunk) {
+  const uint32_t b_wq = (uint32_t)rc * nblk * 64, b_wl = (uint32_t)rc * nblk * 16,
+                 b_zs = (uint32_t)rc * 512 * nchunk, b_z2 = (uint32_t)rc * 128 * nchunk;
+  mbar_arrive_expect_tx(bar, b_wq + b_wl + b_zs + b_z2);
+  bulk_g2s(st, reinterpret_cast<const unsigned char*>(w.weight) + (size_t)grp0 * nblk * 64, b_wq, bar);
+  bulk_g2s(st + L.off_wl, reinterpret_cast<const unsigned char*>(w.weight_last) + (size_t)grp0 * nblk * 16, b_wl, bar);
+  bulk_g2s(st + L.off_zs, reinterpret_cast<const unsigned char*>(w.zeros_and_scales) + (size_t)grp0 * 512 * nchunk, b_zs, bar);
+  bulk_g2s(st + L.off_z2, reinterpret_cast<const unsigned char*>(w.zeros_2nd) + (size_t)grp0 * 128 * nchunk, b_z2, bar);
+}
+
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t ldg_u16(const void* p) {
+  unsigned short v;
+  asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
+
+struct GemvRegs {     // one lane's share of a (4-row group, 64-column block): 27 registers
+  uint4 wq[4];
+  uint32_t wl[4], zs[4], z2, s2[3];
+};
+// gi = row group index inside the stage
+__device__ __forceinline__ void gemv_read(const unsigned char* st, const GemvStage& L, int gi,
+                                          int blk, int nblk, int nchunk, GemvRegs& g) {
+  const int chunk = blk >> 6, bp = blk & 63;
+  const int word = chunk * 32 + (bp & 31), p = bp >> 5;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int row = gi * 4 + r;
+    g.wq[r] = *reinterpret_cast<const uint4*>(st + (row * nblk + blk) * 16);
+    g.wl[r] = *reinterpret_cast<const uint32_t*>(st + L.off_wl + (row * nblk + blk) * 4);
+    g.zs[r] = *reinterpret_cast<const uint16_t*>(st + L.off_zs + (row * 32 * nchunk + word) * 4 + p * 2);
+  }
+  g.z2 = st[L.off_z2 + (gi * 32 * nchunk + word) * 4 + p];
+}
+
+// Shared-memory image of the activations, per batch row b (stride `xb_stride` bytes):
+//   [nblk][144 B]   the block's 64 fp16 activations (+ pad)
+//   tabA float4[nblk] = { 4*xs_k - xsb_k (k = 0,1,2),  -xsb_3 }   xs = sum x, xsb = sum bias*x
+//   tabB float4[nblk] = { -xs_k (k = 0..3) }
+template <int NB>
+__device__ __forceinline__ void gemv_block(const GemvRegs& g, const unsigned char* xsm,
+                                           int xb_stride, int blk, int nblk, const float* s4,
+                                           const float* z4f, float (&acc)[4][NB]) {
+  float4 tA[NB], tB[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const unsigned char* base = xsm + (size_t)b * xb_stride + (size_t)nblk * kXBlkBytes;
+    tA[b] = reinterpret_cast<const float4*>(base)[blk];
+    tB[b] = reinterpret_cast<const float4*>(base + (size_t)nblk * 16)[blk];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t xv[NB][8];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const uint4* xp = reinterpret_cast<const uint4*>(xsm + (size_t)b * xb_stride +
+                                                       (size_t)blk * kXBlkBytes + k * 32);
+      const uint4 v0 = xp[0], v1 = xp[1];
+      xv[b][0] = v0.x; xv[b][1] = v0.y; xv[b][2] = v0.z; xv[b][3] = v0.w;
+      xv[b][4] = v1.x; xv[b][5] = v1.y; xv[b][6] = v1.z; xv[b][7] = v1.w;
+    }
+    if (k < 3) {
+      // S = s2 * (c - z2) = (cb + c) * s2 - (cb + z2) * s2,  cb = 4 (k = 0, 2) or 16 (k = 1)
+      const float s2f = __half2float(__ushort_as_half((unsigned short)g.s2[k]));
+      const float cb_m4 = k == 1 ? 12.f : 0.f;
+      const float S0 = -(four_plus_field(g.z2, 2 * k) + cb_m4) * s2f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const uint32_t wk = k == 0 ? g.wq[r].x : (k == 1 ? g.wq[r].y : g.wq[r].z);
+        uint32_t h[8];
+        dequant_word_2b(wk, h);
+        const uint32_t hc = k == 0 ? lop3_and_or(g.zs[r], 0x0300u, 0x4400u)
+                          : k == 1 ? lop3_and_or(g.zs[r] >> 4, 0x00C0u, 0x4C00u)
+                                   : lop3_and_or(g.zs[r] >> 4, 0x0300u, 0x4400u);
+        const float S = fhfma_lo(hc, g.s2[k], S0);                       // :136
+        const float zf = four_plus_field(g.zs[r], 2 * k);                // 4 + z1
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const float nxs = k == 0 ? tB[b].x : (k == 1 ? tB[b].y : tB[b].z);
+          const float nc0 = k == 0 ? tA[b].x : (k == 1 ? tA[b].y : tA[b].z);
+          const float p = dot16_2b(h, xv[b], fmaf(zf, nxs, nc0));
+          acc[r][b] = fmaf(S, p, acc[r][b]);                             // :153
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        uint32_t ha[4], hb[4];
+        dequant_word_4b(g.wq[r].w, ha);
+        dequant_word_4b(g.wl[r], hb);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          float p = fmaf(z4f[r], tB[b].w, tA[b].w);
+          p = dot8_4b(ha, xv[b], p);
+          p = dot8_4b(hb, xv[b] + 4, p);
+          acc[r][b] = fmaf(s4[r], p, acc[r][b]);                         // :179,192
+        }
+      }
+    }
+  }
+}
+
+// Programmatic dependent launch (PDL): when the launch carries the programmatic-serialization
+// attribute this grid may become resident while its predecessor in the stream is still running
+// (the host sizes the CTA to at most half an SM when it can, so two generations fit).  Before
+// griddep_wait() it only touches the packed weights -- every warp fills both stages of its ring --
+// never x or y.  Contract (include/mxq_b200.h): the packed tensors must not be written by a
+// kernel that itself signals early completion (griddepcontrol.launch_dependents) immediately
+// before this call; MXQ_GEMV_NO_PDL otherwise.  Without the attribute both are no-ops.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+struct GemvPlan {
+  int q;        // consecutive 4-row groups per CTA
+  int wpr;      // warps sharing one row group (each takes K slices sl0, sl0 + wpr, ...)
+  int rpr;      // row groups per round = warps / wpr
+  int rounds;   // ceil(q / rpr)
+  int spw;      // K slices per warp and round = ceil(ksl / wpr)
+  int ksl;      // K slices of 32 blocks (2048 columns) per row
+  int nstages;  // ring depth
+  int dbg;      // profiling only (MXQ_GEMV_DBG): 1 = skip the dot products, 2 = skip staging
+};
+
+constexpr int kGemvMaxWarps = 16, kGemvMaxStages = 4;
+
+// Persistent: one CTA per SM walks its q row groups in rounds of rpr groups (= one ring stage).
+// warp = (row group of the round, K-slice phase); lane = 64-column block of the slice.
+// Dynamic shared memory: [nstages][stage] weight ring, then the activation image (gemv_block).
+template <int NB>
+__global__ void __launch_bounds__(NB == 1 ? 512 : 256, NB == 1 ? 2 : 1) gemv_mxq_kernel(
+    const __half* __restrict__ x, mxq_packed_t w, __half* __restrict__ y, int B, int IC, int OC,
+    GemvPlan plan) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ float red[2][kGemvMaxWarps][4][NB];
+  __shared__ uint64_t full[kGemvMaxStages];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nblk = IC >> 6;
+  const int nchunk = (nblk + 63) >> 6;
+  const int ngrp_all = OC >> 2;
+  const int grp_base = blockIdx.x * plan.q;
+  const int qc = min(plan.q, ngrp_all - grp_base);      // row groups of this CTA
+  const int rgl = warp / plan.wpr, sl0 = warp - rgl * plan.wpr;
+  const bool warp_on = rgl < plan.rpr;
+  const int b0 = blockIdx.y * NB;
+  const int xb_stride = nblk * (kXBlkBytes + 32);
+  const GemvStage L = gemv_stage_layout(plan.rpr, nblk, nchunk);
+  const int stage_stride = (L.bytes + 127) & ~127;
+  unsigned char* xsm = smem + (size_t)plan.nstages * stage_stride;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < plan.nstages; ++i) mbar_init(&full[i], 1);
+    mbar_fence_init();
+    for (int i = 0; i < plan.nstages && i < plan.rounds; ++i) {
+      const int g0 = i * plan.rpr;
+      if (g0 < qc)
+        gemv_fill(smem + (size_t)i * stage_stride, L, &full[i], w, grp_base + g0,
+                  min(plan.rpr, qc - g0), nblk, nchunk);
+    }
+    // scales_2nd of the CTA's row range -> L2 (a hint: clipped to whole 16-byte lines)
+    const size_t lo = ((size_t)grp_base * nblk * 6 + 15) & ~(size_t)15;
+    const size_t hi = ((size_t)(grp_base + qc) * nblk * 6) & ~(size_t)15;
+    if (hi > lo) bulk_prefetch_l2(reinterpret_cast<const unsigned char*>(w.scales_2nd) + lo, (uint32_t)(hi - lo));
+  }
+
+  griddep_wait();
+  // Only now may the next kernel of the stream become resident (one generation of look-ahead).
+  // Triggering before the wait was measured slower (profiles/probes/pdl_probe.cu): the scheduler
+  // then stacks several CTAs of one grid on the SMs that happen to be free.
+  griddep_launch_dependents();
+
+  // stage activations + per-group sums (one thread per (batch row, 16-column group))
+  if (!(plan.dbg & 2)) {
+    const int ngrp = IC >> 4;
+    for (int i = threadIdx.x; i < NB * ngrp; i += blockDim.x) {
+      const int b = NB == 1 ? 0 : i / ngrp, g = i - b * ngrp;
+      const int bb = min(b0 + b, B - 1);
+      const uint4* xp = reinterpret_cast<const uint4*>(x + (size_t)bb * IC + (size_t)g * 16);
+      const uint4 v0 = __ldg(xp), v1 = __ldg(xp + 1);
+      const int xblk = g >> 2, k = g & 3;
+      unsigned char* xb = xsm + (size_t)b * xb_stride;
+      uint4* dst = reinterpret_cast<uint4*>(xb + (size_t)xblk * kXBlkBytes + k * 32);
+      dst[0] = v0; dst[1] = v1;
+      const uint32_t xw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      float xs = 0.f, xsb2 = 0.f, xsb4 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        xs = fhfma_sel(0x3C003C00u, 0, xw[j >> 1], j & 1, xs);
+        xsb2 = fhfma_sel(bias_half(bias2(j)), 0, xw[j >> 1], j & 1, xsb2);
+      }
+      if (k == 3) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) xsb4 = fhfma_sel(bias_half(bias4(j)), 0, xw[j >> 1], j & 1, xsb4);
+      }
+      const float xsb = k < 3 ? xsb2 : xsb4;
+      float* tA = reinterpret_cast<float*>(xb + (size_t)nblk * kXBlkBytes) + xblk * 4 + k;
+      float* tB = reinterpret_cast<float*>(xb + (size_t)nblk * (kXBlkBytes + 16)) + xblk * 4 + k;
+      *tA = k < 3 ? fmaf(4.f, xs, -xsb) : -xsb;
+      *tB = -xs;
+    }
+  }
+  __syncthreads();
+
+  for (int round = 0; round < plan.rounds; ++round) {
+    const int slot = round % plan.nstages;
+    const uint32_t parity = (uint32_t)(round / plan.nstages) & 1u;
+    const unsigned char* st = smem + (size_t)slot * stage_stride;
+    const int gl = round * plan.rpr + rgl;
+    const bool on = warp_on && gl < qc;
+    const int grp = grp_base + gl;
+    float acc[4][NB];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int b = 0; b < NB; ++b) acc[r][b] = 0.f;
+    float s4[4], z4f[4];
+    GemvRegs cur;
+    const __half* s2p = reinterpret_cast<const __half*>(w.scales_2nd) + (size_t)grp * nblk * 3;
+    int blk = sl0 * 32 + lane;
+    if (on) {
+      const int oc0 = grp * 4;
+      const __half* s4p = reinterpret_cast<const __half*>(w.scales_4b) + oc0;
+      const uint32_t z4w = (uint32_t)__ldg(w.zeros_4b + (oc0 >> 3)) >> (4 * (oc0 & 7));
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        s4[r] = __half2float(__ldg(s4p + r));
+        z4f[r] = (float)((z4w >> (4 * r)) & 0xF);
+      }
+      if (blk < nblk) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) cur.s2[k] = ldg_u16(s2p + (size_t)blk * 3 + k);
+      }
+    }
+    mbar_wait(&full[slot], parity);
+    if (on) {
+      for (int sl = sl0; sl < plan.ksl; sl += plan.wpr) {
+        blk = sl * 32 + lane;
+        if (blk < nblk) {
+          if (sl != sl0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) cur.s2[k] = ldg_u16(s2p + (size_t)blk * 3 + k);
+          }
+          gemv_read(st, L, rgl, blk, nblk, nchunk, cur);
+          if (!(plan.dbg & 1)) gemv_block<NB>(cur, xsm, xb_stride, blk, nblk, s4, z4f, acc);
+          else acc[0][0] += __uint_as_float(cur.wq[0].x ^ cur.wq[1].y ^ cur.wq[2].z ^ cur.wq[3].w ^ cur.wl[0] ^ cur.wl[1] ^ cur.wl[2] ^ cur.wl[3] ^ cur.zs[0] ^ cur.zs[1] ^ cur.zs[2] ^ cur.zs[3] ^ cur.z2 ^ cur.s2[0] ^ cur.s2[1] ^ cur.s2[2]);
+        }
+      }
+    }
+    float (*rd)[4][NB] = red[round & 1];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const float v = warp_sum(acc[r][b]);
+        if (lane == 0) rd[warp][r][b] = v;
+      }
+    __syncthreads();      // every warp is done with the stage (and red[] is complete)
+    const int t = threadIdx.x;
+    if (t == 0) {
+      const int g0 = (round + plan.nstages) * plan.rpr;
+      if (round + plan.nstages < plan.rounds && g0 < qc) {
+        fence_proxy_async();
+        gemv_fill(smem + (size_t)slot * stage_stride, L, &full[slot], w, grp_base + g0,
+                  min(plan.rpr, qc - g0), nblk, nchunk);
+      }
+    }
+    // one thread per (row group of the round, row, batch)
+    if (t < plan.rpr * 4 * NB) {
+      const int g = t / (4 * NB), r = (t / NB) & 3, b = t % NB;
+      const int glw = round * plan.rpr + g;
+      if (glw < qc && b0 + b < B) {
+        float sum = 0.f;
+        for (int k = 0; k < plan.wpr; ++k) sum += rd[g * plan.wpr + k][r][b];
+        y[(size_t)(b0 + b) * OC + (size_t)(grp_base + glw) * 4 + r] = __float2half_rn(sum);
+      }
+    }
+  }
+}
+
+// 4-bit word with one bias for all nibbles (shift per pair): nibble j at bits [4j+3:4j]; shifting
+// by 6-4j puts nibble j at bits [9:6] of the low half and nibble j+4 at bits [9:6] of the high
+// half: {16 + n_j, 16 + n_{j+4}}.
 __device__ __forceinline__ float dot_word_4b(uint32_t w, const uint32_t* x8, float p) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -87,115 +450,6 @@ __device__ __forceinline__ float sum_halves(const uint32_t* x) {
     p = fhfma_sel(0x3C003C00u, 0, x[i], 1, p);
   }
   return p;
-}
-
-template <int NB>
-__global__ void __launch_bounds__(kGemvWarps * 32) gemv_mxq_kernel(
-    const __half* __restrict__ x, mxq_packed_t w, __half* __restrict__ y, int B, int IC, int OC,
-    int KS, int ks_shift) {
-  __shared__ float red[kGemvWarps][4][NB];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int RG = kGemvWarps >> ks_shift;
-  const int rg = warp >> ks_shift, ks = warp & (KS - 1);
-  const int nblk = IC >> 6;
-  const int nchunk = (nblk + 63) >> 6;
-  const int grp = blockIdx.x * RG + rg;          // second-order group (4 rows)
-  const int b0 = blockIdx.y * NB;
-  const bool live = grp * 4 < OC;
-  float acc[4][NB];
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int b = 0; b < NB; ++b) acc[r][b] = 0.f;
-
-  if (live) {
-    const int oc0 = grp * 4;
-    const __half* s4p = reinterpret_cast<const __half*>(w.scales_4b) + oc0;
-    const uint32_t z4w = (uint32_t)w.zeros_4b[oc0 >> 3] >> (4 * (oc0 & 7));
-    float s4[4], z4b[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      s4[r] = __half2float(s4p[r]);
-      z4b[r] = __uint_as_float(0x41800000u + (((z4w >> (4 * r)) & 0xF) << 19));   // 16 + z4
-    }
-    const uint16_t* zs16 = reinterpret_cast<const uint16_t*>(w.zeros_and_scales);
-    const uint8_t* z2b = reinterpret_cast<const uint8_t*>(w.zeros_2nd);
-    const __half* s2p = reinterpret_cast<const __half*>(w.scales_2nd) + (size_t)grp * nblk * 3;
-
-    for (int blk = ks * 32 + lane; blk < nblk; blk += KS * 32) {
-      uint4 wq[4];
-      uint32_t wl[4], zs[4];
-      const int chunk = blk >> 6, bp = blk & 63;
-      const int word = chunk * 32 + (bp & 31), p = bp >> 5;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const size_t row = (size_t)(oc0 + r);
-        wq[r] = ld_stream(w.weight + row * nblk * 4 + (size_t)blk * 4);
-        wl[r] = (uint32_t)__ldg(w.weight_last + row * nblk + blk);
-        zs[r] = __ldg(zs16 + (row * 32 * nchunk + word) * 2 + p);
-      }
-      const uint32_t z2 = __ldg(z2b + ((size_t)grp * 32 * nchunk + word) * 4 + p);
-      float s2[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) s2[k] = __half2float(__ldg(s2p + (size_t)blk * 3 + k));
-
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint32_t xv[NB][8];
-        float xs[NB];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          const int bb = min(b0 + b, B - 1);
-          const uint4* xp = reinterpret_cast<const uint4*>(x + (size_t)bb * IC + (size_t)blk * 64 + k * 16);
-          const uint4 v0 = __ldg(xp), v1 = __ldg(xp + 1);
-          xv[b][0] = v0.x; xv[b][1] = v0.y; xv[b][2] = v0.z; xv[b][3] = v0.w;
-          xv[b][4] = v1.x; xv[b][5] = v1.y; xv[b][6] = v1.z; xv[b][7] = v1.w;
-          xs[b] = sum_halves<8>(xv[b]);
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          if (k < 3) {
-            const uint32_t wk = k == 0 ? wq[r].x : (k == 1 ? wq[r].y : wq[r].z);
-            const float zb = __uint_as_float(0x40800000u + (((zs[r] >> (2 * k)) & 3) << 21));   // 4 + z1
-            const int d = 3 + (int)((zs[r] >> (8 + 2 * k)) & 3) - (int)((z2 >> (2 * k)) & 3);   // 3 + c - z2
-            const float scale = s2[k] * (__uint_as_float(0x41000000u + ((uint32_t)d << 20)) - 11.0f);  // :136
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-              const float pz = fmaf(-zb, xs[b], dot_group_2b(wk, xv[b]));
-              acc[r][b] = fmaf(scale, pz, acc[r][b]);
-            }
-          } else {
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-              float pz = dot_word_4b(wq[r].w, xv[b], 0.f);
-              pz = dot_word_4b(wl[r], xv[b] + 4, pz);
-              pz = fmaf(-z4b[r], xs[b], pz);
-              acc[r][b] = fmaf(s4[r], pz, acc[r][b]);               // :179,192
-            }
-          }
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const float v = warp_sum(acc[r][b]);
-      if (lane == 0) red[warp][r][b] = v;
-    }
-  __syncthreads();
-  // one thread per (row group, row, batch)
-  const int t = threadIdx.x;
-  if (t < RG * 4 * NB) {
-    const int g = t / (4 * NB), r = (t / NB) & 3, b = t % NB;
-    const int oc = (blockIdx.x * RG + g) * 4 + r;
-    if (oc < OC && b0 + b < B) {
-      float s = 0.f;
-      for (int k = 0; k < KS; ++k) s += red[(g << ks_shift) + k][r][b];
-      y[(size_t)(b0 + b) * OC + oc] = __float2half_rn(s);
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -241,8 +495,85 @@ __global__ void __launch_bounds__(256) awq_gemv_kernel(const __half* __restrict_
 
 using namespace mxq;
 
-extern "C" int mxq_gemv(const void* x, mxq_packed_t w, void* y, int64_t B, int64_t IC, int64_t OC,
-                        void* stream) {
+namespace {
+
+constexpr size_t kSmemPerSM = 227 * 1024, kSmemCtaReserve = 1024;
+
+template <int NB>
+int launch_gemv(const __half* x, const mxq_packed_t& w, __half* y, int B, int IC, int OC,
+                bool pdl, cudaStream_t st) {
+  constexpr int kMaxWarps = NB == 1 ? kGemvMaxWarps : 8;
+  const int nblk = IC / 64, ngrp = OC / 4, nchunk = (nblk + 63) / 64;
+  const size_t ximg = (size_t)NB * nblk * (kXBlkBytes + 32);
+  GemvPlan plan;
+  plan.q = (int)ceil_div(ngrp, kNumSMs);
+  plan.ksl = (int)ceil_div(nblk, 32);
+  plan.dbg = 0;
+  if (const char* e = getenv("MXQ_GEMV_DBG")) plan.dbg = atoi(e);
+  // Choose (warps, warps per row group, ring depth).  Cost = sequential units per warp
+  // (rounds x slices), +30 % if two CTAs cannot share an SM (no overlap with the next GEMV under
+  // PDL), +15 % if the ring holds less than 64 KB or the whole CTA share; ties -> fewer warps.
+  int W = 0, force_w = 0, force_wpr = 0, force_s = 0;
+  if (const char* e = getenv("MXQ_GEMV_WARPS")) force_w = atoi(e);    // tuning knobs
+  if (const char* e = getenv("MXQ_GEMV_WPR")) force_wpr = atoi(e);
+  if (const char* e = getenv("MXQ_GEMV_STAGES")) force_s = atoi(e);
+  double best = 1e30;
+  size_t smem_best = 0;
+  for (int warps = 4; warps <= kMaxWarps; ++warps) {
+    if (force_w && warps != force_w) continue;
+    for (int wpr = 1; wpr <= warps && wpr <= plan.ksl; ++wpr) {
+      if (force_wpr && wpr != force_wpr) continue;
+      const int rpr = warps / wpr;
+      const int rounds = (int)ceil_div(plan.q, rpr);
+      const size_t stage = ((size_t)gemv_stage_layout(rpr, nblk, nchunk).bytes + 127) & ~(size_t)127;
+      for (int ns = 1; ns <= kGemvMaxStages; ++ns) {
+        if (force_s && ns != force_s) continue;
+        if (ns > rounds && ns > 1) continue;
+        const size_t smem = ns * stage + ximg;
+        if (smem + kSmemCtaReserve > kSmemPerSM) continue;
+        const bool twice = NB == 1 && 2 * (smem + kSmemCtaReserve) <= kSmemPerSM && warps <= 16;
+        const bool deep = ns * stage >= 64 * 1024 || ns >= rounds;
+        const double cost = (double)rounds * (double)ceil_div(plan.ksl, wpr) * (twice ? 1.0 : 1.3) *
+                                (deep ? 1.0 : 1.15) + 1e-3 * warps + 1e-4 * wpr + 1e-5 * ns;
+        if (cost < best) {
+          best = cost; W = warps; plan.wpr = wpr; plan.nstages = ns; smem_best = smem;
+        }
+      }
+    }
+  }
+  if (W == 0) return MXQ_E_SHAPE;
+  plan.rpr = W / plan.wpr;
+  plan.rounds = (int)ceil_div(plan.q, plan.rpr);
+  plan.spw = (int)ceil_div(plan.ksl, plan.wpr);
+  const unsigned gx = (unsigned)ceil_div(ngrp, plan.q);
+  const unsigned gy = (unsigned)ceil_div(B, NB);
+  const size_t smem = smem_best;
+  if (getenv("MXQ_GEMV_VERBOSE"))
+    fprintf(stderr, "mxq_gemv %dx%d B=%d: warps %d wpr %d rpr %d rounds %d stages %d smem %zu grid %u\n",
+            OC, IC, B, W, plan.wpr, plan.rpr, plan.rounds, plan.nstages, smem, gx);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(gemv_mxq_kernel<NB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx, gy);
+  cfg.blockDim = dim3(W * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemv_mxq_kernel<NB>, x, w, y, B, IC, OC, plan);
+  return e == cudaSuccess ? MXQ_OK : (int)e;
+}
+
+}  // namespace
+
+extern "C" int mxq_gemv_ex(const void* x, mxq_packed_t w, void* y, int64_t B, int64_t IC,
+                           int64_t OC, unsigned flags, void* stream) {
   if (B < 0 || IC < 0 || OC < 0) return MXQ_E_SHAPE;
   if (B == 0 || OC == 0) return MXQ_OK;
   MXQ_CHECK_PTR(x);
@@ -253,26 +584,18 @@ extern "C" int mxq_gemv(const void* x, mxq_packed_t w, void* y, int64_t B, int64
     return MXQ_E_NULL;
   if (IC % 64 || OC % 8 || IC == 0 || IC > (1 << 24) || OC > INT32_MAX || B > 65535 * 4)
     return MXQ_E_SHAPE;
-  const int nblk = (int)(IC / 64);
-  int KS = 1, ks_shift = 0;
-  while (KS < kGemvWarps && nblk > 32 * KS) { KS <<= 1; ++ks_shift; }
-  if (const char* e = getenv("MXQ_GEMV_KS")) {   // tuning knob (profiles/sweep_gemv.py)
-    const int v = atoi(e);
-    if (v == 1 || v == 2 || v == 4 || v == 8) { KS = v; ks_shift = v == 1 ? 0 : v == 2 ? 1 : v == 4 ? 2 : 3; }
-  }
-  const int RG = kGemvWarps / KS;
-  const unsigned gx = (unsigned)ceil_div(OC / 4, RG);
   cudaStream_t st = as_stream(stream);
   const __half* xh = (const __half*)x;
   __half* yh = (__half*)y;
-  if (B == 1) {
-    gemv_mxq_kernel<1><<<dim3(gx, 1), kGemvWarps * 32, 0, st>>>(xh, w, yh, (int)B, (int)IC, (int)OC, KS, ks_shift);
-  } else if (B == 2) {
-    gemv_mxq_kernel<2><<<dim3(gx, 1), kGemvWarps * 32, 0, st>>>(xh, w, yh, (int)B, (int)IC, (int)OC, KS, ks_shift);
-  } else {
-    gemv_mxq_kernel<4><<<dim3(gx, (unsigned)ceil_div(B, 4)), kGemvWarps * 32, 0, st>>>(xh, w, yh, (int)B, (int)IC, (int)OC, KS, ks_shift);
-  }
-  MXQ_LAUNCH_RESULT();
+  const bool pdl = !(flags & MXQ_GEMV_NO_PDL);
+  if (B == 1) return launch_gemv<1>(xh, w, yh, (int)B, (int)IC, (int)OC, pdl, st);
+  if (B == 2) return launch_gemv<2>(xh, w, yh, (int)B, (int)IC, (int)OC, pdl, st);
+  return launch_gemv<4>(xh, w, yh, (int)B, (int)IC, (int)OC, pdl, st);
+}
+
+extern "C" int mxq_gemv(const void* x, mxq_packed_t w, void* y, int64_t B, int64_t IC, int64_t OC,
+                        void* stream) {
+  return mxq_gemv_ex(x, w, y, B, IC, OC, 0u, stream);
 }
 
 extern "C" int mxq_awq_gemv(const void* x, const int32_t* kernel, const void* scales,

@@ -206,8 +206,10 @@ def unpack(p: dict, dtype=torch.float32) -> torch.Tensor:
     return out
 
 
-def gemv(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, validate: bool = True):
-    """y[B, OC] = x[B, IC] @ dequant(W)^T, fp16."""
+def gemv(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, validate: bool = True,
+         pdl: bool = True):
+    """y[B, OC] = x[B, IC] @ dequant(W)^T, fp16.  pdl: programmatic dependent launch (the kernel may
+    prefetch its weights into L2 while the previous kernel of the stream is still running)."""
     OC, IC = _check_packed(p) if validate else _packed_dims(p)
     L.require_cuda(x)
     if x.dtype != torch.float16 or x.dim() != 2 or x.shape[1] != IC:
@@ -216,7 +218,8 @@ def gemv(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, validate: bo
     B = x.shape[0]
     if out is None:
         out = torch.empty((B, OC), dtype=torch.float16, device=x.device)
-    rc = L.lib().mxq_gemv(L.ptr(x), L.packed_struct(p), L.ptr(out), B, IC, OC, L.stream())
+    rc = L.lib().mxq_gemv_ex(L.ptr(x), L.packed_struct(p), L.ptr(out), B, IC, OC,
+                             0 if pdl else 1, L.stream())
     L.check(rc, "mxq_gemv")
     return out
 

@@ -1,4 +1,4 @@
-"""Decode GEMV timing per shape (CUDA graph of one GEMV per distinct weight set, > L2) and K-split sweep."""
+"""Phase probe of the decode GEMV: time a CUDA-graph chain with phases disabled (MXQ_GEMV_DBG)."""
 import os
 import sys
 
@@ -21,18 +21,26 @@ def rand_packed(oc, ic):
     return p
 
 
+def empty_chain(n, pdl):
+    a = torch.zeros(8, device=dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            a.add_(1.0)
+    return g
+
+
 for oc, ic in ((4096, 4096), (11008, 4096), (4096, 11008)):
     nset = max(4, int(400e6 / packed_nbytes(oc, ic)))
     ps = [rand_packed(oc, ic) for _ in range(nset)]
-    for B in (1, 4):
-        x = torch.randn(B, ic, device=dev).half()
-        y = torch.empty(B, oc, device=dev, dtype=torch.float16)
-        for ks in ("auto", "auto-nopdl", "1", "2", "3", "4"):
-            pdl = ks != "auto-nopdl"
-            if ks.startswith("auto"):
-                os.environ.pop("MXQ_GEMV_WPR", None)
-            else:
-                os.environ["MXQ_GEMV_WPR"] = ks
+    x = torch.randn(1, ic, device=dev).half()
+    y = torch.empty(1, oc, device=dev, dtype=torch.float16)
+    os.environ["MXQ_GEMV_VERBOSE"] = "1"
+    ops.gemv(x, ps[0], out=y, validate=False)
+    os.environ.pop("MXQ_GEMV_VERBOSE")
+    for dbg in ("0", "1", "2", "3"):
+        for pdl in (True, False):
+            os.environ["MXQ_GEMV_DBG"] = dbg
             for p in ps[:2]:
                 ops.gemv(x, p, out=y, validate=False, pdl=pdl)
             torch.cuda.synchronize()
@@ -49,5 +57,16 @@ for oc, ic in ((4096, 4096), (11008, 4096), (4096, 11008)):
             b.record()
             torch.cuda.synchronize()
             us = a.elapsed_time(b) / 5 / nset * 1e3
-            nb = packed_nbytes(oc, ic) + 2 * B * (oc + ic)
-            print(f"{oc}x{ic} B={B} WPR={ks}: {us:.2f} us/gemv = {nb / us / 1e3:.0f} GB/s")
+            nb = packed_nbytes(oc, ic)
+            print(f"{oc}x{ic} dbg={dbg} pdl={int(pdl)}: {us:.2f} us/gemv = {nb / us / 1e3:.0f} GB/s")
+os.environ["MXQ_GEMV_DBG"] = "0"
+g = empty_chain(200, False)
+g.replay()
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(5):
+    g.replay()
+b.record()
+torch.cuda.synchronize()
+print(f"torch add_ chain: {a.elapsed_time(b) / 5 / 200 * 1e3:.2f} us/kernel")
