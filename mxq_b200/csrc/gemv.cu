@@ -93,23 +93,32 @@ __device__ __forceinline__ void dequant_word_4b(uint32_t w, uint32_t* h) {
   h[2] = lop3_and_or(t, 0x003C003Cu, 0x5C005C00u);
   h[3] = lop3_and_or(t, 0x03C003C0u, 0x4C004C00u);
 }
-// p += sum over the 16 codes of a 2-bit word;  x16 = 16 activations as 8 half2 words
+// p + sum over the 16 codes of a 2-bit word;  x16 = 16 activations as 8 half2 words.  Four
+// independent accumulation chains: FHFMA has a long dependent-issue latency and a CTA runs only
+// 3-4 warps per scheduler.
 __device__ __forceinline__ float dot16_2b(const uint32_t* h, const uint32_t* x16, float p) {
+  float q0 = p, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    p = fhfma_sel(h[j], 0, x16[j >> 1], j & 1, p);
-    p = fhfma_sel(h[j], 1, x16[(j + 8) >> 1], j & 1, p);
+  for (int j = 0; j < 8; j += 2) {
+    q0 = fhfma_sel(h[j], 0, x16[j >> 1], j & 1, q0);
+    q1 = fhfma_sel(h[j], 1, x16[(j + 8) >> 1], j & 1, q1);
+    q2 = fhfma_sel(h[j + 1], 0, x16[(j + 1) >> 1], (j + 1) & 1, q2);
+    q3 = fhfma_sel(h[j + 1], 1, x16[(j + 9) >> 1], (j + 1) & 1, q3);
   }
-  return p;
+  return (q0 + q1) + (q2 + q3);
 }
-// p += sum over the 8 nibbles of a 4-bit word;  x8 = 8 activations as 4 half2 words
-__device__ __forceinline__ float dot8_4b(const uint32_t* h, const uint32_t* x8, float p) {
+// p + sum over the 8 nibbles of two 4-bit words;  x16 = the pool's 16 activations
+__device__ __forceinline__ float dot16_4b(const uint32_t* ha, const uint32_t* hb, const uint32_t* x16,
+                                          float p) {
+  float q0 = p, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    p = fhfma_sel(h[j], 0, x8[j >> 1], j & 1, p);
-    p = fhfma_sel(h[j], 1, x8[(j + 4) >> 1], j & 1, p);
+    q0 = fhfma_sel(ha[j], 0, x16[j >> 1], j & 1, q0);
+    q1 = fhfma_sel(ha[j], 1, x16[(j + 4) >> 1], j & 1, q1);
+    q2 = fhfma_sel(hb[j], 0, x16[4 + (j >> 1)], j & 1, q2);
+    q3 = fhfma_sel(hb[j], 1, x16[4 + ((j + 4) >> 1)], j & 1, q3);
   }
-  return p;
+  return (q0 + q1) + (q2 + q3);
 }
 // 4.0f + the 2-bit field of v at bit position pos (exact, no int->float conversion)
 __device__ __forceinline__ float four_plus_field(uint32_t v, int pos) {
@@ -239,9 +248,7 @@ __device__ __forceinline__ void gemv_block(const GemvRegs& g, const unsigned cha
         dequant_word_4b(g.wl[r], hb);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-          float p = fmaf(z4f[r], tB[b].w, tA[b].w);
-          p = dot8_4b(ha, xv[b], p);
-          p = dot8_4b(hb, xv[b] + 4, p);
+          const float p = dot16_4b(ha, hb, xv[b], fmaf(z4f[r], tB[b].w, tA[b].w));
           acc[r][b] = fmaf(s4[r], p, acc[r][b]);                         // :179,192
         }
       }
@@ -274,6 +281,14 @@ struct GemvPlan {
 
 constexpr int kGemvMaxWarps = 16, kGemvMaxStages = 4;
 
+// Profiling only (MXQ_GEMV_DBG & 8): per-CTA %globaltimer stamps {start, waited, staged, done}.
+__device__ unsigned long long g_gemv_trace[4 * 160];
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // Persistent: one CTA per SM walks its q row groups in rounds of rpr groups (= one ring stage).
 // warp = (row group of the round, K-slice phase); lane = 64-column block of the slice.
 // Dynamic shared memory: [nstages][stage] weight ring, then the activation image (gemv_block).
@@ -298,6 +313,8 @@ __global__ void __launch_bounds__(NB == 1 ? 512 : 256, NB == 1 ? 2 : 1) gemv_mxq
   const int stage_stride = (L.bytes + 127) & ~127;
   unsigned char* xsm = smem + (size_t)plan.nstages * stage_stride;
 
+  const bool trace = (plan.dbg & 8) && threadIdx.x == 0 && blockIdx.x < 160;
+  if (trace) g_gemv_trace[blockIdx.x * 4 + 0] = gtimer_ns();
   if (threadIdx.x == 0) {
     for (int i = 0; i < plan.nstages; ++i) mbar_init(&full[i], 1);
     mbar_fence_init();
@@ -318,6 +335,7 @@ __global__ void __launch_bounds__(NB == 1 ? 512 : 256, NB == 1 ? 2 : 1) gemv_mxq
   // Triggering before the wait was measured slower (profiles/probes/pdl_probe.cu): the scheduler
   // then stacks several CTAs of one grid on the SMs that happen to be free.
   griddep_launch_dependents();
+  if (trace) g_gemv_trace[blockIdx.x * 4 + 1] = gtimer_ns();
 
   // stage activations + per-group sums (one thread per (batch row, 16-column group))
   if (!(plan.dbg & 2)) {
@@ -350,6 +368,7 @@ __global__ void __launch_bounds__(NB == 1 ? 512 : 256, NB == 1 ? 2 : 1) gemv_mxq
     }
   }
   __syncthreads();
+  if (trace) g_gemv_trace[blockIdx.x * 4 + 2] = gtimer_ns();
 
   for (int round = 0; round < plan.rounds; ++round) {
     const int slot = round % plan.nstages;
@@ -425,6 +444,7 @@ __global__ void __launch_bounds__(NB == 1 ? 512 : 256, NB == 1 ? 2 : 1) gemv_mxq
       }
     }
   }
+  if (trace) g_gemv_trace[blockIdx.x * 4 + 3] = gtimer_ns();
 }
 
 // 4-bit word with one bias for all nibbles (shift per pair): nibble j at bits [4j+3:4j]; shifting
@@ -591,6 +611,11 @@ extern "C" int mxq_gemv_ex(const void* x, mxq_packed_t w, void* y, int64_t B, in
   if (B == 1) return launch_gemv<1>(xh, w, yh, (int)B, (int)IC, (int)OC, pdl, st);
   if (B == 2) return launch_gemv<2>(xh, w, yh, (int)B, (int)IC, (int)OC, pdl, st);
   return launch_gemv<4>(xh, w, yh, (int)B, (int)IC, (int)OC, pdl, st);
+}
+
+// profiling aid, not part of the documented surface: copies the stamps of the last traced launch
+extern "C" __attribute__((visibility("default"))) int mxq_debug_gemv_trace(unsigned long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_gemv_trace, sizeof(unsigned long long) * 4 * 160);
 }
 
 extern "C" int mxq_gemv(const void* x, mxq_packed_t w, void* y, int64_t B, int64_t IC, int64_t OC,
