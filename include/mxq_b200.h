@@ -137,10 +137,12 @@ MXQ_API int mxq_gemv(const void* x, mxq_packed_t w, void* y, int64_t B, int64_t 
              void* stream);
 
 /* Same, with flags.  By default the kernel is launched with the programmatic-dependent-launch
- * attribute: it may become resident while the previous kernel of `stream` is still running, and
- * until that kernel has completed it only prefetches its own weight stream into L2 (it reads x and
- * writes y strictly afterwards), so the overlap is safe after any predecessor.  MXQ_GEMV_NO_PDL
- * launches it fully serialised. */
+ * attribute: it may become resident while the previous kernel of `stream` is still running.  Until
+ * that kernel has completed it only reads the PACKED WEIGHT tensors (TMA bulk copies into shared
+ * memory); x is read and y written strictly afterwards.  The overlap is therefore safe unless the
+ * previous kernel of the stream writes `w` AND signals early completion itself
+ * (griddepcontrol.launch_dependents) -- no kernel of this library does.  MXQ_GEMV_NO_PDL launches
+ * fully serialised. */
 #define MXQ_GEMV_NO_PDL 1u
 MXQ_API int mxq_gemv_ex(const void* x, mxq_packed_t w, void* y, int64_t B, int64_t IC, int64_t OC,
                         unsigned flags, void* stream);

@@ -2,17 +2,21 @@
 //
 // Replaces mxq_quant/cuda_kernel/csrc/quantization/gemv_mxq_cuda.cu:39-273 (IC hard-wired to
 // 4096, one scalar cvt+FMA chain per weight, legacy stream) and gemv_cuda.cu:45-242,346-399.
-// This kernel is weight-stream (HBM) bound: 0.3756 B per weight.
-//   * warp = one second-order group (4 output rows) x a K-slice; lane = one 64-column block, so
-//     a lane's 128-bit weight load, its 4-bit tail word and its metadata are issued up front for
-//     all 4 rows (>= 100 B in flight per lane) and the activations of the block are loaded once
-//     for the 4 rows;
-//   * dequant two codes per SHF+LOP3 into fp16 {bias+q} pairs (code in the top mantissa bits) that
-//     FHFMA (fma.rn.f32.f16, sm_100) multiplies straight into an fp32 accumulator -- no
-//     int->float conversions, no per-weight subtraction; bias and zero-point are removed once per
-//     (row, group) with the group's activation sum;
-//   * the scale s2*(c - z2) is applied once per (row, group) on the fp32 group sum;
-//   * K-slices of a row group are reduced through shared memory in a fixed order.
+// This kernel is weight-stream (HBM) bound: 0.3756 B per weight.  Design (numbers: profiles/):
+//   * persistent grid, one CTA per SM owning a contiguous range of output rows, so each packed
+//     tensor's share is ONE contiguous byte range: a stage of the shared-memory ring is fetched
+//     with four 1-D TMA bulk copies (cp.async.bulk + mbarrier), issued before the activations
+//     are needed;
+//   * programmatic dependent launch: back-to-back GEMVs overlap the next kernel's launch and
+//     weight fetch with the current kernel's arithmetic (griddepcontrol.wait before x is read);
+//   * warp = one second-order group (4 output rows) x K slices of 2048 columns; lane = one
+//     64-column block (conflict-free 128-bit shared loads);
+//   * the activations are converted ONCE per CTA to block floating point (int16 mantissas per
+//     16-column group, split into signed high / unsigned low bytes) and the 2/4-bit codes meet
+//     them in dp4a -- IDP4A co-issues with the LOP3/SHF unpacking, fp16 FMAs do not
+//     (profiles/probes/fhfma_probe.cu); zero-point and scale s2*(c - z2) are applied once per
+//     (row, group) on the exact integer sum;
+//   * K slices of a row group are reduced through shared memory in a fixed order.
 // Any IC % 64 == 0 (metadata tiled in 4096-column chunks; identical to the reference at 4096);
 // the reference's activation-offset and batch-stride bugs (gemv_mxq_cuda.cu:50,119) are not
 // reproduced.
@@ -172,6 +176,28 @@ __device__ __forceinline__ uint32_t ldg_u16(const void* p) {
   return v;
 }
 
+// scales_2nd of one unit and, when a new row group starts, its 4-bit pool scale / zero words
+struct GemvPre {
+  uint32_t s2[3];
+  uint2 s4;
+  uint32_t z4w;
+};
+__device__ __forceinline__ void gemv_prefetch_meta(GemvPre& pre, const mxq_packed_t& w, int grp, int sl,
+                                                   int lane, int nblk, bool skip, bool new_group) {
+  if (skip) return;
+  const int blk = sl * 32 + lane;
+  if (blk < nblk) {
+    const __half* s2p = reinterpret_cast<const __half*>(w.scales_2nd) + ((size_t)grp * nblk + blk) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pre.s2[k] = ldg_u16(s2p + k);
+  }
+  if (new_group) {
+    const int oc0 = grp * 4;
+    pre.s4 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(w.scales_4b) + oc0));
+    pre.z4w = (uint32_t)__ldg(w.zeros_4b + (oc0 >> 3)) >> (4 * (oc0 & 7));
+  }
+}
+
 struct GemvRegs {     // one lane's share of a (4-row group, 64-column block): 27 registers
   uint4 wq[4];
   uint32_t wl[4], zs[4], z2, s2[3];
@@ -195,17 +221,76 @@ __device__ __forceinline__ void gemv_read(const unsigned char* st, const GemvSta
 //   [nblk][144 B]   the block's 64 fp16 activations (+ pad)
 //   tabA float4[nblk] = { 4*xs_k - xsb_k (k = 0,1,2),  -xsb_3 }   xs = sum x, xsb = sum bias*x
 //   tabB float4[nblk] = { -xs_k (k = 0..3) }
+// ---------------------------------------------------------------------------------------------
+// Integer inner product.  Measured on B200 (profiles/probes/fhfma_probe.cu): LOP3/SHF issue at one
+// warp-instruction per 2 cycles per scheduler, fp16 FMAs (HFMA2, FHFMA) compete with them for the
+// same issue slots, but IDP4A (dp4a) and FFMA/IMAD co-issue with them for free.  So the dot
+// products run on dp4a: the CTA converts each 16-column group of activations once into block
+// floating point -- int16 mantissas X_j = rint(x_j * 2^(14-E)), E = exponent of the group's
+// largest |x| (exact for every element within 2^-4 of it, absolute error <= 2^-16 of it otherwise)
+// -- stored as a signed high byte and an unsigned low byte; codes are unpacked four per register
+// ((w >> 2c) & 0x03030303, 7 ALU instructions per 16 codes); two dp4a chains give
+// sum q_j*hi_j and sum q_j*lo_j exactly, and
+//     sum_j (q_j - z) x_j = 2^(E-14) * [ 256*HI + LO - z * sum_j X_j ]        (integers < 2^24)
+// is converted once per (row, group) and scaled by s2*(c - z2) in fp32.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {   // a: u8 x4, b: s8 x4
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp4a_uu(uint32_t a, uint32_t b, int c) {   // a, b: u8 x4
+  int d;
+  asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int imad(int a, int b, int c) {
+  int d;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// x8: the group's activations as bytes, [0..3] high (signed), [4..7] low (unsigned); register c
+// holds elements {c, c+4, c+8, c+12} (2-bit groups) in bytes 0..3.   Returns 256*HI + LO.
+__device__ __forceinline__ int idot16_2b(uint32_t w, const uint32_t* x8) {
+  const uint32_t b0 = w & 0x03030303u, b1 = (w >> 2) & 0x03030303u, b2 = (w >> 4) & 0x03030303u,
+                 b3 = (w >> 6) & 0x03030303u;
+  int hi = dp4a_us(b0, x8[0], 0), lo = dp4a_uu(b0, x8[4], 0);
+  hi = dp4a_us(b1, x8[1], hi); lo = dp4a_uu(b1, x8[5], lo);
+  hi = dp4a_us(b2, x8[2], hi); lo = dp4a_uu(b2, x8[6], lo);
+  hi = dp4a_us(b3, x8[3], hi); lo = dp4a_uu(b3, x8[7], lo);
+  return imad(hi, 256, lo);
+}
+// pool: word a = columns 48..55, word b = 56..63 (nibble j at bits [4j+3:4j]); registers 0/1 hold
+// the even/odd columns of the first word, 2/3 of the second.
+__device__ __forceinline__ int idot16_4b(uint32_t wa, uint32_t wb, const uint32_t* x8) {
+  const uint32_t a0 = wa & 0x0F0F0F0Fu, a1 = (wa >> 4) & 0x0F0F0F0Fu, c0 = wb & 0x0F0F0F0Fu,
+                 c1 = (wb >> 4) & 0x0F0F0F0Fu;
+  int hi = dp4a_us(a0, x8[0], 0), lo = dp4a_uu(a0, x8[4], 0);
+  hi = dp4a_us(a1, x8[1], hi); lo = dp4a_uu(a1, x8[5], lo);
+  hi = dp4a_us(c0, x8[2], hi); lo = dp4a_uu(c0, x8[6], lo);
+  hi = dp4a_us(c1, x8[3], hi); lo = dp4a_uu(c1, x8[7], lo);
+  return imad(hi, 256, lo);
+}
+
+// Shared-memory image of the activations, per batch row b (stride `xb_stride` bytes):
+//   [nblk][144 B]     per block 4 groups x {4 words of high bytes, 4 words of low bytes} (+ pad)
+//   tabI int4[nblk]   -sum_j X_j of the block's 4 groups
+//   tabF float4[nblk] 2^(E-14) of the block's 4 groups
 template <int NB>
 __device__ __forceinline__ void gemv_block(const GemvRegs& g, const unsigned char* xsm,
                                            int xb_stride, int blk, int nblk, const float* s4,
-                                           const float* z4f, float (&acc)[4][NB]) {
-  float4 tA[NB], tB[NB];
+                                           const int* z4, float (&acc)[4][NB]) {
+  int4 tI[NB];
+  float4 tF[NB];
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     const unsigned char* base = xsm + (size_t)b * xb_stride + (size_t)nblk * kXBlkBytes;
-    tA[b] = reinterpret_cast<const float4*>(base)[blk];
-    tB[b] = reinterpret_cast<const float4*>(base + (size_t)nblk * 16)[blk];
+    tI[b] = reinterpret_cast<const int4*>(base)[blk];
+    tF[b] = reinterpret_cast<const float4*>(base + (size_t)nblk * 16)[blk];
   }
+  uint32_t zsh[4];     // zeros_and_scales >> 4: c_1 at [7:6], c_2 at [9:8], z1_2 at [1:0]
+#pragma unroll
+  for (int r = 0; r < 4; ++r) zsh[r] = g.zs[r] >> 4;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     uint32_t xv[NB][8];
@@ -225,31 +310,26 @@ __device__ __forceinline__ void gemv_block(const GemvRegs& g, const unsigned cha
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const uint32_t wk = k == 0 ? g.wq[r].x : (k == 1 ? g.wq[r].y : g.wq[r].z);
-        uint32_t h[8];
-        dequant_word_2b(wk, h);
         const uint32_t hc = k == 0 ? lop3_and_or(g.zs[r], 0x0300u, 0x4400u)
-                          : k == 1 ? lop3_and_or(g.zs[r] >> 4, 0x00C0u, 0x4C00u)
-                                   : lop3_and_or(g.zs[r] >> 4, 0x0300u, 0x4400u);
+                          : k == 1 ? lop3_and_or(zsh[r], 0x00C0u, 0x4C00u)
+                                   : lop3_and_or(zsh[r], 0x0300u, 0x4400u);
         const float S = fhfma_lo(hc, g.s2[k], S0);                       // :136
-        const float zf = four_plus_field(g.zs[r], 2 * k);                // 4 + z1
+        const int z1 = (int)(k == 0 ? (g.zs[r] & 3u) : k == 1 ? ((g.zs[r] >> 2) & 3u) : (zsh[r] & 3u));
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-          const float nxs = k == 0 ? tB[b].x : (k == 1 ? tB[b].y : tB[b].z);
-          const float nc0 = k == 0 ? tA[b].x : (k == 1 ? tA[b].y : tA[b].z);
-          const float p = dot16_2b(h, xv[b], fmaf(zf, nxs, nc0));
-          acc[r][b] = fmaf(S, p, acc[r][b]);                             // :153
+          const int nxs = k == 0 ? tI[b].x : (k == 1 ? tI[b].y : tI[b].z);
+          const float xsc = k == 0 ? tF[b].x : (k == 1 ? tF[b].y : tF[b].z);
+          const int d = imad(z1, nxs, idot16_2b(wk, xv[b]));
+          acc[r][b] = fmaf(S * xsc, (float)d, acc[r][b]);               // :153
         }
       }
     } else {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        uint32_t ha[4], hb[4];
-        dequant_word_4b(g.wq[r].w, ha);
-        dequant_word_4b(g.wl[r], hb);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-          const float p = dot16_4b(ha, hb, xv[b], fmaf(z4f[r], tB[b].w, tA[b].w));
-          acc[r][b] = fmaf(s4[r], p, acc[r][b]);                         // :179,192
+          const int d = imad(z4[r], tI[b].w, idot16_4b(g.wq[r].w, g.wl[r], xv[b]));
+          acc[r][b] = fmaf(s4[r] * tF[b].w, (float)d, acc[r][b]);       // :179,192
         }
       }
     }
@@ -293,7 +373,7 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 // warp = (row group of the round, K-slice phase); lane = 64-column block of the slice.
 // Dynamic shared memory: [nstages][stage] weight ring, then the activation image (gemv_block).
 template <int NB>
-__global__ void __launch_bounds__(NB == 1 ? 512 : 256, NB == 1 ? 2 : 1) gemv_mxq_kernel(
+__global__ void __launch_bounds__(NB == 1 ? 512 : 256, 1) gemv_mxq_kernel(
     const __half* __restrict__ x, mxq_packed_t w, __half* __restrict__ y, int B, int IC, int OC,
     GemvPlan plan) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -305,6 +385,7 @@ __global__ void __launch_bounds__(NB == 1 ? 512 : 256, NB == 1 ? 2 : 1) gemv_mxq
   const int ngrp_all = OC >> 2;
   const int grp_base = blockIdx.x * plan.q;
   const int qc = min(plan.q, ngrp_all - grp_base);      // row groups of this CTA
+  const int rounds = (qc + plan.rpr - 1) / plan.rpr;     // <= plan.rounds (the last CTA may be short)
   const int rgl = warp / plan.wpr, sl0 = warp - rgl * plan.wpr;
   const bool warp_on = rgl < plan.rpr;
   const int b0 = blockIdx.y * NB;
@@ -318,7 +399,7 @@ __global__ void __launch_bounds__(NB == 1 ? 512 : 256, NB == 1 ? 2 : 1) gemv_mxq
   if (threadIdx.x == 0) {
     for (int i = 0; i < plan.nstages; ++i) mbar_init(&full[i], 1);
     mbar_fence_init();
-    for (int i = 0; i < plan.nstages && i < plan.rounds; ++i) {
+    for (int i = 0; i < plan.nstages && i < rounds; ++i) {
       const int g0 = i * plan.rpr;
       if (g0 < qc)
         gemv_fill(smem + (size_t)i * stage_stride, L, &full[i], w, grp_base + g0,
@@ -329,6 +410,10 @@ __global__ void __launch_bounds__(NB == 1 ? 512 : 256, NB == 1 ? 2 : 1) gemv_mxq
     const size_t hi = ((size_t)(grp_base + qc) * nblk * 6) & ~(size_t)15;
     if (hi > lo) bulk_prefetch_l2(reinterpret_cast<const unsigned char*>(w.scales_2nd) + lo, (uint32_t)(hi - lo));
   }
+
+  // per-row-group scales of the warp's first unit (weights only: allowed before the wait)
+  GemvPre pre;
+  gemv_prefetch_meta(pre, w, grp_base + rgl, sl0, lane, nblk, !(warp_on && rgl < qc), true);
 
   griddep_wait();
   // Only now may the next kernel of the stream become resident (one generation of look-ahead).
@@ -348,29 +433,43 @@ __global__ void __launch_bounds__(NB == 1 ? 512 : 256, NB == 1 ? 2 : 1) gemv_mxq
       const int xblk = g >> 2, k = g & 3;
       unsigned char* xb = xsm + (size_t)b * xb_stride;
       uint4* dst = reinterpret_cast<uint4*>(xb + (size_t)xblk * kXBlkBytes + k * 32);
-      dst[0] = v0; dst[1] = v1;
       const uint32_t xw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-      float xs = 0.f, xsb2 = 0.f, xsb4 = 0.f;
+      float f[16];
+      float gmax = 0.f;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        xs = fhfma_sel(0x3C003C00u, 0, xw[j >> 1], j & 1, xs);
-        xsb2 = fhfma_sel(bias_half(bias2(j)), 0, xw[j >> 1], j & 1, xsb2);
+        f[j] = __half2float(__ushort_as_half((unsigned short)(xw[j >> 1] >> (16 * (j & 1)))));
+        gmax = fmaxf(gmax, fabsf(f[j]));
       }
-      if (k == 3) {
+      // block floating point: X_j = rint(x_j * 2^(14-E)), E = unbiased exponent of gmax
+      gmax = fminf(gmax, 65504.f);                      // inf/nan activations: keep the bit tricks finite
+      const uint32_t eb = __float_as_uint(gmax) >> 23;   // biased exponent (fp16 -> fp32 is never subnormal)
+      const float up = gmax > 0.f ? __uint_as_float((268u - eb) << 23) : 0.f;
+      const float xsc = gmax > 0.f ? __uint_as_float((eb - 14u) << 23) : 0.f;
+      uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+      int xs = 0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) xsb4 = fhfma_sel(bias_half(bias4(j)), 0, xw[j >> 1], j & 1, xsb4);
+      for (int j = 0; j < 16; ++j) {
+        const int X = __float2int_rn(fminf(fmaxf(f[j] * up, -32767.f), 32767.f));
+        xs += X;
+        // 2-bit groups: register j & 3, byte j >> 2;  pool: register (j>>3)*2 + (j&1), byte (j&7)>>1
+        const int reg = k < 3 ? (j & 3) : ((j >> 3) * 2 + (j & 1));
+        const int byte = k < 3 ? (j >> 2) : ((j & 7) >> 1);
+        hi[reg] |= ((uint32_t)(X >> 8) & 0xFFu) << (8 * byte);
+        lo[reg] |= ((uint32_t)X & 0xFFu) << (8 * byte);
       }
-      const float xsb = k < 3 ? xsb2 : xsb4;
-      float* tA = reinterpret_cast<float*>(xb + (size_t)nblk * kXBlkBytes) + xblk * 4 + k;
-      float* tB = reinterpret_cast<float*>(xb + (size_t)nblk * (kXBlkBytes + 16)) + xblk * 4 + k;
-      *tA = k < 3 ? fmaf(4.f, xs, -xsb) : -xsb;
-      *tB = -xs;
+      dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      dst[1] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      int* tI = reinterpret_cast<int*>(xb + (size_t)nblk * kXBlkBytes) + xblk * 4 + k;
+      float* tF = reinterpret_cast<float*>(xb + (size_t)nblk * (kXBlkBytes + 16)) + xblk * 4 + k;
+      *tI = -xs;
+      *tF = xsc;
     }
   }
   __syncthreads();
   if (trace) g_gemv_trace[blockIdx.x * 4 + 2] = gtimer_ns();
 
-  for (int round = 0; round < plan.rounds; ++round) {
+  for (int round = 0; round < rounds; ++round) {
     const int slot = round % plan.nstages;
     const uint32_t parity = (uint32_t)(round / plan.nstages) & 1u;
     const unsigned char* st = smem + (size_t)slot * stage_stride;
@@ -382,35 +481,32 @@ __global__ void __launch_bounds__(NB == 1 ? 512 : 256, NB == 1 ? 2 : 1) gemv_mxq
     for (int r = 0; r < 4; ++r)
 #pragma unroll
       for (int b = 0; b < NB; ++b) acc[r][b] = 0.f;
-    float s4[4], z4f[4];
-    GemvRegs cur;
-    const __half* s2p = reinterpret_cast<const __half*>(w.scales_2nd) + (size_t)grp * nblk * 3;
-    int blk = sl0 * 32 + lane;
-    if (on) {
-      const int oc0 = grp * 4;
-      const __half* s4p = reinterpret_cast<const __half*>(w.scales_4b) + oc0;
-      const uint32_t z4w = (uint32_t)__ldg(w.zeros_4b + (oc0 >> 3)) >> (4 * (oc0 & 7));
+    float s4[4];
+    int z4[4];
+    {
+      const __half2 lo = *reinterpret_cast<const __half2*>(&pre.s4.x);
+      const __half2 hi = *reinterpret_cast<const __half2*>(&pre.s4.y);
+      s4[0] = __low2float(lo); s4[1] = __high2float(lo);
+      s4[2] = __low2float(hi); s4[3] = __high2float(hi);
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        s4[r] = __half2float(__ldg(s4p + r));
-        z4f[r] = (float)((z4w >> (4 * r)) & 0xF);
-      }
-      if (blk < nblk) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) cur.s2[k] = ldg_u16(s2p + (size_t)blk * 3 + k);
-      }
+      for (int r = 0; r < 4; ++r) z4[r] = (int)((pre.z4w >> (4 * r)) & 0xF);
     }
+    GemvRegs cur;
     mbar_wait(&full[slot], parity);
     if (on) {
       for (int sl = sl0; sl < plan.ksl; sl += plan.wpr) {
-        blk = sl * 32 + lane;
-        if (blk < nblk) {
-          if (sl != sl0) {
+        const int blk = sl * 32 + lane;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) cur.s2[k] = ldg_u16(s2p + (size_t)blk * 3 + k);
-          }
+        for (int k = 0; k < 3; ++k) cur.s2[k] = pre.s2[k];
+        // scales of the warp's next unit (next slice, or the first slice of the next round)
+        {
+          const bool last = sl + plan.wpr >= plan.ksl;
+          gemv_prefetch_meta(pre, w, last ? grp + plan.rpr : grp, last ? sl0 : sl + plan.wpr, lane,
+                             nblk, last && (round + 1 >= rounds || gl + plan.rpr >= qc), last);
+        }
+        if (blk < nblk) {
           gemv_read(st, L, rgl, blk, nblk, nchunk, cur);
-          if (!(plan.dbg & 1)) gemv_block<NB>(cur, xsm, xb_stride, blk, nblk, s4, z4f, acc);
+          if (!(plan.dbg & 1)) gemv_block<NB>(cur, xsm, xb_stride, blk, nblk, s4, z4, acc);
           else acc[0][0] += __uint_as_float(cur.wq[0].x ^ cur.wq[1].y ^ cur.wq[2].z ^ cur.wq[3].w ^ cur.wl[0] ^ cur.wl[1] ^ cur.wl[2] ^ cur.wl[3] ^ cur.zs[0] ^ cur.zs[1] ^ cur.zs[2] ^ cur.zs[3] ^ cur.z2 ^ cur.s2[0] ^ cur.s2[1] ^ cur.s2[2]);
         }
       }
@@ -427,7 +523,7 @@ __global__ void __launch_bounds__(NB == 1 ? 512 : 256, NB == 1 ? 2 : 1) gemv_mxq
     const int t = threadIdx.x;
     if (t == 0) {
       const int g0 = (round + plan.nstages) * plan.rpr;
-      if (round + plan.nstages < plan.rounds && g0 < qc) {
+      if (round + plan.nstages < rounds) {
         fence_proxy_async();
         gemv_fill(smem + (size_t)slot * stage_stride, L, &full[slot], w, grp_base + g0,
                   min(plan.rpr, qc - g0), nblk, nchunk);
@@ -517,7 +613,7 @@ using namespace mxq;
 
 namespace {
 
-constexpr size_t kSmemPerSM = 227 * 1024, kSmemCtaReserve = 1024;
+constexpr size_t kSmemPerSM = 227 * 1024, kSmemCtaReserve = 4096;   // static smem + per-CTA reserve
 
 template <int NB>
 int launch_gemv(const __half* x, const mxq_packed_t& w, __half* y, int B, int IC, int OC,

@@ -19,6 +19,10 @@ __global__ void k(float* out, uint32_t seed, long long* cyc) {
       if (MODE == 2) asm volatile("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(h[i]) : "r"(seed), "r"(seed + 1));
       if (MODE == 3) asm volatile("lop3.b32 %0, %0, %1, %2, 0xEA;" : "+r"(h[i]) : "r"(seed), "r"(seed + 7));
       if (MODE == 4) { asm volatile("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(a[i]) : "h"(ws), "h"(xs)); asm volatile("lop3.b32 %0, %0, %1, %2, 0xEA;" : "+r"(h[i]) : "r"(seed), "r"(seed + 7)); }
+      if (MODE == 6) asm volatile("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(h[i]) : "r"(seed), "r"(seed + 7));
+      if (MODE == 7) { asm volatile("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(h[i]) : "r"(seed), "r"(seed + 7)); asm volatile("lop3.b32 %0, %0, %1, %2, 0xEA;" : "+r"(h[(i + 4) & 7]) : "r"(seed), "r"(seed + 7)); }
+      if (MODE == 8) { asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(h[i]) : "r"(seed), "r"(seed + 7)); asm volatile("lop3.b32 %0, %0, %1, %2, 0xEA;" : "+r"(h[(i + 4) & 7]) : "r"(seed), "r"(seed + 7)); }
+      if (MODE == 9) { asm volatile("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(h[i]) : "r"(seed), "r"(seed + 1)); asm volatile("lop3.b32 %0, %0, %1, %2, 0xEA;" : "+r"(h[(i + 4) & 7]) : "r"(seed), "r"(seed + 7)); }
       if (MODE == 5) { asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(a[i]) : "f"(1.0001f), "f"(0.5f)); asm volatile("lop3.b32 %0, %0, %1, %2, 0xEA;" : "+r"(h[i]) : "r"(seed), "r"(seed + 7)); }
     }
   }
@@ -30,15 +34,15 @@ __global__ void k(float* out, uint32_t seed, long long* cyc) {
 }
 int main() {
   float* out; long long* cyc; cudaMalloc(&out, 148 * 512 * 4); cudaMallocManaged(&cyc, 8);
-  const char* names[] = {"FHFMA", "FFMA", "HFMA2", "LOP3", "FHFMA+LOP3", "FFMA+LOP3"};
-  for (int m = 0; m < 6; ++m) {
+  const char* names[] = {"FHFMA", "FFMA", "HFMA2", "LOP3", "FHFMA+LOP3", "FFMA+LOP3", "IDP4A", "IDP4A+LOP3", "IMAD+LOP3", "HFMA2+LOP3"};
+  for (int m = 0; m < 10; ++m) {
     for (int rep = 0; rep < 2; ++rep) {
       switch (m) { case 0: k<0><<<148, 512>>>(out, 123, cyc); break; case 1: k<1><<<148, 512>>>(out, 123, cyc); break;
         case 2: k<2><<<148, 512>>>(out, 123, cyc); break; case 3: k<3><<<148, 512>>>(out, 123, cyc); break;
-        case 4: k<4><<<148, 512>>>(out, 123, cyc); break; case 5: k<5><<<148, 512>>>(out, 123, cyc); break; }
+        case 4: k<4><<<148, 512>>>(out, 123, cyc); break; case 5: k<5><<<148, 512>>>(out, 123, cyc); break; case 6: k<6><<<148, 512>>>(out, 123, cyc); break; case 7: k<7><<<148, 512>>>(out, 123, cyc); break; case 8: k<8><<<148, 512>>>(out, 123, cyc); break; case 9: k<9><<<148, 512>>>(out, 123, cyc); break; }
       cudaDeviceSynchronize();
     }
-    const double instr_per_smsp = (double)N * 8 * (m >= 4 ? 2 : 1) * 4;   // 4 warps per SMSP
+    const double instr_per_smsp = (double)N * 8 * ((m == 4 || m == 5 || m >= 7) ? 2 : 1) * 4;   // 4 warps per SMSP
     printf("%-12s %8lld cycles  %.2f cycles per warp-instr per SMSP\n", names[m], *cyc, *cyc / instr_per_smsp);
   }
   return 0;

@@ -1,4 +1,5 @@
-"""Decode GEMV timing per shape (CUDA graph of one GEMV per distinct weight set, > L2) and K-split sweep."""
+"""Decode GEMV timing per shape (CUDA graph of one GEMV per distinct weight set, > L2), with and
+without programmatic dependent launch.  MXQ_GEMV_WARPS / MXQ_GEMV_WPR / MXQ_GEMV_STAGES override the plan."""
 import os
 import sys
 
@@ -27,7 +28,7 @@ for oc, ic in ((4096, 4096), (11008, 4096), (4096, 11008)):
     for B in (1, 4):
         x = torch.randn(B, ic, device=dev).half()
         y = torch.empty(B, oc, device=dev, dtype=torch.float16)
-        for ks in ("auto", "auto-nopdl", "1", "2", "3", "4"):
+        for ks in ("auto", "auto-nopdl"):
             pdl = ks != "auto-nopdl"
             if ks.startswith("auto"):
                 os.environ.pop("MXQ_GEMV_WPR", None)

@@ -80,6 +80,19 @@ def test_gemv_random_bits(cuda, OC, IC, B):
     assert _rel_err(y, ref) <= TOL
 
 
+@pytest.mark.parametrize("OC,IC,B", [(11008, 256, 4), (11008, 256, 1), (11008, 4096, 2), (4104, 128, 2),
+                                     (1192, 64, 1), (9472, 192, 3), (64, 11008, 4), (64, 28672, 1), (64, 28672, 2)])
+def test_gemv_short_last_cta(cuda, OC, IC, B):
+    """Row counts that leave the last persistent CTA with fewer row groups (and rounds) than the
+    others, for every batch tiling (regression: a stage that is never filled must not be awaited)."""
+    from mxq_b200 import ops
+    p = O.random_packed(OC, IC, seed=OC + IC + B)
+    x = np.random.default_rng(B).standard_normal((B, IC)).astype(np.float16)
+    ref = O.gemm_mxq_f32(x, p)
+    y = ops.gemv(torch.from_numpy(x).to(cuda), packed_to_dev(p, cuda)).cpu().numpy()
+    assert _rel_err(y, ref) <= TOL
+
+
 def test_gemv_packed_weights_end_to_end(cuda):
     """weights -> mxq_pack -> mxq_gemv equals x @ decode(pack(W))^T and approximates x @ W^T."""
     from mxq_b200 import ops
