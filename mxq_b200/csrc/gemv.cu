@@ -628,7 +628,7 @@ int launch_gemv(const __half* x, const mxq_packed_t& w, __half* y, int B, int IC
   if (const char* e = getenv("MXQ_GEMV_DBG")) plan.dbg = atoi(e);
   // Choose (warps, warps per row group, ring depth).  Cost = sequential units per warp
   // (rounds x slices), +30 % if two CTAs cannot share an SM (no overlap with the next GEMV under
-  // PDL), +15 % if the ring holds less than 64 KB or the whole CTA share; ties -> fewer warps.
+  // PDL), +15 % unless the ring holds the whole CTA share or >= 2 stages and 64 KB; ties -> fewer warps.
   int W = 0, force_w = 0, force_wpr = 0, force_s = 0;
   if (const char* e = getenv("MXQ_GEMV_WARPS")) force_w = atoi(e);    // tuning knobs
   if (const char* e = getenv("MXQ_GEMV_WPR")) force_wpr = atoi(e);
@@ -648,7 +648,7 @@ int launch_gemv(const __half* x, const mxq_packed_t& w, __half* y, int B, int IC
         const size_t smem = ns * stage + ximg;
         if (smem + kSmemCtaReserve > kSmemPerSM) continue;
         const bool twice = NB == 1 && 2 * (smem + kSmemCtaReserve) <= kSmemPerSM && warps <= 16;
-        const bool deep = ns * stage >= 64 * 1024 || ns >= rounds;
+        const bool deep = ns >= rounds || (ns >= 2 && ns * stage >= 64 * 1024);
         const double cost = (double)rounds * (double)ceil_div(plan.ksl, wpr) * (twice ? 1.0 : 1.3) *
                                 (deep ? 1.0 : 1.15) + 1e-3 * warps + 1e-4 * wpr + 1e-5 * ns;
         if (cost < best) {
