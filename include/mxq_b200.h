@@ -62,6 +62,23 @@ MXQ_API int mxq_fakequant_fwd(const void* x, void* out, uint8_t* codes, int64_t 
 MXQ_API int mxq_ste_bwd(const void* grad_out, const void* x, void* grad_in, int64_t n, int dtype,
                 float lo, float hi, void* stream);
 
+/* ---- (f-1) SymQuantizer / AsymQuantizer.forward   LLM-QAT/models/utils_quant.py:31-95,98-199 --
+ * Activation / KV-cache fake quantizers (call sites utils_quant.py:717-721,
+ * modeling_llama_quant.py:323-329).  The tensor is `nseg` contiguous segments of `seglen`
+ * elements, one statistic per segment (|x|max for mode 0 = symmetric, min/max for mode 1 =
+ * asymmetric), every op rounded to `dtype` like the reference's eager ATen chain:
+ *   sym : s = reciprocal(m + 1e-6) * (2^(bits-1) - 1);  out = round(x * s) / (s + 1e-6)
+ *   asym: a = (max - min) + 1e-8;  out = round(((x - min) / a) * (2^bits - 1)) / (2^bits - 1) * a + min
+ * Segment i is live iff (i % period) < valid; dead segments use the zero statistic (the
+ * reference's 3-D branch slices dim 1 with column-group indices, :56-64,:144-157, so tokens
+ * beyond (C // G) * G keep zero-initialised statistics).  period = 1 disables this.
+ * seglen * sizeof(dtype) % 16 == 0.  The backward is mxq_ste_bwd (same clipped STE, :89-95).
+ * workspace: mxq_segquant_workspace_bytes(nseg, seglen, dtype) (0 for short segments). */
+MXQ_API size_t mxq_segquant_workspace_bytes(int64_t nseg, int64_t seglen, int dtype);
+MXQ_API int mxq_segquant_fwd(const void* x, void* out, int64_t nseg, int64_t seglen, int dtype,
+                             int mode, int bits, int64_t period, int64_t valid, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 /* ---- (a-5/a-8) calibration statistics --------------------------------------------------------
  * sumsq[c] (+)= sum_t X[t,c]^2 in fp32.  This is the whole of what MXQGPT.add_batch's K x K
  * Hessian is used for (diag(H)==0, mxqgpt.py:369-383,399-403) and the Wanda statistic of

@@ -21,6 +21,7 @@ _DTYPE = {torch.float32: MXQ_F32, torch.float16: MXQ_F16, torch.bfloat16: MXQ_BF
 # every symbol include/mxq_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "mxq_version", "mxq_error_string", "mxq_fakequant_fwd", "mxq_ste_bwd",
+    "mxq_segquant_workspace_bytes", "mxq_segquant_fwd",
     "mxq_colsumsq_workspace_bytes", "mxq_colsumsq", "mxq_wanda_metric",
     "mxq_ptq_workspace_bytes", "mxq_ptq_quant", "mxq_rowquant",
     "mxq_pack_workspace_bytes", "mxq_pack", "mxq_ptq_quant_pack", "mxq_unpack", "mxq_gemv", "mxq_gemv_ex", "mxq_awq_gemv",
@@ -53,6 +54,9 @@ def lib() -> C.CDLL:
     L.mxq_error_string.argtypes = [i32]
     L.mxq_fakequant_fwd.argtypes = [vp, vp, vp, i64, i64, i32, i32, i32, vp, vp]
     L.mxq_ste_bwd.argtypes = [vp, vp, vp, i64, i32, f32, f32, vp]
+    L.mxq_segquant_workspace_bytes.restype = sz
+    L.mxq_segquant_workspace_bytes.argtypes = [i64, i64, i32]
+    L.mxq_segquant_fwd.argtypes = [vp, vp, i64, i64, i32, i32, i32, i64, i64, vp, sz, vp]
     L.mxq_colsumsq_workspace_bytes.restype = sz
     L.mxq_colsumsq_workspace_bytes.argtypes = [i64, i64]
     L.mxq_colsumsq.argtypes = [vp, i64, i64, i32, vp, f32, f32, i32, vp, sz, vp]

@@ -22,6 +22,7 @@ LIB = os.path.join(HERE, "libmxq_b200.so")
 SOURCES = {
     "misc.cu": [],
     "fakequant.cu": ["-fmad=false"],
+    "actquant.cu": ["-fmad=false"],
     "calib.cu": [],
     "ptq.cu": ["-fmad=false"],
     "pack.cu": ["-fmad=false"],

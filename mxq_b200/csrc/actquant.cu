@@ -1,0 +1,359 @@
+// Activation / KV-cache fake quantizers (sm_100a): SymQuantizer and AsymQuantizer of
+// LLM-QAT/models/utils_quant.py:31-199 (call sites utils_quant.py:717-721,
+// modeling_llama_quant.py:323-329).
+//
+// The reference expands one statistic (|x|max, or min/max) over a *segment* of the tensor and then
+// runs an elementwise chain, every op rounded to the tensor dtype:
+//   Sym  (:84-85)   s = reciprocal(m + 1e-6) * qmax;  out = round(x * s) / (s + 1e-6),
+//                   qmax = 2^(bits-1) - 1  (python `int / tensor` is reciprocal-then-multiply)
+//   Asym (:179-183) out = round(((x - b) / (a + 1e-8)) * S) / S * (a + 1e-8) + b,  S = 2^bits - 1
+// Every branch of the reference is "contiguous segments of equal length":
+//   2-D [N, K] group-wise : segments = the K/G groups of every row (G = 128 sym, 8 asym)
+//   3-D [B, T, C]         : the reference slices DIM 1 with the column-group indices (:56-64,
+//                           :144-157), i.e. one statistic per token over all C channels, and only
+//                           for tokens t < (C // G) * G -- later tokens keep the zero statistic
+//   4-D [B, H, T, D]      : one statistic per (b, h) (:72-79, :171-187)
+//   layerwise             : one segment
+// `period` / `valid` express the token quirk: segment i is live iff (i % period) < valid, dead
+// segments use m = 0 (sym) or a = b = 0 (asym) exactly like the reference's zero-initialised
+// tensors.
+//
+// Three kernel families, all memory bound (2 * sizeof(T) bytes per element when the statistic can
+// be taken in one pass):
+//   small segments (<= 32 sixteen-byte chunks, power of two): lane = chunk, xor-shuffle
+//     reduction inside the sub-warp that owns the segment, ONE pass over HBM;
+//   medium segments (<= 3072 chunks, e.g. one token's 4096 / 11008 channels): one CTA per
+//     segment keeps its chunks in registers across a block-wide min/max, ONE pass over HBM;
+//   large segments: a partial min/max kernel (grid = splits x segments) and an apply kernel with
+//     the same decomposition whose second read hits L2 for tensors below 126 MB.
+// Division is IEEE-exact: correctly rounded reciprocal + one Markstein step (common.cuh), with an
+// IEEE fallback whenever the fast quotient is not finite or the divisor is outside the normal
+// checked range (oracle/div_check_sym.c checks the fast path against IEEE division).
+#include "common.cuh"
+
+namespace mxq {
+
+enum { kSym = 0, kAsym = 1 };
+
+struct SegParams {       // per segment, broadcast to its elements
+  float p0, p1, p2, p3;  // sym: s, s2 = s + 1e-6, RN(1/s2), fast;  asym: a, b, RN(1/a), fast
+};
+
+// The fast quotient (reciprocal + one Markstein step) is IEEE-exact for divisors in
+// [1e-30, 1e30] and dividends with |t| >= 1e-30 or t == 0 (oracle/div_check_sym.c, 3e9 operand
+// pairs); anything else -- and any non-finite result -- takes IEEE division.
+__device__ __forceinline__ bool divisor_fast(float a) { return a >= 1e-30f && a <= 1e30f; }
+
+template <typename T>
+__device__ __forceinline__ SegParams seg_params(int mode, float mn, float mx, float qscale) {
+  using D = DT<T>;
+  SegParams P;
+  if (mode == kSym) {
+    const float m = fmaxf(fabsf(mn), fabsf(mx));                       // max |x| (:53,:61)
+    const float c6 = D::rnd(1e-6f);   // the CPU reference casts python scalars to the tensor dtype
+    const float d = D::rnd(__fadd_rn(m, c6));
+    // (:84) `qmax / tensor` is Tensor.__rdiv__ = tensor.reciprocal() * qmax: two rounded ops
+    const float s = D::rnd(__fmul_rn(D::rnd(__frcp_rn(d)), qscale));
+    const float s2 = D::rnd(__fadd_rn(s, c6));                         // (:85)
+    const bool fast = divisor_fast(s2);
+    P.p0 = s; P.p1 = s2; P.p2 = fast ? __frcp_rn(s2) : 0.f; P.p3 = fast ? 1.f : 0.f;
+  } else {
+    const float a = D::rnd(__fadd_rn(D::rnd(__fsub_rn(mx, mn)), D::rnd(1e-8f)));   // alpha + 1e-8 (:179)
+    const bool fast = divisor_fast(a);
+    P.p0 = a; P.p1 = mn; P.p2 = fast ? __frcp_rn(a) : 0.f; P.p3 = fast ? 1.f : 0.f;
+  }
+  return P;
+}
+
+// quotient t / a, correctly rounded; r = RN(1/a), fast = divisor_fast(a)
+__device__ __forceinline__ float div_exact(float t, float a, float r, bool fast) {
+  const float q = div_rn_by(t, a, r);
+  const bool ok = fast && (fabsf(t) >= 1e-30f || t == 0.f) && fabsf(q) <= 3.0e38f;
+  return ok ? q : __fdiv_rn(t, a);
+}
+
+template <typename T>
+__device__ __forceinline__ float quant_elem(int mode, float x, const SegParams& P, float qscale,
+                                            float rq) {
+  using D = DT<T>;
+  const bool fast = P.p3 != 0.f;
+  if (mode == kSym) {
+    const float t = D::rnd(__fmul_rn(x, P.p0));
+    const float r = rintf(t);                                          // torch.round: half to even
+    return D::rnd(div_exact(r, P.p1, P.p2, fast));                     // .div(s + 1e-6) (:85)
+  }
+  float t = D::rnd(__fsub_rn(x, P.p1));
+  t = D::rnd(div_exact(t, P.p0, P.p2, fast));                          // input_normalized (:179)
+  t = D::rnd(__fmul_rn(t, qscale));
+  const float q = rintf(t);                                            // (:181)
+  t = D::rnd(div_exact(q, qscale, rq, true));                          // .div(s), s in [3, 65535]
+  t = D::rnd(__fmul_rn(t, P.p0));
+  return D::rnd(__fadd_rn(t, P.p1));                                   // (:183)
+}
+
+template <typename T>
+__device__ __forceinline__ void chunk_minmax(const uint4& c, float& mn, float& mx) {
+  float f[DT<T>::EPC];
+  DT<T>::unpack(c, f);
+#pragma unroll
+  for (int e = 0; e < DT<T>::EPC; ++e) { mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]); }
+}
+// torch.max / torch.min propagate NaN, fminf / fmaxf drop it: track NaN separately
+template <typename T>
+__device__ __forceinline__ bool chunk_has_nan(const uint4& c) {
+  float f[DT<T>::EPC];
+  DT<T>::unpack(c, f);
+  bool n = false;
+#pragma unroll
+  for (int e = 0; e < DT<T>::EPC; ++e) n |= (f[e] != f[e]);
+  return n;
+}
+
+template <typename T>
+__device__ __forceinline__ uint4 chunk_apply(int mode, const uint4& c, const SegParams& P,
+                                             float qscale, float rq) {
+  float f[DT<T>::EPC];
+  DT<T>::unpack(c, f);
+#pragma unroll
+  for (int e = 0; e < DT<T>::EPC; ++e) f[e] = quant_elem<T>(mode, f[e], P, qscale, rq);
+  return DT<T>::pack(f);
+}
+
+// ---- small segments: one pass -----------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) segquant_small_kernel(const uint4* __restrict__ x,
+                                                             uint4* __restrict__ out,
+                                                             int64_t nchunks, int cps, int mode,
+                                                             float qscale, int64_t period,
+                                                             int64_t valid) {
+  const float rq = __frcp_rn(qscale);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // nchunks is a multiple of cps and cps divides 32, so a segment never straddles warps and the
+  // lanes of a segment enter / leave the loop together
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nchunks; i += stride) {
+    const uint4 c = ld_stream(x + i);
+    float mn = INFINITY, mx = -INFINITY;
+    chunk_minmax<T>(c, mn, mx);
+    unsigned nan = chunk_has_nan<T>(c);
+    for (int o = cps >> 1; o > 0; o >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+    }
+    if (nan) { mn = NAN; mx = NAN; }
+    const int64_t seg = i / cps;
+    if (period > 1 && (seg % period) >= valid) { mn = 0.f; mx = 0.f; }
+    const SegParams P = seg_params<T>(mode, mn, mx, qscale);
+    st_stream(out + i, chunk_apply<T>(mode, c, P, qscale, rq));
+  }
+}
+
+// ---- medium segments: one CTA per segment, chunks stay in registers ---------------------------
+template <typename T, int THREADS, int NC>
+__global__ void __launch_bounds__(THREADS) segquant_block_kernel(const uint4* __restrict__ x,
+                                                                 uint4* __restrict__ out, int cps,
+                                                                 int mode, float qscale,
+                                                                 int64_t period, int64_t valid) {
+  __shared__ float2 part[THREADS / 32];
+  __shared__ unsigned nanflag;
+  const int64_t seg = blockIdx.x;
+  const uint4* xs = x + seg * cps;
+  uint4* os = out + seg * cps;
+  if (threadIdx.x == 0) nanflag = 0;
+  uint4 c[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int idx = i * THREADS + threadIdx.x;
+    if (idx < cps) c[i] = ld_stream(xs + idx);
+  }
+  __syncthreads();
+  float mn = INFINITY, mx = -INFINITY;
+  bool nan = false;
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    if (i * THREADS + threadIdx.x < cps) {
+      chunk_minmax<T>(c[i], mn, mx);
+      nan |= chunk_has_nan<T>(c[i]);
+    }
+  }
+  mn = warp_min(mn); mx = warp_max(mx);
+  if (nan) atomicOr(&nanflag, 1u);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = make_float2(mn, mx);
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; ++w) { mn = fminf(mn, part[w].x); mx = fmaxf(mx, part[w].y); }
+  if (nanflag) { mn = NAN; mx = NAN; }
+  if (period > 1 && (seg % period) >= valid) { mn = 0.f; mx = 0.f; }
+  const SegParams P = seg_params<T>(mode, mn, mx, qscale);
+  const float rq = __frcp_rn(qscale);
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int idx = i * THREADS + threadIdx.x;
+    if (idx < cps) st_stream(os + idx, chunk_apply<T>(mode, c[i], P, qscale, rq));
+  }
+}
+
+template <typename T, int THREADS, int NC>
+static void launch_block(const void* x, void* out, int64_t nseg, int cps, int mode, float qscale,
+                         int64_t period, int64_t valid, cudaStream_t st) {
+  segquant_block_kernel<T, THREADS, NC><<<(unsigned)nseg, THREADS, 0, st>>>(
+      (const uint4*)x, (uint4*)out, cps, mode, qscale, period, valid);
+}
+
+// ---- large segments: partial statistics, then apply ---------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) seg_reduce_kernel(const uint4* __restrict__ x,
+                                                         float2* __restrict__ ws, int64_t cps,
+                                                         int64_t slice) {
+  __shared__ float2 part[8];
+  __shared__ unsigned nanflag;
+  const int64_t seg = blockIdx.y, c0 = (int64_t)blockIdx.x * slice, c1 = min(cps, c0 + slice);
+  const uint4* xs = x + seg * cps;
+  if (threadIdx.x == 0) nanflag = 0;
+  __syncthreads();
+  float mn = INFINITY, mx = -INFINITY;
+  bool nan = false;
+  for (int64_t i = c0 + threadIdx.x; i < c1; i += 256) {
+    const uint4 c = xs[i];
+    chunk_minmax<T>(c, mn, mx);
+    nan |= chunk_has_nan<T>(c);
+  }
+  mn = warp_min(mn); mx = warp_max(mx);
+  if (nan) atomicOr(&nanflag, 1u);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = make_float2(mn, mx);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { mn = fminf(mn, part[w].x); mx = fmaxf(mx, part[w].y); }
+    if (nanflag) { mn = NAN; mx = NAN; }
+    ws[seg * gridDim.x + blockIdx.x] = make_float2(mn, mx);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) seg_apply_kernel(const uint4* __restrict__ x,
+                                                        uint4* __restrict__ out,
+                                                        const float2* __restrict__ ws, int64_t cps,
+                                                        int64_t slice, int mode, float qscale,
+                                                        int64_t period, int64_t valid) {
+  __shared__ SegParams sp;
+  const int64_t seg = blockIdx.y, c0 = (int64_t)blockIdx.x * slice, c1 = min(cps, c0 + slice);
+  if (threadIdx.x < 32) {
+    float mn = INFINITY, mx = -INFINITY;
+    bool nan = false;
+    for (int s = threadIdx.x; s < (int)gridDim.x; s += 32) {
+      const float2 v = ws[seg * gridDim.x + s];
+      nan |= (v.x != v.x);
+      mn = fminf(mn, v.x); mx = fmaxf(mx, v.y);
+    }
+    mn = warp_min(mn); mx = warp_max(mx);
+    if (__any_sync(0xffffffffu, nan)) { mn = NAN; mx = NAN; }
+    if (period > 1 && (seg % period) >= valid) { mn = 0.f; mx = 0.f; }
+    if (threadIdx.x == 0) sp = seg_params<T>(mode, mn, mx, qscale);
+  }
+  __syncthreads();
+  const SegParams P = sp;
+  const float rq = __frcp_rn(qscale);
+  const uint4* xs = x + seg * cps;
+  uint4* os = out + seg * cps;
+  for (int64_t i = c0 + threadIdx.x; i < c1; i += 256) os[i] = chunk_apply<T>(mode, ld_stream(xs + i), P, qscale, rq);
+}
+
+constexpr int64_t kBlockMaxChunks = 3072;   // medium path: <= 12 chunks per thread, 256 threads
+
+static bool seg_is_small(int64_t cps) { return cps <= 32 && (cps & (cps - 1)) == 0; }
+static bool seg_is_medium(int64_t nseg, int64_t cps) {
+  return !seg_is_small(cps) && cps <= kBlockMaxChunks && nseg >= kNumSMs && nseg <= 0x7fffffffll;
+}
+
+static int64_t seg_splits(int64_t nseg, int64_t cps) {
+  // enough CTAs to fill the machine several times over, at least 8 chunks per thread-slice
+  int64_t splits = ceil_div((int64_t)kNumSMs * 8, nseg);
+  const int64_t max_splits = max((int64_t)1, cps / 256);
+  if (splits > max_splits) splits = max_splits;
+  if (splits > 65535) splits = 65535;
+  return max((int64_t)1, splits);
+}
+
+template <typename T>
+static int launch_segquant(const void* x, void* out, int64_t nseg, int64_t seglen, int mode,
+                           int bits, int64_t period, int64_t valid, void* ws, size_t ws_bytes,
+                           cudaStream_t st) {
+  const int64_t cps = seglen * (int64_t)sizeof(T) / 16;
+  const float qscale = mode == kSym ? (float)((1ll << (bits - 1)) - 1) : (float)((1ll << bits) - 1);
+  const bool small = cps <= 32 && (cps & (cps - 1)) == 0;
+  if (small) {
+    const int64_t nchunks = nseg * cps;
+    int64_t blocks = ceil_div(nchunks, 256 * 4);
+    blocks = min(blocks, (int64_t)kNumSMs * 16);
+    segquant_small_kernel<T><<<(unsigned)max((int64_t)1, blocks), 256, 0, st>>>(
+        (const uint4*)x, (uint4*)out, nchunks, (int)cps, mode, qscale, period, valid);
+    MXQ_LAUNCH_RESULT();
+  }
+  if (seg_is_medium(nseg, cps)) {
+    const int c = (int)cps;
+    if (c <= 128) launch_block<T, 128, 1>(x, out, nseg, c, mode, qscale, period, valid, st);
+    else if (c <= 256) launch_block<T, 128, 2>(x, out, nseg, c, mode, qscale, period, valid, st);
+    else if (c <= 512) launch_block<T, 128, 4>(x, out, nseg, c, mode, qscale, period, valid, st);
+    else if (c <= 1024) launch_block<T, 256, 4>(x, out, nseg, c, mode, qscale, period, valid, st);
+    else if (c <= 2048) launch_block<T, 256, 8>(x, out, nseg, c, mode, qscale, period, valid, st);
+    else launch_block<T, 256, 12>(x, out, nseg, c, mode, qscale, period, valid, st);
+    MXQ_LAUNCH_RESULT();
+  }
+  if (nseg > 65535 * 1024ll) return MXQ_E_SHAPE;
+  const int64_t splits = seg_splits(nseg, cps);
+  if (ws_bytes < (size_t)(nseg * splits) * sizeof(float2)) return MXQ_E_WORKSPACE;
+  if (!ws) return MXQ_E_NULL;
+  const int64_t slice = ceil_div(cps, splits);
+  // gridDim.y is limited to 65535: fold the excess into several launches
+  for (int64_t s0 = 0; s0 < nseg; s0 += 65535) {
+    const int64_t ns = min((int64_t)65535, nseg - s0);
+    const dim3 grid((unsigned)splits, (unsigned)ns);
+    const uint4* xs = (const uint4*)x + s0 * cps;
+    float2* w2 = (float2*)ws + s0 * splits;
+    seg_reduce_kernel<T><<<grid, 256, 0, st>>>(xs, w2, cps, slice);
+    // (seg % period) must use the global segment index: period divides 65535 * k only by luck, so
+    // shift `valid` handling into the kernel through an offset-free trick -- launches start at
+    // multiples of 65535, hence pass the tensors pre-offset and require period == 1 beyond them
+    seg_apply_kernel<T><<<grid, 256, 0, st>>>(xs, (uint4*)out + s0 * cps, w2, cps, slice, mode, qscale,
+                                              nseg > 65535 ? 1 : period, valid);
+  }
+  MXQ_LAUNCH_RESULT();
+}
+
+}  // namespace mxq
+
+using namespace mxq;
+
+extern "C" size_t mxq_segquant_workspace_bytes(int64_t nseg, int64_t seglen, int dtype) {
+  if (nseg <= 0 || seglen <= 0) return 0;
+  const int esize = dtype == MXQ_F32 ? 4 : 2;
+  const int64_t cps = seglen * esize / 16;
+  if (seg_is_small(cps) || seg_is_medium(nseg, cps)) return 0;
+  return (size_t)(nseg * seg_splits(nseg, cps)) * sizeof(float2);
+}
+
+extern "C" int mxq_segquant_fwd(const void* x, void* out, int64_t nseg, int64_t seglen, int dtype,
+                                int mode, int bits, int64_t period, int64_t valid, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  if (nseg < 0 || seglen < 0) return MXQ_E_SHAPE;
+  if (nseg == 0 || seglen == 0) return MXQ_OK;
+  MXQ_CHECK_PTR(x);
+  MXQ_CHECK_PTR(out);
+  if (dtype != MXQ_F32 && dtype != MXQ_F16 && dtype != MXQ_BF16) return MXQ_E_DTYPE;
+  if (mode != kSym && mode != kAsym) return MXQ_E_UNSUPPORTED;
+  if (bits < 2 || bits > 16) return MXQ_E_SHAPE;
+  if (period < 1 || valid < 0) return MXQ_E_SHAPE;
+  const int esize = dtype == MXQ_F32 ? 4 : 2;
+  if ((seglen * esize) % 16) return MXQ_E_SHAPE;
+  {
+    const int64_t cps = seglen * esize / 16;
+    if (period > 1 && nseg > 65535 && !seg_is_small(cps) && !seg_is_medium(nseg, cps))
+      return MXQ_E_UNSUPPORTED;
+  }
+  cudaStream_t st = as_stream(stream);
+  switch (dtype) {
+    case MXQ_F32: return launch_segquant<float>(x, out, nseg, seglen, mode, bits, period, valid, workspace, workspace_bytes, st);
+    case MXQ_F16: return launch_segquant<__half>(x, out, nseg, seglen, mode, bits, period, valid, workspace, workspace_bytes, st);
+    default: return launch_segquant<__nv_bfloat16>(x, out, nseg, seglen, mode, bits, period, valid, workspace, workspace_bytes, st);
+  }
+}

@@ -53,6 +53,9 @@ template <typename T, bool kRef, bool kFast16, int LPG, bool kCodes>
 __global__ void __launch_bounds__(kFQThreads) fakequant_fwd_kernel(const FQParams p) {
   using D = DT<T>;
   using P = P16<typename std::conditional<kFast16, T, __half>::type>;
+  // the reference's eager CPU kernels cast the python scalar 1e-8 to the tensor dtype first
+  // (bf16: 1.0012e-8, fp16: 0), then add in fp32 and round
+  const float kEps = D::rnd(1e-8f);
   constexpr int EPC = D::EPC;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* bufs = smem;
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(kFQThreads) fakequant_fwd_kernel(const FQParam
       pmin = fminf(pmin, v.x); pmax = fmaxf(pmax, v.y);
     }
     // utils_quant.py:369-377: fp32 subtract, cast to the tensor dtype on assignment (:383)
-    const float a_pool = D::rnd(__fadd_rn(D::rnd(__fsub_rn(pmax, pmin)), 1e-8f));
+    const float a_pool = D::rnd(__fadd_rn(D::rnd(__fsub_rn(pmax, pmin)), kEps));
     const float b_pool = pmin;
     const float r_pool = __frcp_rn(a_pool);
 
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(kFQThreads) fakequant_fwd_kernel(const FQParam
           const bool pooled = kRef ? ((g & 3) == 3) : ((gtab[g] & MXQ_POOL_FLAG) != 0);
           uint32_t b2 = prmt_b32(mm, mm, 0x1010);
           const uint32_t alpha2 = P::sub(prmt_b32(mm, mm, 0x3232), b2);      // max - min (:358-361)
-          const float ax = __fadd_rn(P::lo(alpha2), 1e-8f);                  // alpha + 1e-8 (:456)
+          const float ax = __fadd_rn(P::lo(alpha2), kEps);                  // alpha + 1e-8 (:456)
           uint32_t a2 = P::pack(ax, ax);                                     // rounded to the dtype
           float a = P::lo(a2);
           float r = rcp_rn_normal(a);
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(kFQThreads) fakequant_fwd_kernel(const FQParam
           if (!valid) continue;
           const int g = c >> lpg_shift;
           const bool pooled = kRef ? ((g & 3) == 3) : ((gtab[g] & MXQ_POOL_FLAG) != 0);
-          float a = D::rnd(__fadd_rn(D::rnd(__fsub_rn(lmax, lmin)), 1e-8f));  // alpha + 1e-8 (:456)
+          float a = D::rnd(__fadd_rn(D::rnd(__fsub_rn(lmax, lmin)), kEps));  // alpha + 1e-8 (:456)
           float b = lmin;
           float r = rcp_rn_normal(a);
           float s = s_low, rs = rs_low;

@@ -56,6 +56,53 @@ def ste_bwd(grad_out: torch.Tensor, x: torch.Tensor, lo: float, hi: float) -> to
     return gi
 
 
+def segquant_plan(shape, mode: str, layerwise: bool):
+    """How Sym/AsymQuantizer (utils_quant.py:31-199) segment a tensor of `shape`:
+    returns (nseg, seglen, period, valid)."""
+    G = 128 if mode == "sym" else 8                       # :58 / :146
+    n = 1
+    for d in shape:
+        n *= int(d)
+    if layerwise:
+        return 1, n, 1, 1                                  # :50-51 / :130-132
+    nd = len(shape)
+    if nd == 2:
+        N, K = shape
+        if K % G:
+            # trailing K % G columns keep zero statistics in the reference (:59-68); rare and
+            # not expressible as equal segments
+            raise NotImplementedError(f"in_features {K} must be a multiple of the group size {G}")
+        return N * (K // G), G, 1, 1
+    if nd == 3:
+        # the loop slices DIM 1 (tokens) with column-group indices and reduces over dim -1:
+        # one statistic per token over all C channels, only for tokens < (C // G) * G
+        B, T, Cc = shape
+        live = min(T, (Cc // G) * G)
+        return B * T, Cc, (T if live < T else 1), (live if live < T else 1)
+    if nd == 4:
+        B, H, T, D = shape
+        return B * H, T * D, 1, 1                          # :72-79 / :171-187
+    raise ValueError("Sym/AsymQuantizer: unsupported tensor rank")   # reference raises ValueError
+
+
+def segquant_fwd(x: torch.Tensor, mode: str, bits: int, nseg: int, seglen: int, period: int = 1,
+                 valid: int = 1, workspace=None) -> torch.Tensor:
+    """Segment-statistic fake quantization (SymQuantizer / AsymQuantizer forward)."""
+    L.require_cuda(x)
+    x = x.contiguous()
+    if nseg * seglen != x.numel():
+        raise ValueError("nseg * seglen must equal the number of elements")
+    out = torch.empty_like(x)
+    need = L.lib().mxq_segquant_workspace_bytes(nseg, seglen, L.dtype_enum(x))
+    if workspace is None or workspace.numel() < need:
+        workspace = _ws(need, x.device)
+    rc = L.lib().mxq_segquant_fwd(L.ptr(x), L.ptr(out), nseg, seglen, L.dtype_enum(x),
+                                  0 if mode == "sym" else 1, int(bits), int(period), int(valid),
+                                  L.ptr(workspace), workspace.numel(), L.stream())
+    L.check(rc, "mxq_segquant_fwd")
+    return out
+
+
 def colsumsq(X: torch.Tensor, out: torch.Tensor | None = None, prev_scale: float = 0.0,
              add_scale: float = 1.0, workspace: torch.Tensor | None = None) -> torch.Tensor:
     """out = prev_scale*out + add_scale * sum_tokens X^2 (per column, fp32)."""

@@ -1,6 +1,8 @@
 """Drop-in for the hot-path symbols of LLM-QAT/models/utils_quant.py:
-``MXAsymQuantizer`` (:310-475) and ``QuantizeLinear`` (:601-727), backed by the fused sm_100a
-kernels in csrc/fakequant.cu.  Same names, argument order and autograd contract as the reference.
+``MXAsymQuantizer`` (:310-475), ``QuantizeLinear`` (:601-727) and the activation / KV-cache
+quantizers ``SymQuantizer`` (:31-95) and ``AsymQuantizer`` (:98-199), backed by the fused sm_100a
+kernels in csrc/fakequant.cu and csrc/actquant.cu.  Same names, argument order and autograd
+contract as the reference.
 """
 from __future__ import annotations
 
@@ -8,6 +10,62 @@ import torch
 import torch.nn as nn
 
 from . import ops
+
+
+def _clip_bounds(clip_val, dtype):
+    lo, hi = (float(v) for v in clip_val.detach().to("cpu", torch.float32).tolist())
+    if dtype != torch.float32:
+        # input.ge(clip_val[1]) compares in the tensor dtype: the 0-dim clip value is cast
+        lo = float(torch.tensor(lo).to(dtype))
+        hi = float(torch.tensor(hi).to(dtype))
+    return lo, hi
+
+
+class _SegQuantizer(torch.autograd.Function):
+    """Shared body of SymQuantizer / AsymQuantizer: one statistic per contiguous segment
+    (ops.segquant_plan states how the reference segments 2-D / 3-D / 4-D tensors), clipped
+    straight-through backward (utils_quant.py:89-95,192-199)."""
+    MODE = "sym"
+
+    @classmethod
+    def _fwd(cls, ctx, input, clip_val, num_bits, layerwise):
+        ctx.save_for_backward(input, clip_val)
+        if input.dim() > 4 or input.dim() < 2:
+            raise ValueError
+        nseg, seglen, period, valid = ops.segquant_plan(tuple(input.shape), cls.MODE, bool(layerwise))
+        return ops.segquant_fwd(input, cls.MODE, int(num_bits), nseg, seglen, period, valid)
+
+    @staticmethod
+    def _bwd(ctx, grad_output):
+        input, clip_val = ctx.saved_tensors
+        lo, hi = _clip_bounds(clip_val, input.dtype)
+        return ops.ste_bwd(grad_output, input, lo, hi), None, None, None
+
+
+class SymQuantizer(_SegQuantizer):
+    """|x|max uniform quantization, group 128 (utils_quant.py:31-95)."""
+    MODE = "sym"
+
+    @staticmethod
+    def forward(ctx, input, clip_val, num_bits, layerwise):
+        return SymQuantizer._fwd(ctx, input, clip_val, num_bits, layerwise)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return _SegQuantizer._bwd(ctx, grad_output)
+
+
+class AsymQuantizer(_SegQuantizer):
+    """min-max quantization, group 8 (utils_quant.py:98-199)."""
+    MODE = "asym"
+
+    @staticmethod
+    def forward(ctx, input, clip_val, num_bits, layerwise):
+        return AsymQuantizer._fwd(ctx, input, clip_val, num_bits, layerwise)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return _SegQuantizer._bwd(ctx, grad_output)
 
 
 class MXAsymQuantizer(torch.autograd.Function):
@@ -33,11 +91,7 @@ class MXAsymQuantizer(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_output):
         input, clip_val = ctx.saved_tensors
-        lo, hi = (float(v) for v in clip_val.detach().to("cpu", torch.float32).tolist())
-        if input.dtype != torch.float32:
-            # input.ge(clip_val[1]) compares in the tensor dtype: the 0-dim clip value is cast
-            lo = float(torch.tensor(lo).to(input.dtype))
-            hi = float(torch.tensor(hi).to(input.dtype))
+        lo, hi = _clip_bounds(clip_val, input.dtype)
         grad_input = ops.ste_bwd(grad_output, input, lo, hi)
         return grad_input, None, None, None
 
@@ -55,10 +109,8 @@ class QuantizeLinear(nn.Linear):
         self.weight_layerwise = weight_layerwise
         self.is_qk = is_qk
         self.symmetric = symmetric
-        if self.a_bits < 32 and self.a_bits > 2:
-            # Sym/AsymQuantizer activation quantizers (utils_quant.py:31-199) are the "next" row
-            # of SURVEY.md 8f; they are off in the reference recipe `run_train.sh 2 32 32`.
-            raise NotImplementedError("activation quantization (a_bits < 32) is not on the MXQ hot path yet")
+        if self.a_bits < 32 and self.a_bits > 2:                  # utils_quant.py:622-626
+            self.act_quantizer = SymQuantizer if symmetric else AsymQuantizer
 
     def forward(self, input_):
         assert len(self.weight.size()) == 2
@@ -72,6 +124,9 @@ class QuantizeLinear(nn.Linear):
         else:
             # w_bits == 1 sign quantizer / BiT-style branch (:649-715): outside the MXQ path.
             raise NotImplementedError("w_bits < 2 is not part of the MXQ hot path")
+        if self.a_bits < 32 and self.a_bits > 2:                  # utils_quant.py:717-721
+            act_clip_val = torch.tensor([-2.0, 2.0])
+            input_ = self.act_quantizer.apply(input_, act_clip_val, self.a_bits, self.act_layerwise)
         out = nn.functional.linear(input_, weight)
         if self.bias is not None:
             out += self.bias.view(1, -1).expand_as(out)

@@ -11,6 +11,7 @@ Reference entry points executed (nothing is copied from them):
   mxq_quant/lib/mxqgpt.py:353-452         MXQGPT.add_batch / fasterquant(blocksize=16)
   mxq_quant/lib/layerwrapper.py:22-35     WrappedGPT.add_batch
   mxq_quant/lib/quantizer.py:23-180       Quantizer (through fasterquant, and directly)
+  LLM-QAT/models/utils_quant.py:31-199    SymQuantizer / AsymQuantizer forward / backward
 """
 from __future__ import annotations
 
@@ -149,6 +150,64 @@ def gen_quantizer(quantizer):
     print("quantizer.npz", len(out), "arrays")
 
 
+def actquant_cases():
+    """name -> (fp32 tensor, layerwise).  Shapes chosen to reach every branch of
+    utils_quant.py:50-81 / :130-187, including the 3-D token-slicing quirk (T > (C // G) * G)."""
+    g = torch.Generator().manual_seed(4)
+    sym, asym = {}, {}
+    x = torch.randn(16, 256, generator=g)
+    x[2, :] = 0.0                       # zero row: max_input = 0 -> s = 127 / 1e-6
+    x[3, :128] = 1e-7                   # max_input comparable to the 1e-6 guard
+    x[4, 5] = 2.5
+    x[4, 6] = -2.0                      # STE clip plants
+    x[5, :] *= 300.0
+    sym["2d_16x256"] = (x, False)
+    sym["3d_2x12x256"] = (torch.randn(2, 12, 256, generator=g), False)
+    sym["3d_dead_1x130x128"] = (torch.randn(1, 130, 128, generator=g), False)   # tokens 128,129 dead
+    sym["3d_1x160x1024"] = (torch.randn(1, 160, 1024, generator=g) * 3.0, False)
+    sym["4d_2x3x8x16"] = (torch.randn(2, 3, 8, 16, generator=g), False)
+    sym["layerwise_4x256"] = (torch.randn(4, 256, generator=g), True)
+    y = torch.randn(16, 64, generator=g) * 0.5
+    y[0, :8] = 0.25                     # constant group: alpha = 0 -> divide by 1e-8
+    y[1, :] = 0.0
+    y[2, 3] = 2.5
+    y[2, 4] = -2.0
+    y[3, :] *= 1e-4
+    asym["2d_16x64"] = (y, False)
+    asym["3d_dead_2x20x16"] = (torch.randn(2, 20, 16, generator=g), False)      # tokens 16..19 dead
+    asym["3d_1x160x1024"] = (torch.randn(1, 160, 1024, generator=g), False)
+    asym["4d_2x4x16x8"] = (torch.randn(2, 4, 16, 8, generator=g), False)
+    asym["layerwise_4x256"] = (torch.randn(4, 256, generator=g), True)
+    return sym, asym
+
+
+def gen_actquant(utils_quant):
+    """SymQuantizer / AsymQuantizer forward + backward (utils_quant.py:31-199)."""
+    out = {}
+    clip = torch.tensor([-2.0, 2.0])
+    sym, asym = actquant_cases()
+    for mode, fn, cases in (("sym", utils_quant.SymQuantizer, sym), ("asym", utils_quant.AsymQuantizer, asym)):
+        for dname, td in TD.items():
+            for cname, (x32, layerwise) in cases.items():
+                for bits in (8, 4):
+                    if bits == 4 and not cname.startswith(("2d", "3d_dead")):
+                        continue
+                    x = x32.to(td).clone().requires_grad_(True)
+                    y = fn.apply(x, clip, bits, layerwise)
+                    key = f"{mode}/{dname}/{cname}/b{bits}"
+                    out[key + "/y"] = y.detach().float().numpy()
+                    if bits == 8:
+                        out[f"{mode}/{dname}/{cname}/x"] = x.detach().float().numpy()
+                    if cname.startswith("2d") and bits == 8:
+                        gg = torch.Generator().manual_seed(5)
+                        go = torch.randn(x.shape, generator=gg).to(td)
+                        y.backward(go)
+                        out[key + "/go"] = go.float().numpy()
+                        out[key + "/gi"] = x.grad.float().numpy()
+    np.savez_compressed(os.path.join(OUT, "actquant.npz"), **out)
+    print("actquant.npz", len(out), "arrays")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -157,6 +216,7 @@ def main():
     gen_fakequant(utils_quant)
     gen_fasterquant(mxqgpt_mod, layerwrapper)
     gen_quantizer(quantizer)
+    gen_actquant(utils_quant)
 
 
 if __name__ == "__main__":

@@ -127,7 +127,8 @@ def fakequant_fwd(x, dtype: str = "fp32", num_bits: int = 2, group: int = 16,
         a4 = rnd((pmax - pmin).astype(F32))        # fp32 subtract then cast on assignment
         alpha[:, pool] = a4
         beta[:, pool] = pmin
-    a = rnd(alpha + F32(1e-8))                     # alpha + 1e-8 (:456)
+    # the CPU kernel casts the python scalar to the tensor dtype before adding (bf16: 1.0012e-8)
+    a = rnd(alpha + rnd(F32(1e-8)))                # alpha + 1e-8 (:456)
     a3, b3, s3 = a[:, :, None], beta[:, :, None], s[:, :, None]
     with np.errstate(divide="ignore", invalid="ignore"):
         t = rnd(xg - b3)
@@ -141,6 +142,96 @@ def fakequant_fwd(x, dtype: str = "fp32", num_bits: int = 2, group: int = 16,
     if return_aux:
         return out, q.reshape(N, K), alpha, beta, s
     return out
+
+
+# --------------------------------------------------------------------------------------
+# (f-1) SymQuantizer / AsymQuantizer.forward   LLM-QAT/models/utils_quant.py:31-95, 98-199
+# --------------------------------------------------------------------------------------
+
+def _act_segments(shape, group: int, layerwise: bool):
+    """The statistic layout of utils_quant.py:50-81 / :130-187 as (view shape with the reduced
+    axis last, live mask over the leading axes or None).
+      layerwise            : one statistic for the tensor (:50-51, :130-132)
+      2-D [N, K]           : the loop slices dim 1 = columns: per (row, group of `group` columns)
+      3-D [B, T, C]        : the SAME loop slices dim 1 = TOKENS i*G:(i+1)*G for i < C // G and
+                             reduces over dim -1: per-token statistic over all C channels, tokens
+                             >= (C // G) * G keep the zero-initialised statistic (:56-64, :144-157)
+      4-D [B, H, T, D]     : per (b, h) over T*D (:72-79, :171-187)"""
+    shape = tuple(int(d) for d in shape)
+    if layerwise:
+        return (1, int(np.prod(shape))), None
+    if len(shape) == 2:
+        N, K = shape
+        if K % group:
+            raise NotImplementedError("trailing K % group columns keep zero statistics")
+        return (N * (K // group), group), None
+    if len(shape) == 3:
+        B, T, Cc = shape
+        live = (np.arange(T) < (Cc // group) * group)
+        return (B * T, Cc), np.tile(live, B)
+    if len(shape) == 4:
+        B, H, T, D = shape
+        return (B * H, T * D), None
+    raise ValueError
+
+
+def sym_quant(x, dtype: str = "fp32", num_bits: int = 8, layerwise: bool = False):
+    """SymQuantizer.forward (utils_quant.py:38-87): max_input = max|x| per segment;
+    s = (2**(bits-1) - 1) / (max_input + 1e-6) -- python-int / tensor dispatches to
+    Tensor.__rdiv__ = tensor.reciprocal() * int, i.e. TWO rounded ops (:84);
+    output = round(input * s).div(s + 1e-6) (:85)."""
+    rnd = rounder(dtype)
+    x = np.asarray(x, dtype=F32)
+    view, live = _act_segments(x.shape, 128, layerwise)
+    xs = x.reshape(view)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        if xs.shape[0] and xs.shape[1]:
+            m = np.abs(xs).max(axis=1, keepdims=True)
+            m = np.where(np.isnan(xs).any(axis=1, keepdims=True), F32(np.nan), m)
+        else:
+            m = np.zeros((xs.shape[0], 1), dtype=F32)
+        if live is not None:
+            m = np.where(live[:, None], m, F32(0))
+        qmax = F32(2 ** (num_bits - 1) - 1)
+        c6 = rnd(F32(1e-6))                        # python scalars are cast to the tensor dtype first
+        d = rnd(m + c6)
+        s = rnd(rnd(F32(1.0) / d) * qmax)
+        t = rnd(xs * s)
+        q = np.rint(t).astype(F32)
+        out = rnd(q / rnd(s + c6))
+    return out.reshape(x.shape)
+
+
+def asym_quant(x, dtype: str = "fp32", num_bits: int = 8, layerwise: bool = False):
+    """AsymQuantizer.forward (utils_quant.py:105-185): alpha = max - min, beta = min per
+    segment; input_normalized = (input - beta) / (alpha + 1e-8) (:179); s = 2**bits - 1;
+    quant_input = round(input_normalized * s).div(s) (:181); output = quant_input *
+    (alpha + 1e-8) + beta (:183).  Every op rounded to the tensor dtype."""
+    rnd = rounder(dtype)
+    x = np.asarray(x, dtype=F32)
+    view, live = _act_segments(x.shape, 8, layerwise)
+    xs = x.reshape(view)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        if xs.shape[0] and xs.shape[1]:
+            mn = xs.min(axis=1, keepdims=True)
+            mx = xs.max(axis=1, keepdims=True)
+        else:
+            mn = np.zeros((xs.shape[0], 1), dtype=F32)
+            mx = mn.copy()
+        if live is not None:
+            mn = np.where(live[:, None], mn, F32(0))
+            mx = np.where(live[:, None], mx, F32(0))
+        alpha = rnd(mx - mn)
+        a = rnd(alpha + rnd(F32(1e-8)))            # python scalars are cast to the tensor dtype first
+        s = F32(2 ** num_bits - 1)
+        t = rnd(xs - mn)
+        t = rnd(t / a)
+        t = rnd(t * s)
+        q = np.rint(t).astype(F32)
+        t = rnd(q / s)
+        t = rnd(t * a)
+        out = rnd(t + mn)
+    return out.reshape(x.shape)
 
 
 # --------------------------------------------------------------------------------------

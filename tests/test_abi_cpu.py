@@ -108,5 +108,21 @@ def test_mirror_signatures_match_reference():
         "scales_4b", "zeros_4b", "group_size"]
     lin = QuantizeLinear(64, 32, w_bits=2)
     assert list(lin.state_dict().keys()) == ["weight"]
-    with pytest.raises(NotImplementedError):
-        QuantizeLinear(64, 32, w_bits=2, a_bits=8)
+    from mxq_b200 import AsymQuantizer, SymQuantizer
+    assert QuantizeLinear(64, 32, w_bits=2, a_bits=8).act_quantizer is SymQuantizer      # :622-626
+    assert QuantizeLinear(64, 32, w_bits=2, a_bits=8, symmetric=False).act_quantizer is AsymQuantizer
+    assert not hasattr(QuantizeLinear(64, 32, w_bits=2, a_bits=2), "act_quantizer")
+    with pytest.raises(RuntimeError, match="CUDA"):                 # no CPU fallback
+        SymQuantizer.apply(torch.zeros(2, 128), torch.tensor([-2.0, 2.0]), 8, False)
+
+
+def test_segquant_plan_follows_reference_slicing():
+    # utils_quant.py:56-64 / :144-157: 2-D -> column groups; 3-D -> per-token statistics with
+    # tokens beyond (C // G) * G dead; 4-D -> per (b, h); layerwise -> one segment
+    assert ops.segquant_plan((16, 256), "sym", False) == (32, 128, 1, 1)
+    assert ops.segquant_plan((16, 64), "asym", False) == (128, 8, 1, 1)
+    assert ops.segquant_plan((2, 12, 256), "sym", False) == (24, 256, 1, 1)
+    assert ops.segquant_plan((1, 130, 128), "sym", False) == (130, 128, 130, 128)
+    assert ops.segquant_plan((2, 20, 16), "asym", False) == (40, 16, 20, 16)
+    assert ops.segquant_plan((2, 3, 8, 16), "sym", False) == (6, 128, 1, 1)
+    assert ops.segquant_plan((4, 256), "asym", True) == (1, 1024, 1, 1)

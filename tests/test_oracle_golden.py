@@ -93,3 +93,23 @@ def test_quantizer_direct(golden_dir):
         assert np.array_equal(y, Q[key + "/y"])
         assert np.array_equal(q.astype(np.uint8), Q[key + "/codes"])
         assert np.array_equal(sq, Q[key + "/scale"]) and np.array_equal(zero, Q[key + "/zero"])
+
+
+def test_actquant_bit_exact(golden_dir):
+    """SymQuantizer / AsymQuantizer restatements vs the unmodified reference (all ranks, layerwise,
+    the 3-D token-slicing quirk, fp32 / bf16 / fp16; NaNs of 0/0 groups must coincide)."""
+    A = np.load(os.path.join(golden_dir, "actquant.npz"))
+    n = 0
+    for k in sorted(k for k in A.files if k.endswith("/y")):
+        mode, dtype, case, b, _ = k.split("/")
+        x = A[f"{mode}/{dtype}/{case}/x"]
+        fn = O.sym_quant if mode == "sym" else O.asym_quant
+        y = fn(x, dtype, int(b[1:]), case.startswith("layerwise"))
+        ref = A[k]
+        same = (y.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(y) & np.isnan(ref))
+        assert same.all(), k
+        if k[:-2] + "/gi" in A.files:
+            gi = O.ste_bwd(A[k[:-2] + "/go"], x)
+            assert np.array_equal(gi.view(np.uint32), A[k[:-2] + "/gi"].view(np.uint32)), k
+        n += 1
+    assert n >= 45
