@@ -65,9 +65,10 @@ __device__ __forceinline__ SegParams seg_params(int mode, float mn, float mx, fl
   return P;
 }
 
-// quotient t / a, correctly rounded; r = RN(1/a), fast = divisor_fast(a)
+// quotient t / a for a > 0, correctly rounded; r = RN(1/a), fast = divisor_fast(a).  The
+// correction step turns a -0 quotient into +0 (the residual is +0), so the sign is restored from t.
 __device__ __forceinline__ float div_exact(float t, float a, float r, bool fast) {
-  const float q = div_rn_by(t, a, r);
+  const float q = copysignf(div_rn_by(t, a, r), t);
   const bool ok = fast && (fabsf(t) >= 1e-30f || t == 0.f) && fabsf(q) <= 3.0e38f;
   return ok ? q : __fdiv_rn(t, a);
 }
