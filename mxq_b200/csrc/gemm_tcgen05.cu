@@ -21,6 +21,8 @@
 // The dequantized operand never touches HBM: weights cost 0.3756 B each per M tile.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mxq {
@@ -154,6 +156,8 @@ struct Params {
   int npeers;                //   over NVLink (fused column all-gather: every tile is stored to all)
   int ldy, col0;             // output row stride (elements) and first output column of this shard
   int M, IC, OC;
+  int dbg;                   // profiling only (MXQ_GEMM_DBG): 1 = one M half, 2 = no TMA after the first ring fill
+  unsigned long long* dbg_host;   // debugging only (MXQ_GEMM_DBG_PTR): pinned host memory for watchdog records
 };
 
 template <bool kDenseB>
@@ -200,6 +204,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_mxq_kernel(const __grid_const
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
+        if ((p.dbg & 2) && kb >= STAGES) {        // profiling: operands stay stale, no smem writes
+          mbar_arrive(&full_a[s]);
+          if (kDenseB) mbar_arrive(&full_b[s]);
+          continue;
+        }
         mbar_arrive_expect_tx(&full_a[s], A_STAGE_BYTES);
         tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_x, kb * BK, m0, &full_a[s]);
         if (kDenseB) {
@@ -222,6 +231,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_mxq_kernel(const __grid_const
         const uint32_t b_addr = smem_u32(smem_b + s * B_STAGE_BYTES);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+          if ((p.dbg & 1) && h == 1) break;       // profiling: half the MMAs
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t ad = make_smem_desc(a_addr + h * (128 * BK * 2) + k * (UMMA_K * 2));
@@ -414,6 +424,392 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_mxq_kernel(const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+
+// =============================================================================================
+// CTA-pair variant (cta_group::2).  Measured on B200 (profiles/probes/probe_gemm_smem.py): a
+// single-CTA tcgen05.mma with both operands in shared memory fetches them at 64 B/cycle, i.e. a
+// 128 x 256 x 16 MMA takes (4 KB + 8 KB) / 64 = 192 cycles instead of its 128-cycle floor -- the
+// single-CTA kernel above tops out near 70 % of the tensor peak however fast the dequantizers are.
+// A CTA pair issues ONE M = 256 MMA per K step: each SM fetches its own 128 x 16 A slice and HALF
+// of B (128 weight rows x 16), 8 KB per 128 cycles = the floor, and each CTA dequantizes only 128
+// weight rows per K block.
+//
+//   cluster (2,1,1) along M: rank r owns tokens [m0 + 256 r, +256) (two M = 128 halves, 512 TMEM
+//   columns) and dequantizes weight rows [n0 + 128 r, +128) of the pair's 256;
+//   warp 0      : TMA producer of its CTA's A tile; transaction bytes of BOTH CTAs land on the
+//                 leader's full_a barrier (cp.async.bulk.tensor .cta_group::2)
+//   warp 1      : TMEM alloc (cta_group::2, both CTAs); the leader's lane 0 issues every MMA and
+//                 multicasts tcgen05.commit to both CTAs' empty / tmem_full barriers
+//   warps 2..9  : dequantizers, thread = weight row, two sets of 4 warps taking alternate groups
+//                 of 4 K blocks (each set has two groups' worth of MMA time per group); they arrive
+//                 on their own CTA's full_b barrier, rank 1's idle warp-1 thread relays that to the
+//                 leader's full_b_peer with a cluster-scope release; afterwards the epilogue.
+// =============================================================================================
+namespace pair {
+
+constexpr int BM = 256;        // tokens per CTA
+constexpr int BN = 256;        // weight rows per CTA pair (UMMA N)
+constexpr int BNH = 128;       // weight rows dequantized per CTA
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;    // 32 KB
+constexpr int B_STAGE_BYTES = BNH * BK * 2;   // 16 KB
+constexpr int SET_WARPS = NUM_DEQ_WARPS / 2;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + STG_BYTES;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of rank 1 -> same offset in rank 0
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior MMAs of the pair have completed) on the barrier at this offset in both CTAs
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// TMA load whose completion bytes are reported to the barrier at shared::cluster address `bar_addr`
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                                 uint32_t bar_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+// remote arrive with cluster-scope release (compiles to MEMBAR.ALL.GPU + arrive: issue it from a
+// thread without loads in flight)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+// debugging: waits that leave a record {site, kb, block, rank} in pinned host memory before trapping
+__device__ __noinline__ void wd_record(unsigned long long* h, int site, int kb) {
+  if (h) {
+    const unsigned long long v = ((unsigned long long)site << 48) | ((unsigned long long)(kb & 0xFFFF) << 32) |
+                                 ((unsigned long long)(blockIdx.y & 0xFF) << 24) | ((unsigned long long)(blockIdx.x & 0xFF) << 16) |
+                                 (threadIdx.x & 0xFFFF);
+    const unsigned slot = atomicAdd((unsigned*)h, 1u);
+    if (slot < 60) h[1 + slot] = v;
+    __threadfence_system();
+  }
+}
+__device__ __forceinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, unsigned long long* h, int site, int kb,
+                                              bool cluster) {
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!(cluster ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity))) {
+    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 1000000000LL) {
+      wd_record(h, site, kb);
+      // let the other stuck threads record too before the context dies
+      const long long t1 = clock64();
+      while (clock64() - t1 < 200000000LL) {}
+      __trap();
+    }
+  }
+}
+
+template <bool kDenseB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+    gemm_mxq_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                         const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint64_t* full_a = bars;                 // [STAGES]  used in the leader only
+  uint64_t* full_b = bars + STAGES;        // [STAGES]  per CTA: this CTA's half of B is in place
+  // empty[set][stage]: the K blocks that pass through a stage alternate between the two dequantizer
+  // sets, and a set only ever waits for the OTHER set's K block to be consumed.  One barrier per
+  // (set, stage) lets every waiter observe every phase of the barrier it waits on -- with a single
+  // barrier per stage a set would skip phases and the parity test could not tell "not yet" from
+  // "two phases ago".
+  uint64_t* empty = bars + 2 * STAGES;     // [2][STAGES]  per CTA
+  uint64_t* full_b_peer = bars + 4 * STAGES;   // [STAGES]  leader only: rank 1's half is in place
+  uint64_t* tmem_full = bars + 5 * STAGES; // [1]       per CTA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 * STAGES + 1);
+  uint8_t* stage_base = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int nrow0 = n0 + (int)rank * BNH;          // first weight row this CTA dequantizes
+  const int num_kb = p.IC / BK;
+  // K block kb is dequantized by set (kb >> 2) & 1 and is the (kb >> 3)-th block of that set in its
+  // stage; its consumption completes phase (kb >> 3) of empty[set][kb % STAGES]
+  auto empty_of = [&](int kb) { return &empty[((kb >> 2) & 1) * STAGES + (kb % STAGES)]; };
+  auto wait_stage_free = [&](int kb, int site) {    // before K block kb may overwrite its stage
+    if (kb >= STAGES) mbar_wait_dbg(empty_of(kb - STAGES), ((kb - STAGES) >> 3) & 1, p.dbg_host, site, kb, false);
+  };
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    if (kDenseB) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_a[s], 1);                                  // the leader's arrive.expect_tx
+      mbar_init(&full_b[s], kDenseB ? 1 : SET_WARPS);            // one warp set of this CTA
+      mbar_init(&full_b_peer[s], 1);                             // rank 1's relay thread
+      mbar_init(&empty[s], 1);
+      mbar_init(&empty[STAGES + s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();            // barriers of both CTAs are initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: this CTA's 256 tokens; completion reported to the leader =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        wait_stage_free(kb, 1);
+        if (rank == 0) {
+          mbar_arrive_expect_tx(&full_a[s], 2 * A_STAGE_BYTES);
+          if (kDenseB) mbar_arrive_expect_tx(&full_b[s], 2 * B_STAGE_BYTES);
+        }
+        tma_load_2d_pair(smem_a + s * A_STAGE_BYTES, &tmap_x, kb * BK, m0, smem_u32(&full_a[s]) & kPeerBitMask);
+        if (kDenseB)
+          tma_load_2d_pair(smem_b + s * B_STAGE_BYTES, &tmap_w, kb * BK, nrow0, smem_u32(&full_b[s]) & kPeerBitMask);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: leader CTA only =====
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(256, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait_dbg(&full_a[s], ph, p.dbg_host, 2, kb, true);
+        mbar_wait_dbg(&full_b[s], ph, p.dbg_host, 3, kb, false);
+        if (!kDenseB) mbar_wait_dbg(&full_b_peer[s], ph, p.dbg_host, 4, kb, true);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_a + s * A_STAGE_BYTES);
+        const uint32_t b_addr = smem_u32(smem_b + s * B_STAGE_BYTES);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ad = make_smem_desc(a_addr + h * (128 * BK * 2) + k * (UMMA_K * 2));
+            const uint64_t bd = make_smem_desc(b_addr + k * (UMMA_K * 2));
+            umma2_f16(tmem_base + h * BN, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma2_commit_both(empty_of(kb));   // frees the stage in both CTAs
+      }
+      umma2_commit_both(tmem_full);        // accumulators of both CTAs complete
+    } else if (!kDenseB && rank == 1 && lane == 0) {
+      // Relay: the dequantizers publish their half of B on this CTA's own barrier (cheap .cta
+      // release); this otherwise idle thread forwards it to the leader with a cluster-scope
+      // release -- a MEMBAR.ALL.GPU that would stall a dequantizer on its prefetch loads.
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait_dbg(&full_b[s], (kb / STAGES) & 1, p.dbg_host, 5, kb, false);
+        mbar_arrive_cluster(smem_u32(&full_b_peer[s]) & kPeerBitMask);
+      }
+    }
+  } else {
+    // ===== dequant producers (thread = weight row, two alternating warp sets), then epilogue =====
+    const int dw = warp - 2;                      // 0..7
+    const int set = dw >> 2;                      // groups g with (g & 1) == set
+    const int row_local = (dw & 3) * 32 + lane;   // 0..127
+    const int oc = nrow0 + row_local;
+    if (!kDenseB) {
+      const bool row_ok = oc < p.OC;
+      const int ocs = row_ok ? oc : 0;
+      const int nblk = num_kb;
+      const int nchunk = (nblk + 63) >> 6;
+      const uint4* wrow = reinterpret_cast<const uint4*>(p.w.weight + (size_t)ocs * nblk * 4);
+      const int32_t* wlrow = p.w.weight_last + (size_t)ocs * nblk;
+      const uint16_t* zsrow = reinterpret_cast<const uint16_t*>(p.w.zeros_and_scales) + (size_t)ocs * 64 * nchunk;
+      const uint8_t* z2row = reinterpret_cast<const uint8_t*>(p.w.zeros_2nd) + (size_t)(ocs >> 2) * 128 * nchunk;
+      const __half* s2row = reinterpret_cast<const __half*>(p.w.scales_2nd) + (size_t)(ocs >> 2) * nblk * 3;
+      const float s4 = __half2float(reinterpret_cast<const __half*>(p.w.scales_4b)[ocs]);
+      const uint32_t z4 = ((uint32_t)p.w.zeros_4b[ocs >> 3] >> (4 * (ocs & 7))) & 0xF;
+      const uint32_t z4magic = (0x6400u | z4) * 0x00010001u;
+      const uint32_t s4h2 = h2_bcast(row_ok ? s4 : 0.f);
+
+      auto produce = [&](int kb, const uint4& cwq, uint32_t cwl, uint32_t czs, uint32_t cz2,
+                         float s20, float s21, float s22) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        uint4 ch[8];
+        const uint32_t ws[3] = {cwq.x, cwq.y, cwq.z};
+        const float cs2[3] = {s20, s21, s22};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const uint32_t z1 = (czs >> (2 * k)) & 3;
+          const float c = (float)((czs >> (8 + 2 * k)) & 3);
+          const float zz = (float)((cz2 >> (2 * k)) & 3);
+          const float scale = row_ok ? cs2[k] * (c - zz) : 0.f;
+          dequant_2b(ws[k], (0x6400u | z1) * 0x00010001u, h2_bcast(scale), ch[2 * k], ch[2 * k + 1]);
+        }
+        ch[6] = dequant_4b(cwq.w, z4magic, s4h2);
+        ch[7] = dequant_4b(cwl, z4magic, s4h2);
+        wait_stage_free(kb, 6);
+        uint8_t* brow = smem_b + s * B_STAGE_BYTES + row_local * 128;
+        const int sw = row_local & 7;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(brow + ((c ^ sw) << 4)) = ch[c];
+        // generic stores to this CTA's shared memory -> async proxy (the pair's tensor cores).  The
+        // unqualified fence.proxy.async compiles to MEMBAR.ALL.GPU and stalls on the prefetch loads.
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_b[s]);
+      };
+
+      if ((nblk & 3) == 0) {
+        uint8_t* stg = stage_base + dw * (32 * STG_PITCH);
+        const int ngroups = nblk >> 2;
+        const int q = lane & 3, r8 = lane >> 2;
+        const uint4* wbase[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int orow = nrow0 + (dw & 3) * 32 + 8 * i + r8;
+          orow = orow < p.OC ? orow : 0;
+          wbase[i] = reinterpret_cast<const uint4*>(p.w.weight + (size_t)orow * nblk * 4) + q;
+        }
+        const uint4* wl4 = reinterpret_cast<const uint4*>(wlrow);
+        const uint32_t* zsw = reinterpret_cast<const uint32_t*>(p.w.zeros_and_scales) + (size_t)ocs * 32 * nchunk;
+        const uint32_t* z2w = reinterpret_cast<const uint32_t*>(p.w.zeros_2nd) + (size_t)(ocs >> 2) * 32 * nchunk;
+        const uint2* s2v2 = reinterpret_cast<const uint2*>(s2row);
+        uint4 pw[4], pwl, pzs, pz2;
+        uint2 ps2[3];
+        auto fetch = [&](int g) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pw[i] = __ldg(wbase[i] + 4 * g);
+          pwl = __ldg(wl4 + g);
+          const int kb0 = 4 * g;
+          const int mword = (kb0 >> 6) * 32 + (kb0 & 31);
+          pzs = __ldg(reinterpret_cast<const uint4*>(zsw + mword));
+          pz2 = __ldg(reinterpret_cast<const uint4*>(z2w + mword));
+#pragma unroll
+          for (int i = 0; i < 3; ++i) ps2[i] = __ldg(s2v2 + 3 * g + i);
+        };
+        if (set < ngroups) fetch(set);
+        for (int g = set; g < ngroups; g += 2) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(stg + (8 * i + r8) * STG_PITCH + q * 16) = pw[i];
+          const uint4 cwl = pwl, czs = pzs, cz2 = pz2;
+          const uint2 cs2[3] = {ps2[0], ps2[1], ps2[2]};
+          __syncwarp();
+          uint4 wq[4];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) wq[kk] = *reinterpret_cast<const uint4*>(stg + lane * STG_PITCH + kk * 16);
+          __syncwarp();
+          if (g + 2 < ngroups) fetch(g + 2);
+          const int hsh = (((4 * g) & 63) >> 5) * 16;
+          const uint32_t wlw[4] = {cwl.x, cwl.y, cwl.z, cwl.w};
+          const uint32_t zsv[4] = {czs.x, czs.y, czs.z, czs.w};
+          const uint32_t z2v[4] = {cz2.x, cz2.y, cz2.z, cz2.w};
+          const uint32_t s2w[6] = {cs2[0].x, cs2[0].y, cs2[1].x, cs2[1].y, cs2[2].x, cs2[2].y};
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            float sv[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const int hidx = 3 * kk + k;
+              const uint32_t wsel = s2w[hidx >> 1];
+              sv[k] = __half2float(__ushort_as_half((unsigned short)((hidx & 1) ? (wsel >> 16) : (wsel & 0xFFFF))));
+            }
+            produce(4 * g + kk, wq[kk], wlw[kk], (zsv[kk] >> hsh) & 0xFFFF, (z2v[kk] >> (hsh >> 1)) & 0xFF,
+                    sv[0], sv[1], sv[2]);
+          }
+        }
+      } else {
+        // generic K (IC % 256 != 0): per-block scalar loads, K blocks [4g, 4g+4) go to set g & 1
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (((kb >> 2) & 1) != set) continue;
+          const int chunk = kb >> 6, bp = kb & 63;
+          const int word = chunk * 32 + (bp & 31), hw = bp >> 5;
+          const uint4 cwq = __ldg(wrow + kb);
+          const uint32_t cwl = (uint32_t)__ldg(wlrow + kb);
+          const uint32_t czs = __ldg(zsrow + word * 2 + hw);
+          const uint32_t cz2 = __ldg(z2row + word * 4 + hw);
+          const __half* sp = s2row + (size_t)kb * 3;
+          produce(kb, cwq, cwl, czs, cz2, __half2float(__ldg(sp)), __half2float(__ldg(sp + 1)),
+                  __half2float(__ldg(sp + 2)));
+        }
+      }
+    }
+    // ===== epilogue: TMEM -> registers -> fp16 -> global =====
+    mbar_wait_dbg(tmem_full, 0, p.dbg_host, 7, 0, true);
+    tc_fence_after();
+    const int half = dw >> 2;                 // accumulator (token half)
+    const int quad = warp & 3;                // TMEM lane quarter this warp may access
+    const int token = m0 + half * 128 + quad * 32 + lane;
+    const size_t yoff = (size_t)token * p.ldy + p.col0 + n0;
+#pragma unroll 1
+    for (int cb = 0; cb < BN / 32; ++cb) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + half * BN + cb * 32, v);
+      tmem_ld_wait();
+      if (token < p.M) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int col = n0 + cb * 32 + q * 8;
+          if (col + 8 <= p.OC) {
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              oh[e] = __floats2half2_rn(__uint_as_float(v[q * 8 + 2 * e]), __uint_as_float(v[q * 8 + 2 * e + 1]));
+            for (int pe = 0; pe < p.npeers; ++pe)
+              *reinterpret_cast<uint4*>(p.y[pe] + yoff + cb * 32 + q * 8) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();            // neither CTA exits (or frees TMEM) while the pair's MMAs may read it
+  if (warp == 1) tmem_dealloc2(tmem_base, TMEM_COLS);
+}
+
+}  // namespace pair
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -441,8 +837,35 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
   return r == CUDA_SUCCESS ? MXQ_OK : MXQ_E_UNSUPPORTED;
 }
 
+// CTA-pair kernel: grid.x = 2 * ceil(M / 512) (cluster of 2 along x), grid.y = ceil(OC / 256)
+template <bool kDenseB>
+static int launch_pair(const void* x, const Params& p, cudaStream_t st) {
+  CUtensorMap mx, mw;
+  int rc = make_map(&mx, x, p.M, p.IC, pair::BM);
+  if (rc) return rc;
+  if (kDenseB) {
+    rc = make_map(&mw, p.wdense, p.OC, p.IC, pair::BNH);
+    if (rc) return rc;
+  } else {
+    mw = mx;
+  }
+  auto k = pair::gemm_mxq_pair_kernel<kDenseB>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(2u * (unsigned)ceil_div(p.M, 2 * pair::BM), (unsigned)ceil_div(p.OC, pair::BN));
+  Params pp = p;
+  pp.dbg = 0;
+  pp.dbg_host = nullptr;
+  if (const char* e = getenv("MXQ_GEMM_DBG")) pp.dbg = atoi(e);
+  if (const char* e = getenv("MXQ_GEMM_DBG_PTR")) pp.dbg_host = (unsigned long long*)strtoull(e, nullptr, 0);
+  k<<<grid, THREADS, pair::SMEM_BYTES, st>>>(mx, mw, pp);
+  MXQ_LAUNCH_RESULT();
+}
+
 template <bool kDenseB>
 static int launch(const void* x, const Params& p, cudaStream_t st) {
+  // More than one M tile: CTA pairs (M = 256 MMAs).  MXQ_GEMM_SINGLE forces the one-CTA kernel.
+  if (p.M > BM && !getenv("MXQ_GEMM_SINGLE")) return launch_pair<kDenseB>(x, p, st);
   CUtensorMap mx, mw;
   int rc = make_map(&mx, x, p.M, p.IC, BM);
   if (rc) return rc;
@@ -453,10 +876,13 @@ static int launch(const void* x, const Params& p, cudaStream_t st) {
     mw = mx;
   }
   auto k = gemm_mxq_kernel<kDenseB>;
+  Params pp = p;
+  pp.dbg = 0;
+  if (const char* e = getenv("MXQ_GEMM_DBG")) pp.dbg = atoi(e);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((unsigned)ceil_div(p.OC, BN), (unsigned)ceil_div(p.M, BM));
-  k<<<grid, THREADS, SMEM_BYTES, st>>>(mx, mw, p);
+  k<<<grid, THREADS, SMEM_BYTES, st>>>(mx, mw, pp);
   MXQ_LAUNCH_RESULT();
 }
 

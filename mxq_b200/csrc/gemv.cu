@@ -140,31 +140,47 @@ __device__ __forceinline__ float fhfma_lo(uint32_t a, uint32_t b, float c) {   /
 //   [off_wl)  weight_last       (g*4 + r)*nblk*4 + b*4
 //   [off_zs)  zeros_and_scales  (g*4 + r)*128*nchunk + word*4 (+2 for the upper half)
 //   [off_z2)  zeros_2nd         g*128*nchunk + word*4 (+ byte)
-// scales_2nd (6 % of the bytes; its groups start on 2-byte boundaries, so no bulk copy) is
-// prefetched into L2 and read with ordinary loads issued before the stage barrier is waited on.
+//   [off_s2)  scales_2nd        the 16-byte-aligned range enclosing the stage's groups (they start
+//                               on 2-byte boundaries): (g*nblk + b)*6 + 2k + slop
 // ---------------------------------------------------------------------------------------------
 struct GemvStage {
-  int off_wl, off_zs, off_z2, bytes;
+  int off_wl, off_zs, off_z2, off_s2, bytes;
 };
 __host__ __device__ inline GemvStage gemv_stage_layout(int rpr, int nblk, int nchunk) {
   GemvStage L;
   L.off_wl = rpr * nblk * 64;
   L.off_zs = L.off_wl + rpr * nblk * 16;
   L.off_z2 = L.off_zs + rpr * 512 * nchunk;
-  L.bytes = L.off_z2 + rpr * 128 * nchunk;
+  L.off_s2 = L.off_z2 + rpr * 128 * nchunk;
+  // scales_2nd: rpr * nblk * 6 bytes starting on a 2-byte boundary -> fetched as the enclosing
+  // 16-byte-aligned range (up to 14 bytes of slop in front, 14 behind)
+  L.bytes = L.off_s2 + ((rpr * nblk * 6 + 15) & ~15) + 16;
   return L;
 }
-// thread 0: fetch `rc` row groups starting at `grp0` into stage `st`
+// thread 0: fetch `rc` row groups starting at `grp0` into stage `st`.  s2_total = byte size of
+// the scales_2nd tensor: the aligned range is clipped to it and a clipped tail (< 16 bytes, only
+// when the tensor size is not a multiple of 16) is copied with plain loads -- ordered before the
+// consumers by the release of arrive.expect_tx / acquire of the barrier wait.
 __device__ __forceinline__ void gemv_fill(unsigned char* st, const GemvStage& L, uint64_t* bar,
                                           const mxq_packed_t& w, int grp0, int rc, int nblk,
-                                          int nchunk) {
+                                          int nchunk, size_t s2_total) {
   const uint32_t b_wq = (uint32_t)rc * nblk * 64, b_wl = (uint32_t)rc * nblk * 16,
                  b_zs = (uint32_t)rc * 512 * nchunk, b_z2 = (uint32_t)rc * 128 * nchunk;
-  mbar_arrive_expect_tx(bar, b_wq + b_wl + b_zs + b_z2);
+  const size_t s2_b0 = (size_t)grp0 * nblk * 6, s2_b1 = s2_b0 + (size_t)rc * nblk * 6;
+  const size_t s2_a0 = s2_b0 & ~(size_t)15;
+  size_t s2_a1 = (s2_b1 + 15) & ~(size_t)15;
+  if (s2_a1 > s2_total) s2_a1 = s2_total & ~(size_t)15;
+  const unsigned char* s2g = reinterpret_cast<const unsigned char*>(w.scales_2nd);
+  for (size_t b = s2_a1 > s2_a0 ? s2_a1 : s2_a0; b < s2_b1; b += 2)
+    *reinterpret_cast<unsigned short*>(st + L.off_s2 + (b - s2_a0)) =
+        *reinterpret_cast<const unsigned short*>(s2g + b);
+  const uint32_t b_s2 = s2_a1 > s2_a0 ? (uint32_t)(s2_a1 - s2_a0) : 0u;
+  mbar_arrive_expect_tx(bar, b_wq + b_wl + b_zs + b_z2 + b_s2);
   bulk_g2s(st, reinterpret_cast<const unsigned char*>(w.weight) + (size_t)grp0 * nblk * 64, b_wq, bar);
   bulk_g2s(st + L.off_wl, reinterpret_cast<const unsigned char*>(w.weight_last) + (size_t)grp0 * nblk * 16, b_wl, bar);
   bulk_g2s(st + L.off_zs, reinterpret_cast<const unsigned char*>(w.zeros_and_scales) + (size_t)grp0 * 512 * nchunk, b_zs, bar);
   bulk_g2s(st + L.off_z2, reinterpret_cast<const unsigned char*>(w.zeros_2nd) + (size_t)grp0 * 128 * nchunk, b_z2, bar);
+  if (b_s2) bulk_g2s(st + L.off_s2, s2g + s2_a0, b_s2, bar);
 }
 
 __device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
@@ -176,26 +192,17 @@ __device__ __forceinline__ uint32_t ldg_u16(const void* p) {
   return v;
 }
 
-// scales_2nd of one unit and, when a new row group starts, its 4-bit pool scale / zero words
+// 4-bit pool scale / zero words of a row group (per output row: 8 + 2 bytes per group, read with
+// ordinary loads one round ahead)
 struct GemvPre {
-  uint32_t s2[3];
   uint2 s4;
   uint32_t z4w;
 };
-__device__ __forceinline__ void gemv_prefetch_meta(GemvPre& pre, const mxq_packed_t& w, int grp, int sl,
-                                                   int lane, int nblk, bool skip, bool new_group) {
+__device__ __forceinline__ void gemv_prefetch_meta(GemvPre& pre, const mxq_packed_t& w, int grp, bool skip) {
   if (skip) return;
-  const int blk = sl * 32 + lane;
-  if (blk < nblk) {
-    const __half* s2p = reinterpret_cast<const __half*>(w.scales_2nd) + ((size_t)grp * nblk + blk) * 3;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) pre.s2[k] = ldg_u16(s2p + k);
-  }
-  if (new_group) {
-    const int oc0 = grp * 4;
-    pre.s4 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(w.scales_4b) + oc0));
-    pre.z4w = (uint32_t)__ldg(w.zeros_4b + (oc0 >> 3)) >> (4 * (oc0 & 7));
-  }
+  const int oc0 = grp * 4;
+  pre.s4 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(w.scales_4b) + oc0));
+  pre.z4w = (uint32_t)__ldg(w.zeros_4b + (oc0 >> 3)) >> (4 * (oc0 & 7));
 }
 
 struct GemvRegs {     // one lane's share of a (4-row group, 64-column block): 27 registers
@@ -203,8 +210,9 @@ struct GemvRegs {     // one lane's share of a (4-row group, 64-column block): 2
   uint32_t wl[4], zs[4], z2, s2[3];
 };
 // gi = row group index inside the stage
+// s2_slop = (first group of the stage * nblk * 6) & 15
 __device__ __forceinline__ void gemv_read(const unsigned char* st, const GemvStage& L, int gi,
-                                          int blk, int nblk, int nchunk, GemvRegs& g) {
+                                          int blk, int nblk, int nchunk, int s2_slop, GemvRegs& g) {
   const int chunk = blk >> 6, bp = blk & 63;
   const int word = chunk * 32 + (bp & 31), p = bp >> 5;
 #pragma unroll
@@ -215,6 +223,10 @@ __device__ __forceinline__ void gemv_read(const unsigned char* st, const GemvSta
     g.zs[r] = *reinterpret_cast<const uint16_t*>(st + L.off_zs + (row * 32 * nchunk + word) * 4 + p * 2);
   }
   g.z2 = st[L.off_z2 + (gi * 32 * nchunk + word) * 4 + p];
+  const unsigned short* s2p =
+      reinterpret_cast<const unsigned short*>(st + L.off_s2 + s2_slop + (gi * nblk + blk) * 6);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) g.s2[k] = s2p[k];
 }
 
 // Shared-memory image of the activations, per batch row b (stride `xb_stride` bytes):
@@ -392,6 +404,7 @@ __global__ void __launch_bounds__(NB == 1 ? 512 : 256, 1) gemv_mxq_kernel(
   const int xb_stride = nblk * (kXBlkBytes + 32);
   const GemvStage L = gemv_stage_layout(plan.rpr, nblk, nchunk);
   const int stage_stride = (L.bytes + 127) & ~127;
+  const size_t s2_total = (size_t)ngrp_all * nblk * 6;
   unsigned char* xsm = smem + (size_t)plan.nstages * stage_stride;
 
   const bool trace = (plan.dbg & 8) && threadIdx.x == 0 && blockIdx.x < 160;
@@ -403,17 +416,13 @@ __global__ void __launch_bounds__(NB == 1 ? 512 : 256, 1) gemv_mxq_kernel(
       const int g0 = i * plan.rpr;
       if (g0 < qc)
         gemv_fill(smem + (size_t)i * stage_stride, L, &full[i], w, grp_base + g0,
-                  min(plan.rpr, qc - g0), nblk, nchunk);
+                  min(plan.rpr, qc - g0), nblk, nchunk, s2_total);
     }
-    // scales_2nd of the CTA's row range -> L2 (a hint: clipped to whole 16-byte lines)
-    const size_t lo = ((size_t)grp_base * nblk * 6 + 15) & ~(size_t)15;
-    const size_t hi = ((size_t)(grp_base + qc) * nblk * 6) & ~(size_t)15;
-    if (hi > lo) bulk_prefetch_l2(reinterpret_cast<const unsigned char*>(w.scales_2nd) + lo, (uint32_t)(hi - lo));
   }
 
-  // per-row-group scales of the warp's first unit (weights only: allowed before the wait)
+  // 4-bit pool parameters of the warp's first row group (weights only: allowed before the wait)
   GemvPre pre;
-  gemv_prefetch_meta(pre, w, grp_base + rgl, sl0, lane, nblk, !(warp_on && rgl < qc), true);
+  gemv_prefetch_meta(pre, w, grp_base + rgl, !(warp_on && rgl < qc));
 
   griddep_wait();
   // Only now may the next kernel of the stream become resident (one generation of look-ahead).
@@ -492,20 +501,15 @@ __global__ void __launch_bounds__(NB == 1 ? 512 : 256, 1) gemv_mxq_kernel(
       for (int r = 0; r < 4; ++r) z4[r] = (int)((pre.z4w >> (4 * r)) & 0xF);
     }
     GemvRegs cur;
+    // pool parameters of the warp's row group of the next round
+    gemv_prefetch_meta(pre, w, grp + plan.rpr, !(on && round + 1 < rounds && gl + plan.rpr < qc));
+    const int s2_slop = (int)(((size_t)(grp_base + round * plan.rpr) * nblk * 6) & 15);
     mbar_wait(&full[slot], parity);
     if (on) {
       for (int sl = sl0; sl < plan.ksl; sl += plan.wpr) {
         const int blk = sl * 32 + lane;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) cur.s2[k] = pre.s2[k];
-        // scales of the warp's next unit (next slice, or the first slice of the next round)
-        {
-          const bool last = sl + plan.wpr >= plan.ksl;
-          gemv_prefetch_meta(pre, w, last ? grp + plan.rpr : grp, last ? sl0 : sl + plan.wpr, lane,
-                             nblk, last && (round + 1 >= rounds || gl + plan.rpr >= qc), last);
-        }
         if (blk < nblk) {
-          gemv_read(st, L, rgl, blk, nblk, nchunk, cur);
+          gemv_read(st, L, rgl, blk, nblk, nchunk, s2_slop, cur);
           if (!(plan.dbg & 1)) gemv_block<NB>(cur, xsm, xb_stride, blk, nblk, s4, z4, acc);
           else acc[0][0] += __uint_as_float(cur.wq[0].x ^ cur.wq[1].y ^ cur.wq[2].z ^ cur.wq[3].w ^ cur.wl[0] ^ cur.wl[1] ^ cur.wl[2] ^ cur.wl[3] ^ cur.zs[0] ^ cur.zs[1] ^ cur.zs[2] ^ cur.zs[3] ^ cur.z2 ^ cur.s2[0] ^ cur.s2[1] ^ cur.s2[2]);
         }
@@ -526,7 +530,7 @@ __global__ void __launch_bounds__(NB == 1 ? 512 : 256, 1) gemv_mxq_kernel(
       if (round + plan.nstages < rounds) {
         fence_proxy_async();
         gemv_fill(smem + (size_t)slot * stage_stride, L, &full[slot], w, grp_base + g0,
-                  min(plan.rpr, qc - g0), nblk, nchunk);
+                  min(plan.rpr, qc - g0), nblk, nchunk, s2_total);
       }
     }
     // one thread per (row group of the round, row, batch)

@@ -1,0 +1,27 @@
+"""Where does the dense-B tcgen05 pipeline lose time?  MXQ_GEMM_DBG=1 issues only one M half of the
+MMAs, =2 stops the TMA loads after the first ring fill (no shared-memory writes), =3 both."""
+import os, sys, torch
+sys.path.insert(0, os.getcwd())
+from mxq_b200 import ops
+dev = torch.device("cuda:0")
+def timeit(fn, iters=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters * 1e3
+M = 2048
+for OC, IC in ((4096, 4096), (4096, 11008)):
+    W = (torch.randn(OC, IC, device=dev) * 0.02).half()
+    x = torch.randn(M, IC, device=dev).half()
+    p = ops.pack(W)
+    y = torch.empty(M, OC, device=dev, dtype=torch.float16)
+    ws = torch.zeros(1024, dtype=torch.uint8, device=dev)
+    for dbg in (0, 1, 2, 3):
+        os.environ["MXQ_GEMM_DBG"] = str(dbg)
+        td = timeit(lambda: ops.gemm_dense(x, W))
+        tp = timeit(lambda: ops.gemm(x, p, out=y, workspace=ws, validate=False))
+        print(f"{OC}x{IC} dbg={dbg}: dense {td:.1f} us ({td*1e3/ (IC/64):.0f} ns/kblock)  packed {tp:.1f} us ({tp*1e3/(IC/64):.0f} ns/kblock)", flush=True)
+os.environ.pop("MXQ_GEMM_DBG")

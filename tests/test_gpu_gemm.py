@@ -15,7 +15,9 @@ def _rel(got, ref):
     return float(np.abs(got.astype(np.float64) - ref).max() / np.abs(ref).max())
 
 
-@pytest.mark.parametrize("M,OC,IC", [(256, 256, 64), (256, 256, 256), (128, 512, 4096), (300, 264, 1024)])
+# M > 256 runs the CTA-pair (cta_group::2) kernel, M <= 256 the single-CTA one
+@pytest.mark.parametrize("M,OC,IC", [(256, 256, 64), (256, 256, 256), (128, 512, 4096), (300, 264, 1024),
+                                     (512, 256, 64), (512, 256, 256), (1024, 512, 1024), (700, 264, 4096)])
 def test_dense_pipeline(cuda, M, OC, IC):
     """tcgen05 + TMA + TMEM pipeline alone (dense fp16 B operand through TMA)."""
     from mxq_b200 import ops
@@ -28,7 +30,8 @@ def test_dense_pipeline(cuda, M, OC, IC):
 
 
 @pytest.mark.parametrize("M,OC,IC", [(256, 256, 64), (256, 256, 4096), (2048, 512, 4096), (77, 264, 128),
-                                     (512, 256, 11008), (1000, 1024, 8192)])
+                                     (512, 256, 11008), (1000, 1024, 8192), (512, 256, 64), (512, 256, 512),
+                                     (257, 136, 192), (2048, 264, 320)])
 def test_packed_random_bits(cuda, M, OC, IC):
     from mxq_b200 import ops
     p = O.random_packed(OC, IC, seed=M + OC + IC)

@@ -81,7 +81,8 @@ def test_gemv_random_bits(cuda, OC, IC, B):
 
 
 @pytest.mark.parametrize("OC,IC,B", [(11008, 256, 4), (11008, 256, 1), (11008, 4096, 2), (4104, 128, 2),
-                                     (1192, 64, 1), (9472, 192, 3), (64, 11008, 4), (64, 28672, 1), (64, 28672, 2)])
+                                     (1192, 64, 1), (9472, 192, 3), (64, 11008, 4), (64, 28672, 1), (64, 28672, 2),
+                                     (4096, 11008, 4), (4096, 11008, 2), (11008, 4096, 4)])
 def test_gemv_short_last_cta(cuda, OC, IC, B):
     """Row counts that leave the last persistent CTA with fewer row groups (and rounds) than the
     others, for every batch tiling (regression: a stage that is never filled must not be awaited)."""
