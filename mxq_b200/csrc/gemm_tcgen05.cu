@@ -495,6 +495,14 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// Arrive on the barrier at shared::cluster address `bar_addr` (the leader's) with the default
+// .release.cta semantics.  The stores being published are st.shared to the issuing CTA's own shared
+// memory, already pushed to the async proxy by fence.proxy.async.shared::cta: CTA-scope
+// performed-ness of a shared-memory store IS its presence in that SM's shared memory, which is
+// what the pair's tensor cores read.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
 // remote arrive with cluster-scope release (compiles to MEMBAR.ALL.GPU + arrive: issue it from a
 // thread without loads in flight)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_addr) {
@@ -574,6 +582,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
   const int num_kb = p.IC / BK;
   // K block kb is dequantized by set (kb >> 2) & 1 and is the (kb >> 3)-th block of that set in its
   // stage; its consumption completes phase (kb >> 3) of empty[set][kb % STAGES]
+  const bool direct = !(p.dbg & 16);   // MXQ_GEMM_DBG=16: publish rank 1's half through the relay thread
   auto empty_of = [&](int kb) { return &empty[((kb >> 2) & 1) * STAGES + (kb % STAGES)]; };
   auto wait_stage_free = [&](int kb, int site) {    // before K block kb may overwrite its stage
     if (kb >= STAGES) mbar_wait_dbg(empty_of(kb - STAGES), ((kb - STAGES) >> 3) & 1, p.dbg_host, site, kb, false);
@@ -584,7 +593,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
     if (kDenseB) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_a[s], 1);                                  // the leader's arrive.expect_tx
-      mbar_init(&full_b[s], kDenseB ? 1 : SET_WARPS);            // one warp set of this CTA
+      // one warp set of this CTA (relay mode) or of both CTAs (direct mode: rank 1 arrives remotely)
+      mbar_init(&full_b[s], kDenseB ? 1 : (direct ? 2 * SET_WARPS : SET_WARPS));
       mbar_init(&full_b_peer[s], 1);                             // rank 1's relay thread
       mbar_init(&empty[s], 1);
       mbar_init(&empty[STAGES + s], 1);
@@ -618,12 +628,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
     // ===== MMA issuer: leader CTA only =====
     if (rank == 0 && lane == 0) {
       constexpr uint32_t idesc = make_idesc(256, BN);
+      long long wait_a = 0, wait_b = 0;          // debugging: cycles the issuer spent on each barrier
+      const long long c_begin = clock64();
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
+        const long long c0 = clock64();
         mbar_wait_dbg(&full_a[s], ph, p.dbg_host, 2, kb, true);
-        mbar_wait_dbg(&full_b[s], ph, p.dbg_host, 3, kb, false);
-        if (!kDenseB) mbar_wait_dbg(&full_b_peer[s], ph, p.dbg_host, 4, kb, true);
+        const long long c1 = clock64();
+        mbar_wait_dbg(&full_b[s], ph, p.dbg_host, 3, kb, direct);
+        const long long c2 = clock64();
+        wait_a += c1 - c0; wait_b += c2 - c1;
+        if (!kDenseB && !direct) mbar_wait_dbg(&full_b_peer[s], ph, p.dbg_host, 4, kb, true);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem_a + s * A_STAGE_BYTES);
         const uint32_t b_addr = smem_u32(smem_b + s * B_STAGE_BYTES);
@@ -639,7 +655,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         umma2_commit_both(empty_of(kb));   // frees the stage in both CTAs
       }
       umma2_commit_both(tmem_full);        // accumulators of both CTAs complete
-    } else if (!kDenseB && rank == 1 && lane == 0) {
+      if (p.dbg_host && blockIdx.x == 0 && blockIdx.y == 0) {
+        volatile unsigned long long* hv = p.dbg_host;
+        hv[61] = (unsigned long long)wait_a;
+        hv[62] = (unsigned long long)wait_b;
+        hv[63] = (unsigned long long)(clock64() - c_begin);
+        __threadfence_system();
+      }
+    } else if (!kDenseB && !direct && rank == 1 && lane == 0) {
       // Relay: the dequantizers publish their half of B on this CTA's own barrier (cheap .cta
       // release); this otherwise idle thread forwards it to the leader with a cluster-scope
       // release -- a MEMBAR.ALL.GPU that would stall a dequantizer on its prefetch loads.
@@ -677,6 +700,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         uint4 ch[8];
         const uint32_t ws[3] = {cwq.x, cwq.y, cwq.z};
         const float cs2[3] = {s20, s21, s22};
+        if (p.dbg & 32) {          // profiling: no dequant arithmetic (garbage operand)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) ch[c] = make_uint4(cwq.x + c, cwq.y, czs, cwl);
+        } else {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const uint32_t z1 = (czs >> (2 * k)) & 3;
@@ -687,16 +714,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         }
         ch[6] = dequant_4b(cwq.w, z4magic, s4h2);
         ch[7] = dequant_4b(cwl, z4magic, s4h2);
-        wait_stage_free(kb, 6);
+        }
+        if (p.dbg & 512) {         // profiling: every lane polls the barrier
+          wait_stage_free(kb, 6);
+        } else {                   // one lane polls, __syncwarp orders the others' stores after its acquire
+          if (lane == 0) wait_stage_free(kb, 6);
+          __syncwarp();
+        }
         uint8_t* brow = smem_b + s * B_STAGE_BYTES + row_local * 128;
         const int sw = row_local & 7;
+        if (!(p.dbg & 256)) {     // dbg 256: profiling, no operand stores
 #pragma unroll
-        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(brow + ((c ^ sw) << 4)) = ch[c];
+          for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(brow + ((c ^ sw) << 4)) = ch[c];
+        }
         // generic stores to this CTA's shared memory -> async proxy (the pair's tensor cores).  The
         // unqualified fence.proxy.async compiles to MEMBAR.ALL.GPU and stalls on the prefetch loads.
-        fence_proxy_async();
+        if (!(p.dbg & 128)) fence_proxy_async();   // dbg 128: profiling, no proxy fence (wrong results)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full_b[s]);
+        if (lane == 0) {
+          if (direct) mbar_arrive_remote(smem_u32(&full_b[s]) & kPeerBitMask);
+          else mbar_arrive(&full_b[s]);
+        }
       };
 
       if ((nblk & 3) == 0) {
@@ -739,7 +777,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) wq[kk] = *reinterpret_cast<const uint4*>(stg + lane * STG_PITCH + kk * 16);
           __syncwarp();
-          if (g + 2 < ngroups) fetch(g + 2);
+          if (g + 2 < ngroups && !(p.dbg & 64)) fetch(g + 2);   // dbg 64: profiling, reuse the first group's words
           const int hsh = (((4 * g) & 63) >> 5) * 16;
           const uint32_t wlw[4] = {cwl.x, cwl.y, cwl.z, cwl.w};
           const uint32_t zsv[4] = {czs.x, czs.y, czs.z, czs.w};
