@@ -581,6 +581,21 @@ def run_components(torch, dev, pk):
         out[f"fakequant_fwd_{name}"] = {"ms": mf, "GBps": 2 * nb / mf / 1e6, "frac_hbm": 2 * nb / mf / 1e6 / pk["hbm"]}
         out[f"ste_bwd_{name}"] = {"ms": mb, "GBps": 3 * nb / mb / 1e6, "frac_hbm": 3 * nb / mb / 1e6 / pk["hbm"]}
         del xs, gs, outs
+    # activation / KV-cache fake quantizers on a QAT-sized bf16 activation [2, 2048, 4096]
+    try:
+        nset = 6
+        xs = [torch.randn(2, 2048, 4096, device=dev).to(torch.bfloat16) for _ in range(nset)]
+        outs = [torch.empty_like(xs[0]) for _ in range(nset)]
+        nb = xs[0].numel() * 2
+        for mode, bits in (("sym", 8), ("asym", 4)):
+            nseg, seglen, period, valid = ops.segquant_plan(tuple(xs[0].shape), mode, False)
+            ms = timeit(lambda i: ops.L.check(ops.L.lib().mxq_segquant_fwd(
+                xs[i % nset].data_ptr(), outs[i % nset].data_ptr(), nseg, seglen, ops.L.MXQ_BF16,
+                0 if mode == "sym" else 1, bits, period, valid, None, 0, ops.L.stream()), "segquant"), 30)
+            out[f"actquant_{mode}{bits}_bf16"] = {"ms": ms, "GBps": 2 * nb / ms / 1e6, "frac_hbm": 2 * nb / ms / 1e6 / pk["hbm"]}
+        del xs, outs
+    except Exception as e:
+        out["actquant"] = {"error": repr(e)[:200]}
     # config 2: decode GEMV over the 7 linears of 8 layers of packed random-bit weights (> L2), CUDA graph
     shapes = [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)]
     nl = 8
@@ -627,7 +642,13 @@ def run_components(torch, dev, pk):
             ws = torch.zeros(4096, dtype=torch.uint8, device=dev)
             ms = timeit(lambda i: ops.gemm(x, p, out=y, workspace=ws, validate=False), 10)
             tf = 2.0 * M * oc * ic / ms / 1e9
-            res[f"{oc}x{ic}"] = {"ms": ms, "TFLOPs": tf, "frac_tensor_burst": tf / pk["tf_burst"]}
+            # same-shape dense fp16 comparator: cuBLAS through torch.matmul (library GEMM, no dequant)
+            Wd = (torch.randn(oc, ic, device=dev) * 0.02).half()
+            msc = timeit(lambda i: torch.matmul(x, Wd.t(), out=y), 10)
+            tfc = 2.0 * M * oc * ic / msc / 1e9
+            res[f"{oc}x{ic}"] = {"ms": ms, "TFLOPs": tf, "frac_tensor_burst": tf / pk["tf_burst"],
+                                 "cublas_fp16_dense_TFLOPs": tfc, "frac_of_cublas": tf / tfc}
+            del Wd
         out["gemm_prefill_m2048"] = res
     except Exception as e:
         out["gemm_prefill_m2048"] = {"error": repr(e)[:200]}

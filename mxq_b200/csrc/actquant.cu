@@ -29,6 +29,8 @@
 // Division is IEEE-exact: correctly rounded reciprocal + one Markstein step (common.cuh), with an
 // IEEE fallback whenever the fast quotient is not finite or the divisor is outside the normal
 // checked range (oracle/div_check_sym.c checks the fast path against IEEE division).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mxq {
@@ -36,8 +38,13 @@ namespace mxq {
 enum { kSym = 0, kAsym = 1 };
 
 struct SegParams {       // per segment, broadcast to its elements
-  float p0, p1, p2, p3;  // sym: s, s2 = s + 1e-6, RN(1/s2), fast;  asym: a, b, RN(1/a), fast
+  float p0, p1, p2, p3;  // sym: s, s2 = s + 1e-6, RN(1/s2), clean;  asym: a, b, RN(1/a), clean
 };
+// clean = the whole segment may take the packed fast path (chunk_apply_fast): live segment, finite
+// statistics, divisor inside the checked range.  Then every intermediate is finite and
+// |round(...)| < 2^22, so rounding can use the 1.5 * 2^23 magic constant and the quotients need no
+// per-element guard (sym: the dividend is an integer; asym: a dividend below 1e-30 quantizes to
+// code 0 whether or not its quotient is correctly rounded).
 
 // The fast quotient (reciprocal + one Markstein step) is IEEE-exact for divisors in
 // [1e-30, 1e30] and dividends with |t| >= 1e-30 or t == 0 (oracle/div_check_sym.c, 3e9 operand
@@ -45,9 +52,10 @@ struct SegParams {       // per segment, broadcast to its elements
 __device__ __forceinline__ bool divisor_fast(float a) { return a >= 1e-30f && a <= 1e30f; }
 
 template <typename T>
-__device__ __forceinline__ SegParams seg_params(int mode, float mn, float mx, float qscale) {
+__device__ __forceinline__ SegParams seg_params(int mode, float mn, float mx, float qscale, bool live) {
   using D = DT<T>;
   SegParams P;
+  const bool finite = live && fabsf(mn) <= 3.0e38f && fabsf(mx) <= 3.0e38f;
   if (mode == kSym) {
     const float m = fmaxf(fabsf(mn), fabsf(mx));                       // max |x| (:53,:61)
     const float c6 = D::rnd(1e-6f);   // the CPU reference casts python scalars to the tensor dtype
@@ -56,11 +64,11 @@ __device__ __forceinline__ SegParams seg_params(int mode, float mn, float mx, fl
     const float s = D::rnd(__fmul_rn(D::rnd(__frcp_rn(d)), qscale));
     const float s2 = D::rnd(__fadd_rn(s, c6));                         // (:85)
     const bool fast = divisor_fast(s2);
-    P.p0 = s; P.p1 = s2; P.p2 = fast ? __frcp_rn(s2) : 0.f; P.p3 = fast ? 1.f : 0.f;
+    P.p0 = s; P.p1 = s2; P.p2 = fast ? __frcp_rn(s2) : 0.f; P.p3 = (fast && finite) ? 1.f : 0.f;
   } else {
     const float a = D::rnd(__fadd_rn(D::rnd(__fsub_rn(mx, mn)), D::rnd(1e-8f)));   // alpha + 1e-8 (:179)
     const bool fast = divisor_fast(a);
-    P.p0 = a; P.p1 = mn; P.p2 = fast ? __frcp_rn(a) : 0.f; P.p3 = fast ? 1.f : 0.f;
+    P.p0 = a; P.p1 = mn; P.p2 = fast ? __frcp_rn(a) : 0.f; P.p3 = (fast && finite) ? 1.f : 0.f;
   }
   return P;
 }
@@ -77,7 +85,7 @@ template <typename T>
 __device__ __forceinline__ float quant_elem(int mode, float x, const SegParams& P, float qscale,
                                             float rq) {
   using D = DT<T>;
-  const bool fast = P.p3 != 0.f;
+  const bool fast = P.p2 != 0.f;       // RN(1/divisor) is only set for divisors in the checked range
   if (mode == kSym) {
     const float t = D::rnd(__fmul_rn(x, P.p0));
     const float r = rintf(t);                                          // torch.round: half to even
@@ -110,9 +118,95 @@ __device__ __forceinline__ bool chunk_has_nan(const uint4& c) {
   return n;
 }
 
+
+// ---- packed fast path for clean segments ------------------------------------------------------
+// 16-bit tensors: the dtype-rounded product / difference is ONE packed f16x2 / bf16x2 instruction
+// (RN16(RN32(a op b)) == RN16(a op b), common.cuh), rounding to integer and the two quotients run
+// on fp32x2 (FADD2 / FMUL2 / FFMA2).  fp32 tensors: everything on fp32x2.
+// |v| < 2^22, half to even.  The magic add is issued as two scalar __fadd_rn: ptxas contracts a
+// packed mul.rn.f32x2 feeding add.rn.f32x2 into FFMA2 even with -fmad=false (common.cuh), which
+// would round the product only once and break ties differently from torch.round.
+__device__ __forceinline__ f32x2 rint2_magic(f32x2 v) {
+  float v0, v1;
+  upk2(v, v0, v1);
+  const f32x2 m = pk2(__fadd_rn(v0, 12582912.0f), __fadd_rn(v1, 12582912.0f));
+  return add2(m, pk2(-12582912.0f, -12582912.0f));
+}
+__device__ __forceinline__ uint32_t copysign_u32(uint32_t mag, uint32_t sgn) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xD8;" : "=r"(d) : "r"(mag), "r"(sgn));   // (mag & ~m) | (sgn & m)
+  return d;
+}
+
+template <typename T>
+__device__ __forceinline__ uint4 chunk_apply_fast(int mode, const uint4& c, const SegParams& P, float qs,
+                                                  float rq) {
+  const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+  uint32_t o[4];
+  if constexpr (sizeof(T) == 4) {
+    if (mode == kSym) {
+      const f32x2 s_2 = pk2(P.p0, P.p0), na_2 = pk2(-P.p1, -P.p1), r_2 = pk2(P.p2, P.p2);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const f32x2 t = mul2(pk2(__uint_as_float(w[2 * h]), __uint_as_float(w[2 * h + 1])), s_2);
+        const f32x2 q = div2_rn_by(rint2_magic(t), na_2, r_2);
+        float q0, q1, t0, t1;
+        upk2(q, q0, q1); upk2(t, t0, t1);
+        o[2 * h] = copysign_u32(__float_as_uint(q0), __float_as_uint(t0));       // round(-0.3) = -0
+        o[2 * h + 1] = copysign_u32(__float_as_uint(q1), __float_as_uint(t1));
+      }
+    } else {
+      const f32x2 b_2 = pk2(P.p1, P.p1), a_2 = pk2(P.p0, P.p0), na_2 = pk2(-P.p0, -P.p0), r_2 = pk2(P.p2, P.p2);
+      const f32x2 s_2 = pk2(qs, qs), ns_2 = pk2(-qs, -qs), rs_2 = pk2(rq, rq);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const f32x2 t = sub2(pk2(__uint_as_float(w[2 * h]), __uint_as_float(w[2 * h + 1])), b_2);
+        const f32x2 u = mul2(div2_rn_by(t, na_2, r_2), s_2);
+        const f32x2 v = mul2(div2_rn_by(rint2_magic(u), ns_2, rs_2), a_2);
+        float v0, v1;
+        upk2(v, v0, v1);
+        o[2 * h] = __float_as_uint(__fadd_rn(v0, P.p1));        // scalar adds: never contracted into FFMA2
+        o[2 * h + 1] = __float_as_uint(__fadd_rn(v1, P.p1));
+      }
+    }
+  } else {
+    using P16T = P16<typename std::conditional<sizeof(T) == 2, T, __half>::type>;
+    if (mode == kSym) {
+      const uint32_t s2h = P16T::pack(P.p0, P.p0);
+      const f32x2 na_2 = pk2(-P.p1, -P.p1), r_2 = pk2(P.p2, P.p2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t t2 = P16T::mul(w[i], s2h);                                 // rnd(x * s)
+        const float t0 = P16T::lo(t2), t1 = P16T::hi(t2);
+        const f32x2 q = div2_rn_by(rint2_magic(pk2(t0, t1)), na_2, r_2);
+        float q0, q1;
+        upk2(q, q0, q1);
+        q0 = __uint_as_float(copysign_u32(__float_as_uint(q0), __float_as_uint(t0)));
+        q1 = __uint_as_float(copysign_u32(__float_as_uint(q1), __float_as_uint(t1)));
+        o[i] = P16T::pack(q0, q1);
+      }
+    } else {
+      const uint32_t b2h = P16T::pack(P.p1, P.p1), a2h = P16T::pack(P.p0, P.p0), s2h = P16T::pack(qs, qs);
+      const f32x2 na_2 = pk2(-P.p0, -P.p0), r_2 = pk2(P.p2, P.p2), ns_2 = pk2(-qs, -qs), rs_2 = pk2(rq, rq);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t t2 = P16T::sub(w[i], b2h);                                 // rnd(x - beta)
+        float n0, n1;
+        upk2(div2_rn_by(pk2(P16T::lo(t2), P16T::hi(t2)), na_2, r_2), n0, n1);
+        const uint32_t u2 = P16T::mul(P16T::pack(n0, n1), s2h);                   // rnd(rnd(n) * S)
+        float v0, v1;
+        upk2(div2_rn_by(rint2_magic(pk2(P16T::lo(u2), P16T::hi(u2))), ns_2, rs_2), v0, v1);
+        o[i] = P16T::add(P16T::mul(P16T::pack(v0, v1), a2h), b2h);                // rnd(rnd(v * a) + beta)
+      }
+    }
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 template <typename T>
 __device__ __forceinline__ uint4 chunk_apply(int mode, const uint4& c, const SegParams& P,
                                              float qscale, float rq) {
+  if (P.p3 != 0.f) return chunk_apply_fast<T>(mode, c, P, qscale, rq);
   float f[DT<T>::EPC];
   DT<T>::unpack(c, f);
 #pragma unroll
@@ -143,8 +237,9 @@ __global__ void __launch_bounds__(256) segquant_small_kernel(const uint4* __rest
     }
     if (nan) { mn = NAN; mx = NAN; }
     const int64_t seg = i / cps;
-    if (period > 1 && (seg % period) >= valid) { mn = 0.f; mx = 0.f; }
-    const SegParams P = seg_params<T>(mode, mn, mx, qscale);
+    const bool live = !(period > 1 && (seg % period) >= valid);
+    if (!live) { mn = 0.f; mx = 0.f; }
+    const SegParams P = seg_params<T>(mode, mn, mx, qscale, live);
     st_stream(out + i, chunk_apply<T>(mode, c, P, qscale, rq));
   }
 }
@@ -184,8 +279,9 @@ __global__ void __launch_bounds__(THREADS) segquant_block_kernel(const uint4* __
 #pragma unroll
   for (int w = 0; w < THREADS / 32; ++w) { mn = fminf(mn, part[w].x); mx = fmaxf(mx, part[w].y); }
   if (nanflag) { mn = NAN; mx = NAN; }
-  if (period > 1 && (seg % period) >= valid) { mn = 0.f; mx = 0.f; }
-  const SegParams P = seg_params<T>(mode, mn, mx, qscale);
+  const bool live = !(period > 1 && (seg % period) >= valid);
+  if (!live) { mn = 0.f; mx = 0.f; }
+  const SegParams P = seg_params<T>(mode, mn, mx, qscale, live);
   const float rq = __frcp_rn(qscale);
 #pragma unroll
   for (int i = 0; i < NC; ++i) {
@@ -248,8 +344,9 @@ __global__ void __launch_bounds__(256) seg_apply_kernel(const uint4* __restrict_
     }
     mn = warp_min(mn); mx = warp_max(mx);
     if (__any_sync(0xffffffffu, nan)) { mn = NAN; mx = NAN; }
-    if (period > 1 && (seg % period) >= valid) { mn = 0.f; mx = 0.f; }
-    if (threadIdx.x == 0) sp = seg_params<T>(mode, mn, mx, qscale);
+    const bool live = !(period > 1 && (seg % period) >= valid);
+    if (!live) { mn = 0.f; mx = 0.f; }
+    if (threadIdx.x == 0) sp = seg_params<T>(mode, mn, mx, qscale, live);
   }
   __syncthreads();
   const SegParams P = sp;
@@ -275,12 +372,18 @@ static int64_t seg_splits(int64_t nseg, int64_t cps) {
   return max((int64_t)1, splits);
 }
 
+template <typename T> static float host_rnd(float v) { return v; }
+template <> float host_rnd<__half>(float v) { return __half2float(__float2half_rn(v)); }
+template <> float host_rnd<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
 template <typename T>
 static int launch_segquant(const void* x, void* out, int64_t nseg, int64_t seglen, int mode,
                            int bits, int64_t period, int64_t valid, void* ws, size_t ws_bytes,
                            cudaStream_t st) {
   const int64_t cps = seglen * (int64_t)sizeof(T) / 16;
-  const float qscale = mode == kSym ? (float)((1ll << (bits - 1)) - 1) : (float)((1ll << bits) - 1);
+  // qmax / S enter the reference as python scalars, which its CPU kernels cast to the tensor dtype
+  // first (only matters above 8 bits for bf16, 11 bits for fp16)
+  const float qscale = host_rnd<T>(mode == kSym ? (float)((1ll << (bits - 1)) - 1) : (float)((1ll << bits) - 1));
   const bool small = cps <= 32 && (cps & (cps - 1)) == 0;
   if (small) {
     const int64_t nchunks = nseg * cps;

@@ -1,0 +1,122 @@
+"""Packed-checkpoint side of the MXQ path: the reference stops at fp16
+fake-quantized weights (mxq_quant/main.py:96-100 saves them with ``save_pretrained``) and its only
+consumer of the packed 2/4-bit layout is the raw ``gemv_mxq_forward_cuda`` binding
+(cuda_kernel/test_correct_gemv.py:49).  This module closes the loop PTQ -> pack -> inference:
+
+  MXQLinear            nn.Module holding the seven packed tensors of gemv_mxq_cuda.cu:39-208 as
+                       buffers (state-dict keys = the binding's argument names); forward routes
+                       decode-sized inputs to the GEMV kernel and prefill-sized ones to the
+                       tcgen05 dequant-GEMM
+  pack_linear          nn.Linear (fp16) -> MXQLinear, optionally with the calibration statistic
+  convert_model        swap every nn.Linear that nas_quant(args.pack=True) annotated
+  save_packed / load_packed   the packed tensors of a converted model, as one torch file
+
+There is no CPU fallback: MXQLinear.forward raises for non-CUDA inputs.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+PACKED_KEYS = ("weight", "weight_last", "zeros_and_scales", "zeros_2nd", "scales_2nd", "scales_4b", "zeros_4b")
+FORMAT = "mxq_b200.packed.v1"
+
+
+class MXQLinear(nn.Module):
+    """y = x @ dequant(W)^T for a packed mixed 2/4-bit weight [out_features, in_features]."""
+
+    GEMV_MAX_TOKENS = 8        # up to here the weight-streaming GEMV wins over a 256-token MMA tile
+
+    def __init__(self, in_features: int, out_features: int, device=None):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        for k, (shape, dt) in ops.packed_shapes(out_features, in_features).items():
+            self.register_buffer(k, torch.zeros(shape, dtype=dt, device=device))
+        self._ws = None
+
+    @property
+    def packed(self) -> dict:
+        return {k: getattr(self, k) for k in PACKED_KEYS}
+
+    @classmethod
+    def from_packed(cls, packed: dict) -> "MXQLinear":
+        OC, IC = packed["weight"].shape[0], packed["weight"].shape[1] * 16
+        m = cls(IC, OC, device=packed["weight"].device)
+        for k in PACKED_KEYS:
+            getattr(m, k).copy_(packed[k])
+        return m
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("MXQLinear needs CUDA tensors (no CPU fallback)")
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, self.in_features)
+        if x2.dtype != torch.float16:
+            x2 = x2.half()
+        if x2.shape[0] == 0:
+            return x.new_zeros((*lead, self.out_features), dtype=torch.float16)
+        if x2.shape[0] <= self.GEMV_MAX_TOKENS:
+            y = ops.gemv(x2, self.packed, validate=False)
+        else:
+            if self._ws is None or self._ws.device != x2.device:
+                self._ws = torch.zeros(4096, dtype=torch.uint8, device=x2.device)
+            y = ops.gemm(x2, self.packed, workspace=self._ws, validate=False)
+        return y.reshape(*lead, self.out_features)
+
+    def dequantize(self, dtype=torch.float16) -> torch.Tensor:
+        return ops.unpack(self.packed, dtype)
+
+    def extra_repr(self) -> str:
+        return f"in_features={self.in_features}, out_features={self.out_features}, bits=3.0 (2/4 mixed)"
+
+
+@torch.no_grad()
+def pack_linear(linear: nn.Linear, colstat: torch.Tensor | None = None) -> MXQLinear:
+    """Quantize an fp16 nn.Linear into the packed layout (encode policy: DESIGN.md section 2).
+    `colstat`: calibration column statistic, zero = dead column (mxqgpt.py:401-403)."""
+    if linear.bias is not None:
+        raise ValueError("the MXQ path has no bias (utils_quant.py:613)")
+    W = linear.weight.data
+    if not W.is_cuda:
+        raise RuntimeError("pack_linear needs CUDA weights (no CPU fallback)")
+    return MXQLinear.from_packed(ops.pack(W.half(), colstat))
+
+
+def convert_model(model: nn.Module) -> nn.Module:
+    """Replace every nn.Linear carrying ``mxq_packed`` (set by nas_quant with args.pack) in place."""
+    for name, child in list(model.named_children()):
+        if isinstance(child, nn.Linear) and hasattr(child, "mxq_packed"):
+            setattr(model, name, MXQLinear.from_packed(child.mxq_packed))
+        else:
+            convert_model(child)
+    return model
+
+
+def save_packed(model: nn.Module, path: str) -> None:
+    """{"format", "linears": {module name: {packed key: tensor}}} of every MXQLinear in `model`."""
+    linears = {n: {k: v.detach().cpu() for k, v in m.packed.items()}
+               for n, m in model.named_modules() if isinstance(m, MXQLinear)}
+    torch.save({"format": FORMAT, "linears": linears}, path)
+
+
+def load_packed(model: nn.Module, path: str, device=None) -> nn.Module:
+    """Swap the named nn.Linear / MXQLinear modules of `model` for MXQLinear loaded from `path`."""
+    blob = torch.load(path, map_location="cpu")
+    if blob.get("format") != FORMAT:
+        raise ValueError(f"{path}: not an {FORMAT} file")
+    for name, packed in blob["linears"].items():
+        parent = model
+        *path_, leaf = name.split(".")
+        for part in path_:
+            parent = getattr(parent, part)
+        old = getattr(parent, leaf)
+        dev = device
+        if dev is None:
+            t = next(iter(old.parameters()), None)
+            if t is None:
+                t = next(iter(old.buffers()))
+            dev = t.device
+        setattr(parent, leaf, MXQLinear.from_packed({k: v.to(dev) for k, v in packed.items()}))
+    return model

@@ -192,7 +192,7 @@ def sym_quant(x, dtype: str = "fp32", num_bits: int = 8, layerwise: bool = False
             m = np.zeros((xs.shape[0], 1), dtype=F32)
         if live is not None:
             m = np.where(live[:, None], m, F32(0))
-        qmax = F32(2 ** (num_bits - 1) - 1)
+        qmax = rnd(F32(2 ** (num_bits - 1) - 1))   # python scalar, cast to the tensor dtype
         c6 = rnd(F32(1e-6))                        # python scalars are cast to the tensor dtype first
         d = rnd(m + c6)
         s = rnd(rnd(F32(1.0) / d) * qmax)
@@ -223,7 +223,7 @@ def asym_quant(x, dtype: str = "fp32", num_bits: int = 8, layerwise: bool = Fals
             mx = np.where(live[:, None], mx, F32(0))
         alpha = rnd(mx - mn)
         a = rnd(alpha + rnd(F32(1e-8)))            # python scalars are cast to the tensor dtype first
-        s = F32(2 ** num_bits - 1)
+        s = rnd(F32(2 ** num_bits - 1))            # python scalar, cast to the tensor dtype
         t = rnd(xs - mn)
         t = rnd(t / a)
         t = rnd(t * s)
