@@ -304,6 +304,164 @@ __global__ void __launch_bounds__(kFQThreads) fakequant_fwd_kernel(const FQParam
   }
 }
 
+
+// -------------------------------------------------------------------------------------------
+// Row-resident variant for the reference recipe (group 16, {low, low, low, pool 4}): one CTA per
+// row, the row's 16-byte chunks stay in registers between the pooled min/max and the quantize
+// pass, so the kernel is a single load -> reduce -> compute -> store stream with nothing staged
+// in shared memory but the per-warp partial statistics.  Measured faster than the TMA ring above
+// on B200 for rows of up to 3072 chunks (profiles/): more independent loads in flight per SM and
+// no per-stage block barrier.
+// -------------------------------------------------------------------------------------------
+template <typename T, int THREADS, int NC>
+__global__ void __launch_bounds__(THREADS) fakequant_row_kernel(const uint4* __restrict__ x,
+                                                                uint4* __restrict__ out, int cpr,
+                                                                int low_bits) {
+  using D = DT<T>;
+  constexpr bool k16 = sizeof(T) == 2;
+  using P = P16<typename std::conditional<k16, T, __half>::type>;
+  constexpr int EPC = D::EPC;
+  constexpr int LPG = 16 / EPC;                       // lanes (chunks) per 16-column group
+  constexpr int LPG_SHIFT = LPG == 2 ? 1 : 2;
+  __shared__ float2 part[THREADS / 32];
+  const float kEps = D::rnd(1e-8f);
+  const uint4* xr = x + (size_t)blockIdx.x * cpr;
+  uint4* orow = out + (size_t)blockIdx.x * cpr;
+  const int lane = threadIdx.x & 31;
+
+  uint4 ch[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int c = i * THREADS + threadIdx.x;
+    ch[i] = c < cpr ? ld_stream(xr + c) : make_uint4(0, 0, 0, 0);
+  }
+  // ---- pooled min/max of the row (every fourth group) ----------------------------------------
+  float pmin = INFINITY, pmax = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int c = i * THREADS + threadIdx.x;
+    if (c < cpr && ((c >> LPG_SHIFT) & 3) == 3) {
+      float f[EPC];
+      D::unpack(ch[i], f);
+#pragma unroll
+      for (int e = 0; e < EPC; ++e) { pmin = fminf(pmin, f[e]); pmax = fmaxf(pmax, f[e]); }
+    }
+  }
+  pmin = warp_min(pmin); pmax = warp_max(pmax);
+  if (lane == 0) part[threadIdx.x >> 5] = make_float2(pmin, pmax);
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; ++w) { pmin = fminf(pmin, part[w].x); pmax = fmaxf(pmax, part[w].y); }
+  // utils_quant.py:369-377: fp32 subtract, cast to the tensor dtype on assignment (:383)
+  const float a_pool = D::rnd(__fadd_rn(D::rnd(__fsub_rn(pmax, pmin)), kEps));
+  const float b_pool = pmin;
+  const float r_pool = __frcp_rn(a_pool);
+  const float s_low = (float)((1 << low_bits) - 1);
+  const float rs_low = __frcp_rn(s_low), rs_pool = __frcp_rn(15.0f);
+
+  // ---- quantize / dequantize -------------------------------------------------------------------
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int c = i * THREADS + threadIdx.x;
+    const bool valid = c < cpr;          // cpr % LPG == 0 and THREADS % LPG == 0: groups never straddle
+    const bool pooled = ((c >> LPG_SHIFT) & 3) == 3;
+    if constexpr (k16) {
+      uint32_t mn = P::vmin(P::vmin(ch[i].x, ch[i].y), P::vmin(ch[i].z, ch[i].w));
+      uint32_t mx = P::vmax(P::vmax(ch[i].x, ch[i].y), P::vmax(ch[i].z, ch[i].w));
+      mn = P::vmin(mn, prmt_b32(mn, mn, 0x1032));
+      mx = P::vmax(mx, prmt_b32(mx, mx, 0x1032));
+      uint32_t mm = valid ? prmt_b32(mn, mx, 0x5410) : P::kPosInfNegInf;   // lo: min, hi: max
+#pragma unroll
+      for (int o = LPG >> 1; o > 0; o >>= 1) {
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, mm, o);
+        mm = prmt_b32(P::vmin(mm, other), P::vmax(mm, other), 0x7610);
+      }
+      if (!valid) continue;
+      uint32_t b2 = prmt_b32(mm, mm, 0x1010);
+      const uint32_t alpha2 = P::sub(prmt_b32(mm, mm, 0x3232), b2);        // max - min (:358-361)
+      const float ax = __fadd_rn(P::lo(alpha2), kEps);                     // alpha + 1e-8 (:456)
+      uint32_t a2 = P::pack(ax, ax);
+      float a = P::lo(a2);
+      float r = rcp_rn_normal(a);
+      uint32_t s2 = P::kS3, ch2 = P::kC3, cl2 = 0u;
+      if (pooled) {
+        a = a_pool; r = r_pool; a2 = P::pack(a_pool, a_pool); b2 = P::pack(b_pool, b_pool);
+        s2 = P::kS15; ch2 = P::kC15hi; cl2 = P::kC15lo;
+      }
+      const uint32_t w[4] = {ch[i].x, ch[i].y, ch[i].z, ch[i].w};
+      const f32x2 na_2 = pk2(-a, -a), r_2 = pk2(r, r);
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t t2 = P::sub(w[j], b2);                              // x - beta
+        float n_lo, n_hi;
+        upk2(div2_rn_by(pk2(P::lo(t2), P::hi(t2)), na_2, r_2), n_lo, n_hi);
+        const uint32_t n2 = P::pack(n_lo, n_hi);
+        const uint32_t m2 = P::add(P::mul(n2, s2), P::kMagic);             // round-half-even
+        const uint32_t q2 = P::sub(m2, P::kMagic);
+        const uint32_t v2 = P::fma(q2, ch2, P::mul(q2, cl2));              // == RN16(RN32(q / s))
+        o[j] = P::add(P::mul(v2, a2), b2);
+      }
+      st_stream(orow + c, make_uint4(o[0], o[1], o[2], o[3]));
+    } else {
+      float f[EPC];
+      D::unpack(ch[i], f);
+      float lmin = INFINITY, lmax = -INFINITY;
+      if (valid) {
+#pragma unroll
+        for (int e = 0; e < EPC; ++e) { lmin = fminf(lmin, f[e]); lmax = fmaxf(lmax, f[e]); }
+      }
+#pragma unroll
+      for (int o = LPG >> 1; o > 0; o >>= 1) {
+        lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+      }
+      if (!valid) continue;
+      float a = D::rnd(__fadd_rn(D::rnd(__fsub_rn(lmax, lmin)), kEps));    // alpha + 1e-8 (:456)
+      float b = lmin;
+      float r = rcp_rn_normal(a);
+      float sq = s_low, rs = rs_low;
+      if (pooled) { a = a_pool; b = b_pool; r = r_pool; sq = 15.0f; rs = rs_pool; }
+      const f32x2 b_2 = pk2(b, b), a_2 = pk2(a, a), na_2 = pk2(-a, -a), r_2 = pk2(r, r);
+      const f32x2 s_2 = pk2(sq, sq), ns_2 = pk2(-sq, -sq), rs_2 = pk2(rs, rs);
+      const f32x2 nm_2 = pk2(-12582912.0f, -12582912.0f);
+      float o4[4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const f32x2 t = sub2(pk2(f[2 * h], f[2 * h + 1]), b_2);
+        const f32x2 u = mul2(div2_rn_by(t, na_2, r_2), s_2);
+        float u0, u1;
+        upk2(u, u0, u1);
+        const float m0 = __fadd_rn(u0, 12582912.0f), m1 = __fadd_rn(u1, 12582912.0f);
+        const f32x2 q = add2(pk2(m0, m1), nm_2);
+        const f32x2 wv = mul2(div2_rn_by(q, ns_2, rs_2), a_2);
+        float w0, w1;
+        upk2(wv, w0, w1);
+        o4[2 * h] = __fadd_rn(w0, b);
+        o4[2 * h + 1] = __fadd_rn(w1, b);
+      }
+      st_stream(orow + c, make_uint4(__float_as_uint(o4[0]), __float_as_uint(o4[1]),
+                                     __float_as_uint(o4[2]), __float_as_uint(o4[3])));
+    }
+  }
+}
+
+template <typename T>
+static bool launch_fq_row(const FQParams& p, cudaStream_t st) {
+  const int c = p.cpr;
+  const uint4* x = (const uint4*)p.x;
+  uint4* o = (uint4*)p.out;
+  const unsigned g = (unsigned)p.rows;
+  if (c <= 256) fakequant_row_kernel<T, 128, 2><<<g, 128, 0, st>>>(x, o, c, p.low_bits);
+  else if (c <= 512) fakequant_row_kernel<T, 128, 4><<<g, 128, 0, st>>>(x, o, c, p.low_bits);
+  else if (c <= 1024) fakequant_row_kernel<T, 256, 4><<<g, 256, 0, st>>>(x, o, c, p.low_bits);
+  else if (c <= 1536) fakequant_row_kernel<T, 256, 6><<<g, 256, 0, st>>>(x, o, c, p.low_bits);
+  else if (c <= 2048) fakequant_row_kernel<T, 256, 8><<<g, 256, 0, st>>>(x, o, c, p.low_bits);
+  else if (c <= 3072) fakequant_row_kernel<T, 256, 12><<<g, 256, 0, st>>>(x, o, c, p.low_bits);
+  else return false;
+  return true;
+}
+
 // -------------------------------------------------------------------------------------------
 // STE backward: pure streaming select, 3 tensors, 128-bit accesses, 4 chunks in flight / thread
 // -------------------------------------------------------------------------------------------
@@ -453,6 +611,18 @@ extern "C" int mxq_fakequant_fwd(const void* x, void* out, uint8_t* codes, int64
   if (grid > p.num_sets) grid = p.num_sets;
   cudaStream_t st = as_stream(stream);
   const bool ref = group_bits == nullptr;
+  // reference recipe at group 16 without code output: the row-resident kernel (rows of up to 3072
+  // chunks; the packed 16-bit arithmetic exists for 2-bit groups only).  MXQ_FQ_RING forces the ring.
+  if (ref && group == 16 && !codes && p.cpr <= 3072 && rows >= kNumSMs && (esize == 4 || low_bits == 2) &&
+      !getenv("MXQ_FQ_RING")) {
+    bool ok = false;
+    switch (dtype) {
+      case MXQ_F32: ok = launch_fq_row<float>(p, st); break;
+      case MXQ_F16: ok = launch_fq_row<__half>(p, st); break;
+      default: ok = launch_fq_row<__nv_bfloat16>(p, st); break;
+    }
+    if (ok) MXQ_LAUNCH_RESULT();
+  }
   switch (dtype) {
     case MXQ_F32: return launch_fq<float>(p, ref, smem, grid, st);
     case MXQ_F16: return launch_fq<__half>(p, ref, smem, grid, st);

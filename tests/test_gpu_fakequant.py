@@ -38,6 +38,28 @@ def test_golden_forward_backward(cuda, fq):
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("shape", [(160, 11008), (200, 8192), (256, 4096), (150, 1536), (1000, 256), (148, 64)])
+def test_row_kernel_vs_oracle_and_ring(cuda, dtype, shape, monkeypatch):
+    """rows >= 148 without code output take the row-resident kernel (every chunks-per-thread
+    variant); it must equal the oracle and the TMA-ring kernel (MXQ_FQ_RING) bit for bit."""
+    from mxq_b200 import ops
+    g = torch.Generator().manual_seed(shape[0] * 3 + shape[1] + len(dtype))
+    x = (torch.randn(*shape, generator=g) * 0.02).to(TD[dtype])
+    x[5, :16] = 0.25                      # constant group
+    x[6, :] = 0.0                         # zero row
+    want = O.fakequant_fwd(x.float().numpy(), dtype, 2)
+    xd = x.to(cuda)
+    got = ops.fakequant_fwd(xd)
+    assert bits_equal(to_np(got), want)
+    monkeypatch.setenv("MXQ_FQ_RING", "1")
+    ring = ops.fakequant_fwd(xd)
+    assert bits_equal(to_np(ring), want)
+    if dtype == "fp32":                   # fp32 rows support any low bit-width
+        monkeypatch.delenv("MXQ_FQ_RING")
+        assert bits_equal(to_np(ops.fakequant_fwd(xd, num_bits=3)), O.fakequant_fwd(x.float().numpy(), dtype, 3))
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16", "fp16"])
 @pytest.mark.parametrize("shape", [(256, 4096), (48, 11008), (3, 64), (1000, 256)])
 def test_seeded_vs_oracle_with_codes(cuda, dtype, shape):
     from mxq_b200 import ops
