@@ -95,6 +95,19 @@ MXQ_API int mxq_colsumsq(const void* X, int64_t tokens, int64_t cols, int dtype,
 MXQ_API int mxq_wanda_metric(const void* W, const float* scaler_row, float* out, int64_t rows,
                      int64_t cols, int dtype, void* stream);
 
+/* ---- (f-3) importance-driven 2/4-bit allocation ------------------------------------------------
+ * importance[g] = sum_{r, c in group g} |W[r,c]| * sqrt(scaler_row[c])   (the Wanda metric of
+ * prune.py:177 summed per column group; scaler_row == NULL: plain |W|).  Of every 4 consecutive
+ * groups the most important one gets {0x80 | 4} (pooled 4-bit), the others `low_bits`; ties go to
+ * the lowest index.  The result is a group_bits mask for mxq_fakequant_fwd / mxq_ptq_quant.
+ * W fp16 [rows, cols]; cols % (4*group) == 0; importance (optional) double[cols/group].
+ * Deterministic and exact: |W| column sums are accumulated as 64-bit integers in units of 2^-24.
+ * workspace: mxq_allocate_bits_workspace_bytes(cols). */
+MXQ_API size_t mxq_allocate_bits_workspace_bytes(int64_t cols);
+MXQ_API int mxq_allocate_bits(const void* W, const float* scaler_row, int64_t rows, int64_t cols, int group,
+                              int low_bits, uint8_t* group_bits, double* importance, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* ---- (a-6/a-7) MXQGPT.fasterquant(blocksize=16) + Quantizer ----------------------------------
  * mxq_quant/lib/mxqgpt.py:387-448, mxq_quant/lib/quantizer.py:5-20,61-121,149-155.
  * W (fp16 [rows, cols]) -> Wq (fp16 fake-quantized, may alias W).  colstat (optional fp32[cols]):

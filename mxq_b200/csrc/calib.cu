@@ -100,6 +100,61 @@ __global__ void wanda_metric_kernel(const T* __restrict__ W, const float* __rest
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Importance-driven 2/4-bit allocation (the reference hard-wires "the last 16
+// of every 64 columns are 4-bit", utils_quant.py:340-385 / mxqgpt.py:404-419, and computes the
+// Wanda metric |W| * sqrt(scaler_row) only on its pruning paths, prune.py:177).
+//   importance[g] = sum over rows and the group's columns of |W[r,c]| * sqrt(scaler_row[c])
+// Of every 4 consecutive groups the most important one becomes the pooled 4-bit group.
+// The column sums of |W| are EXACT: fp16 magnitudes are integer multiples of 2^-24, so they are
+// accumulated as 64-bit integers (order-independent, atomics allowed); the per-group combination
+// runs in fp64 in a fixed order.  Oracle and kernel therefore agree bit for bit and the mask never
+// depends on the launch geometry.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colabs_i64_kernel(const __half* __restrict__ W,
+                                                         unsigned long long* __restrict__ colabs,
+                                                         int64_t rows, int cols, int rows_per_slab) {
+  const int chunk = blockIdx.x * 256 + threadIdx.x;          // 8 columns
+  if (chunk * 8 >= cols) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_slab;
+  const int64_t r1 = min(rows, r0 + rows_per_slab);
+  unsigned long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t r = r0; r < r1; ++r) {
+    float f[8];
+    DT<__half>::unpack(ld_stream(W + (size_t)r * cols + (size_t)chunk * 8), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float m = fabsf(f[e]) * 16777216.0f;             // exact: |fp16| * 2^24 < 2^40
+      acc[e] += (m <= 1.1e12f) ? (unsigned long long)__float2ll_rn(m) : 0ull;   // inf / nan weights: ignored
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) atomicAdd(colabs + (size_t)chunk * 8 + e, acc[e]);
+}
+
+__global__ void alloc_bits_kernel(const unsigned long long* __restrict__ colabs,
+                                  const float* __restrict__ scaler_row, int cols, int group, int low_bits,
+                                  uint8_t* __restrict__ group_bits, double* __restrict__ importance) {
+  const int blk = blockIdx.x * blockDim.x + threadIdx.x;     // 4 consecutive groups
+  const int nblk = cols / (4 * group);
+  if (blk >= nblk) return;
+  double best = -1.0;
+  int arg = 0;
+  for (int k = 0; k < 4; ++k) {
+    const int c0 = (blk * 4 + k) * group;
+    double acc = 0.0;
+    for (int j = 0; j < group; ++j) {
+      const double a = __dmul_rn((double)colabs[c0 + j], 1.0 / 16777216.0);
+      const double w = scaler_row ? __dsqrt_rn((double)scaler_row[c0 + j]) : 1.0;
+      acc = __dadd_rn(acc, __dmul_rn(a, w));                  // never contracted: the oracle rounds twice
+    }
+    if (importance) importance[blk * 4 + k] = acc;
+    if (acc > best) { best = acc; arg = k; }                 // ties -> lowest index
+  }
+  for (int k = 0; k < 4; ++k) group_bits[blk * 4 + k] = (uint8_t)(k == arg ? (MXQ_POOL_FLAG | 4) : low_bits);
+}
+
 static int slabs_for(int64_t tokens, int cpr) {
   const int col_tiles = (int)ceil_div(cpr, kCSThreads);
   int slabs = (kNumSMs * 8) / col_tiles;  // ~8 CTAs of 256 threads per SM
@@ -168,5 +223,38 @@ extern "C" int mxq_wanda_metric(const void* W, const float* scaler_row, float* o
     wanda_metric_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)W, scaler_row, out, rows, (int)cols);
   else
     return MXQ_E_DTYPE;
+  MXQ_LAUNCH_RESULT();
+}
+
+extern "C" size_t mxq_allocate_bits_workspace_bytes(int64_t cols) {
+  return cols > 0 ? (size_t)cols * sizeof(unsigned long long) : 16;
+}
+
+extern "C" int mxq_allocate_bits(const void* W, const float* scaler_row, int64_t rows, int64_t cols, int group,
+                                 int low_bits, uint8_t* group_bits, double* importance, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  if (rows < 0 || cols <= 0 || group <= 0) return MXQ_E_SHAPE;
+  if (cols % (4 * group) || cols % 8 || cols > (1 << 24) || low_bits < 1 || low_bits > 8) return MXQ_E_SHAPE;
+  MXQ_CHECK_PTR(W);
+  MXQ_CHECK_PTR(workspace);
+  if (!group_bits) return MXQ_E_NULL;
+  if (workspace_bytes < (size_t)cols * sizeof(unsigned long long)) return MXQ_E_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  unsigned long long* colabs = (unsigned long long*)workspace;
+  cudaError_t e = cudaMemsetAsync(colabs, 0, (size_t)cols * sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return (int)e;
+  if (rows > 0) {
+    const int col_tiles = (int)ceil_div(cols / 8, 256);
+    int slabs = (kNumSMs * 8) / col_tiles;
+    if (slabs < 1) slabs = 1;
+    if (slabs > rows) slabs = (int)rows;
+    const int rows_per_slab = (int)ceil_div(rows, slabs);
+    slabs = (int)ceil_div(rows, rows_per_slab);
+    colabs_i64_kernel<<<dim3((unsigned)col_tiles, (unsigned)slabs), 256, 0, st>>>((const __half*)W, colabs, rows,
+                                                                               (int)cols, rows_per_slab);
+  }
+  const int nblk = (int)(cols / (4 * group));
+  alloc_bits_kernel<<<(unsigned)ceil_div(nblk, 128), 128, 0, st>>>(colabs, scaler_row, (int)cols, group, low_bits,
+                                                                   group_bits, importance);
   MXQ_LAUNCH_RESULT();
 }

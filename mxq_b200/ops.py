@@ -134,6 +134,28 @@ def wanda_metric(W: torch.Tensor, scaler_row: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def allocate_group_bits(W: torch.Tensor, scaler_row: torch.Tensor | None = None, group: int = 16,
+                        low_bits: int = 2, return_importance: bool = False):
+    """Importance-driven 2/4-bit allocation: of every 4 consecutive `group`-column groups the one with
+    the largest sum of |W| * sqrt(scaler_row) (Wanda metric, prune.py:177) becomes the pooled 4-bit
+    group.  Returns the uint8 group_bits mask for fakequant_fwd / ptq_quant (and the fp64 importances)."""
+    L.require_cuda(W, scaler_row)
+    if W.dtype != torch.float16:
+        raise TypeError("allocate_group_bits expects fp16 weights")
+    W = W.contiguous()
+    rows, cols = W.shape
+    if cols % (4 * group):
+        raise ValueError(f"cols={cols} must be a multiple of 4*group={4 * group}")
+    sr = None if scaler_row is None else scaler_row.contiguous().float()
+    gb = torch.empty(cols // group, dtype=torch.uint8, device=W.device)
+    imp = torch.empty(cols // group, dtype=torch.float64, device=W.device) if return_importance else None
+    ws = _ws(L.lib().mxq_allocate_bits_workspace_bytes(cols), W.device)
+    rc = L.lib().mxq_allocate_bits(L.ptr(W), L.ptr(sr), rows, cols, group, low_bits, L.ptr(gb), L.ptr(imp),
+                                   L.ptr(ws), ws.numel(), L.stream())
+    L.check(rc, "mxq_allocate_bits")
+    return (gb, imp) if return_importance else gb
+
+
 def ptq_quant(W: torch.Tensor, colstat: torch.Tensor | None = None, low_bits: int = 2,
               group: int = 16, group_bits=None, return_codes: bool = False, out=None,
               workspace=None):

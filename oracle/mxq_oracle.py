@@ -144,6 +144,33 @@ def fakequant_fwd(x, dtype: str = "fp32", num_bits: int = 2, group: int = 16,
     return out
 
 
+def allocate_group_bits(W16, scaler_row=None, group: int = 16, low_bits: int = 2):
+    """Importance-driven allocation (SURVEY.md 8f rank 3): importance[g] = sum_{r, c in g}
+    |W[r,c]| * sqrt(scaler_row[c]) -- the Wanda metric of mxq_quant/lib/prune.py:177 summed per
+    column group -- and of every 4 consecutive groups the most important one becomes the pooled
+    4-bit group (ties: lowest index); the reference itself always takes the last one
+    (utils_quant.py:340-385).  Exact arithmetic: |fp16| column sums as integers in units of 2^-24,
+    then fp64 in column order.  Returns (group_bits uint8[K/group], importance float64[K/group])."""
+    W = np.asarray(W16, dtype=np.float16)
+    N, K = W.shape
+    if K % (4 * group):
+        raise ValueError("cols must be a multiple of 4*group")
+    mag = np.abs(W.astype(np.float64)) * 16777216.0
+    mag = np.where(np.isfinite(mag), mag, 0.0)
+    colabs = mag.astype(np.int64).sum(axis=0)
+    a = colabs.astype(np.float64) * (1.0 / 16777216.0)
+    w = np.ones(K) if scaler_row is None else np.sqrt(np.asarray(scaler_row, dtype=np.float32).astype(np.float64))
+    term = (a * w).reshape(K // group, group)
+    imp = np.zeros(K // group)
+    for j in range(group):                      # fixed order, like the kernel
+        imp = imp + term[:, j]
+    blocks = imp.reshape(-1, 4)
+    arg = np.argmax(blocks, axis=1)             # first maximum
+    gb = np.full((K // group // 4, 4), low_bits, dtype=np.uint8)
+    gb[np.arange(gb.shape[0]), arg] = POOL | 4
+    return gb.reshape(-1), imp
+
+
 # --------------------------------------------------------------------------------------
 # (f-1) SymQuantizer / AsymQuantizer.forward   LLM-QAT/models/utils_quant.py:31-95, 98-199
 # --------------------------------------------------------------------------------------

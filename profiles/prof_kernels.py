@@ -13,7 +13,7 @@ from mxq_b200 import ops  # noqa: E402
 
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-which = sys.argv[1:] or ["fq", "ste", "ptq", "pack", "gemv", "stats", "gemm"]
+which = sys.argv[1:] or ["fq", "ste", "act", "ptq", "pack", "gemv", "stats", "gemm"]
 REP = 3
 
 if "fq" in which:
@@ -23,6 +23,13 @@ if "fq" in which:
             ops.fakequant_fwd(x)
     x = (torch.randn(4096, 11008, device=dev) * 0.02).bfloat16()
     ops.fakequant_fwd(x)
+if "act" in which:
+    from mxq_b200 import AsymQuantizer, SymQuantizer
+    clip = torch.tensor([-2.0, 2.0])
+    xa = torch.randn(2, 2048, 4096, device=dev).bfloat16()
+    for _ in range(REP):
+        SymQuantizer.apply(xa, clip, 8, False)
+        AsymQuantizer.apply(xa, clip, 4, False)
 if "ste" in which:
     for dt in (torch.float32, torch.bfloat16):
         x = (torch.randn(4096, 4096, device=dev) * 0.02).to(dt)
@@ -60,7 +67,7 @@ if "gemv" in which or "gemm" in which:
                 ops.gemv(x, p)
     if "gemm" in which:
         try:
-            for oc, ic in ((4096, 4096), (11008, 4096)):
+            for oc, ic in ((4096, 4096), (11008, 4096), (4096, 11008)):
                 p = rand_packed(oc, ic)
                 x = torch.randn(2048, ic, device=dev).half()
                 for _ in range(REP):

@@ -130,3 +130,24 @@ def test_colsumsq_shapes_and_dtypes(cuda):
     b = a.clone()
     ops.colsumsq(X, out=b, prev_scale=0.5, add_scale=0.25)
     assert torch.allclose(b, 0.75 * a, rtol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(64, 256), (4096, 4096), (1000, 11008), (16, 64)])
+def test_allocate_group_bits_bit_exact(cuda, shape):
+    """f-3: importance-driven 2/4-bit allocation mask and fp64 importances equal the oracle exactly
+    (integer column sums + fixed-order fp64), and the mask drives the PTQ / fake-quant kernels."""
+    from mxq_b200 import ops
+    g = torch.Generator().manual_seed(shape[0] + shape[1])
+    W = (torch.randn(*shape, generator=g) * 0.02).half()
+    W[:, 16:32] *= 6
+    sr = torch.rand(shape[1], generator=g) * 4
+    sr[7] = 0
+    for stat in (None, sr):
+        want_gb, want_imp = O.allocate_group_bits(W.numpy(), None if stat is None else stat.numpy())
+        gb, imp = ops.allocate_group_bits(W.to(cuda), None if stat is None else stat.to(cuda), return_importance=True)
+        assert np.array_equal(imp.cpu().numpy(), want_imp), "importances (fp64, bit-exact)"
+        assert np.array_equal(gb.cpu().numpy(), want_gb), "allocation mask"
+    if shape[0] % 16 == 0:
+        out = ops.fakequant_fwd(W.to(cuda).float(), group_bits=gb)
+        want = O.fakequant_fwd(W.float().numpy(), "fp32", 2, group_bits=want_gb)
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))

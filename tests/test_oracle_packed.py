@@ -116,3 +116,29 @@ def test_random_packed_decode_matches_scalar_formula():
             z4 = (int(p["zeros_4b"].view(np.uint32)[oc // 8]) >> (4 * (oc % 8))) & 0xF
             want = np.float32(p["scales_4b"][oc]) * np.float32(q - z4)
         assert W[oc, col] == np.float32(want)
+
+
+def test_allocate_group_bits_oracle():
+    """f-3: the most important of every 4 groups gets the pooled 4-bit slot; ties -> lowest index;
+    with uniform importance the mask differs from the positional recipe only in which slot is 4-bit."""
+    rng = np.random.default_rng(0)
+    W = (rng.standard_normal((32, 256)) * 0.02).astype(np.float16)
+    W[:, 16:32] *= 8                       # block 0: group 1 salient
+    W[:, 64 + 32:64 + 48] *= 8             # block 1: group 2 salient
+    gb, imp = O.allocate_group_bits(W)
+    assert gb.reshape(-1, 4)[0].tolist() == [2, O.POOL | 4, 2, 2]
+    assert gb.reshape(-1, 4)[1].tolist() == [2, 2, O.POOL | 4, 2]
+    assert (gb == (O.POOL | 4)).sum() == 256 // 64 and imp.shape == (16,)
+    # activation statistics can override the weight magnitudes
+    sr = np.ones(256, np.float32)
+    sr[0:16] = 1e4
+    gb2, _ = O.allocate_group_bits(W, sr)
+    assert gb2.reshape(-1, 4)[0].tolist() == [O.POOL | 4, 2, 2, 2]
+    # ties
+    Wc = np.full((16, 64), 0.5, np.float16)
+    assert O.allocate_group_bits(Wc)[0].tolist() == [O.POOL | 4, 2, 2, 2]
+    # the mask is a valid recipe for the fake quantizer and lowers the error on the salient columns
+    x = W.astype(np.float32)
+    e_pos = np.abs(O.fakequant_fwd(x, "fp32", 2) - x)[:, 16:32].mean()
+    e_imp = np.abs(O.fakequant_fwd(x, "fp32", 2, group_bits=gb) - x)[:, 16:32].mean()
+    assert e_imp < e_pos
