@@ -14,7 +14,7 @@ from mxq_b200 import ops  # noqa: E402
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 which = sys.argv[1:] or ["fq", "ste", "act", "ptq", "pack", "gemv", "stats", "gemm"]
-REP = 3
+REP = int(os.environ.get("MXQ_PROF_REP", "3"))
 
 if "fq" in which:
     for dt in (torch.float32, torch.bfloat16):
