@@ -476,7 +476,7 @@ def run_qat(args):
                 "config": {"workload": "LLM-QAT run_train.sh 2 32 32 step (KD vs frozen teacher, AdamW, gradient checkpointing)",
                            "model": f"Llama-2-7B architecture, {layers} layers, random init", "per_gpu_batch": B, "seq_len": T,
                            "parallelism": f"dp{world}", "quantized_linears": nq},
-                "roofline": {"bound": "hbm", "kernel": "fakequant_fwd_kernel<bf16> x2 + ste_bwd_kernel<bf16> over all quantized weights",
+                "roofline": {"bound": "hbm", "kernel": "fakequant_row_kernel<bf16> x2 + ste_bwd_kernel<bf16> over all quantized weights",
                              "achieved": fq_bytes / (fq_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                              "frac": fq_bytes / (fq_ms * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
                              "ms_per_step": fq_ms, "share_of_step": fq_ms / ms},
@@ -632,6 +632,26 @@ def run_components(torch, dev, pk):
                                  "launches": nl * len(shapes), "note": "CUDA graph of 56 GEMVs, 0.6 GB of packed weights"}
     except Exception as e:
         out["gemv_decode_b1"] = {"error": repr(e)[:200]}
+    # same 8 layers with the linears that share an input grouped per launch: q/k/v, o, gate/up, down
+    def gemv_grouped_all():
+        for layer in packs:
+            ops.gemv_grouped(xin[4096], layer[0:3], outs=yq, validate=False)
+            ops.gemv(xin[4096], layer[3], out=yout[4096], validate=False)
+            ops.gemv_grouped(xin[4096], layer[4:6], outs=yg, validate=False)
+            ops.gemv(xin[11008], layer[6], out=yout[4096], validate=False)
+    try:
+        yq = [torch.empty(1, 4096, device=dev, dtype=torch.float16) for _ in range(3)]
+        yg = [torch.empty(1, 11008, device=dev, dtype=torch.float16) for _ in range(2)]
+        gemv_grouped_all()
+        torch.cuda.synchronize()
+        graph2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph2):
+            gemv_grouped_all()
+        ms = timeit(lambda i: graph2.replay(), 20)
+        out["gemv_decode_b1_grouped"] = {"ms_per_8_layers": ms, "GBps": gbytes / ms / 1e6, "frac_hbm": gbytes / ms / 1e6 / pk["hbm"],
+                                         "launches": nl * 4, "note": "q/k/v and gate/up share their input: one grouped launch each (mxq_gemv_grouped)"}
+    except Exception as e:
+        out["gemv_decode_b1_grouped"] = {"error": repr(e)[:200]}
     # config 2: prefill dequant-GEMM, M = 2048
     try:
         M = 2048

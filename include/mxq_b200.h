@@ -177,6 +177,13 @@ MXQ_API int mxq_gemv(const void* x, mxq_packed_t w, void* y, int64_t B, int64_t 
 MXQ_API int mxq_gemv_ex(const void* x, mxq_packed_t w, void* y, int64_t B, int64_t IC, int64_t OC,
                         unsigned flags, void* stream);
 
+/* Grouped decode GEMV (extension): up to 4 packed linears of the SAME [OC, IC] that share the
+ * activation x -- q/k/v, gate/up of a decoder layer -- in one launch: y[i] = x @ dequant(w[i])^T.
+ * `w` and `y` are HOST arrays of n entries.  One launch pays the fixed latencies (prologue,
+ * activation staging, first weight fill) once per group instead of once per linear. */
+MXQ_API int mxq_gemv_grouped(const void* x, const mxq_packed_t* w, void* const* y, int n, int64_t B,
+                             int64_t IC, int64_t OC, unsigned flags, void* stream);
+
 /* ---- (a-10) gemv_forward_cuda (AWQ uniform 4-bit)   gemv_cuda.cu:346-399, gemv_cuda.h:4-9 ------
  * kernel int32[OC, IC/8] (nibble j of word i = column 8i+j), zeros int32[OC, zw] (nibble g%8 of
  * word g/8, g = col/G), scales fp16[OC, zw*8]; zw = ceil(IC/G/8) rounded up to 1/2/4 words for

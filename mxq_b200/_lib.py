@@ -25,7 +25,7 @@ SYMBOLS = [
     "mxq_colsumsq_workspace_bytes", "mxq_colsumsq", "mxq_wanda_metric",
     "mxq_allocate_bits_workspace_bytes", "mxq_allocate_bits",
     "mxq_ptq_workspace_bytes", "mxq_ptq_quant", "mxq_rowquant",
-    "mxq_pack_workspace_bytes", "mxq_pack", "mxq_ptq_quant_pack", "mxq_unpack", "mxq_gemv", "mxq_gemv_ex", "mxq_awq_gemv",
+    "mxq_pack_workspace_bytes", "mxq_pack", "mxq_ptq_quant_pack", "mxq_unpack", "mxq_gemv", "mxq_gemv_ex", "mxq_gemv_grouped", "mxq_awq_gemv",
     "mxq_gemm_workspace_bytes", "mxq_gemm", "mxq_gemm_scatter", "mxq_gemm_dense",
 ]
 
@@ -76,6 +76,7 @@ def lib() -> C.CDLL:
     L.mxq_unpack.argtypes = [PackedC, i64, i64, vp, i32, vp]
     L.mxq_gemv.argtypes = [vp, PackedC, vp, i64, i64, i64, vp]
     L.mxq_gemv_ex.argtypes = [vp, PackedC, vp, i64, i64, i64, C.c_uint, vp]
+    L.mxq_gemv_grouped.argtypes = [vp, C.POINTER(PackedC), C.POINTER(vp), i32, i64, i64, i64, C.c_uint, vp]
     L.mxq_awq_gemv.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i32, vp]
     L.mxq_gemm_workspace_bytes.restype = sz
     L.mxq_gemm_workspace_bytes.argtypes = [i64, i64, i64]

@@ -373,6 +373,18 @@ struct GemvPlan {
 
 constexpr int kGemvMaxWarps = 16, kGemvMaxStages = 4;
 
+// Up to kGemvMaxGroup linears of one shape that share the activation vector (q/k/v, gate/up) run
+// as ONE launch: the grid is split evenly between them, every CTA stages x once and walks a longer
+// row range, so the fixed latencies of a launch (prologue, activation staging, first fill) are paid
+// once per group instead of once per linear.  n == 1 is the plain GEMV.
+constexpr int kGemvMaxGroup = 4;
+struct GemvGroup {
+  mxq_packed_t w[kGemvMaxGroup];
+  __half* y[kGemvMaxGroup];
+  int n;       // linears in the launch
+  int gxl;     // CTAs per linear (gridDim.x = n * gxl)
+};
+
 // Profiling only (MXQ_GEMV_DBG & 8): per-CTA %globaltimer stamps {start, waited, staged, done}.
 __device__ unsigned long long g_gemv_trace[4 * 160];
 __device__ __forceinline__ unsigned long long gtimer_ns() {
@@ -386,8 +398,12 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 // Dynamic shared memory: [nstages][stage] weight ring, then the activation image (gemv_block).
 template <int NB>
 __global__ void __launch_bounds__(NB == 1 ? 512 : 256, 1) gemv_mxq_kernel(
-    const __half* __restrict__ x, mxq_packed_t w, __half* __restrict__ y, int B, int IC, int OC,
+    const __half* __restrict__ x, const __grid_constant__ GemvGroup G, int B, int IC, int OC,
     GemvPlan plan) {
+  const int li = blockIdx.x / G.gxl;                     // which linear of the group (CTA-uniform)
+  const int cta = blockIdx.x - li * G.gxl;
+  const mxq_packed_t w = G.w[li];
+  __half* __restrict__ y = G.y[li];
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ float red[2][kGemvMaxWarps][4][NB];
   __shared__ uint64_t full[kGemvMaxStages];
@@ -395,7 +411,7 @@ __global__ void __launch_bounds__(NB == 1 ? 512 : 256, 1) gemv_mxq_kernel(
   const int nblk = IC >> 6;
   const int nchunk = (nblk + 63) >> 6;
   const int ngrp_all = OC >> 2;
-  const int grp_base = blockIdx.x * plan.q;
+  const int grp_base = cta * plan.q;
   const int qc = min(plan.q, ngrp_all - grp_base);      // row groups of this CTA
   const int rounds = (qc + plan.rpr - 1) / plan.rpr;     // <= plan.rounds (the last CTA may be short)
   const int rgl = warp / plan.wpr, sl0 = warp - rgl * plan.wpr;
@@ -620,19 +636,23 @@ namespace {
 constexpr size_t kSmemPerSM = 227 * 1024, kSmemCtaReserve = 4096;   // static smem + per-CTA reserve
 
 template <int NB>
-int launch_gemv(const __half* x, const mxq_packed_t& w, __half* y, int B, int IC, int OC,
+int launch_gemv(const __half* x, const mxq_packed_t* ws, void* const* ys, int n, int B, int IC, int OC,
                 bool pdl, cudaStream_t st) {
   constexpr int kMaxWarps = NB == 1 ? kGemvMaxWarps : 8;
   const int nblk = IC / 64, ngrp = OC / 4, nchunk = (nblk + 63) / 64;
   const size_t ximg = (size_t)NB * nblk * (kXBlkBytes + 32);
   GemvPlan plan;
-  plan.q = (int)ceil_div(ngrp, kNumSMs);
+  const int cpl = kNumSMs / n;                            // CTAs per linear
+  plan.q = (int)ceil_div(ngrp, cpl);
   plan.ksl = (int)ceil_div(nblk, 32);
   plan.dbg = 0;
   if (const char* e = getenv("MXQ_GEMV_DBG")) plan.dbg = atoi(e);
   // Choose (warps, warps per row group, ring depth).  Cost = sequential units per warp
   // (rounds x slices), +30 % if two CTAs cannot share an SM (no overlap with the next GEMV under
   // PDL), +15 % unless the ring holds the whole CTA share or >= 2 stages and 64 KB; ties -> fewer warps.
+  // (A latency model fitted to same-shape chains -- 8 warps so that two generations fit in the
+  // register file -- won 13 % on 4096^2 alone but lost 17 % on the mixed-shape decode chain of
+  // bench.py: profiles/sweep_gemv_grouped.py, profiles/README.md.)
   int W = 0, force_w = 0, force_wpr = 0, force_s = 0;
   if (const char* e = getenv("MXQ_GEMV_WARPS")) force_w = atoi(e);    // tuning knobs
   if (const char* e = getenv("MXQ_GEMV_WPR")) force_wpr = atoi(e);
@@ -665,7 +685,11 @@ int launch_gemv(const __half* x, const mxq_packed_t& w, __half* y, int B, int IC
   plan.rpr = W / plan.wpr;
   plan.rounds = (int)ceil_div(plan.q, plan.rpr);
   plan.spw = (int)ceil_div(plan.ksl, plan.wpr);
-  const unsigned gx = (unsigned)ceil_div(ngrp, plan.q);
+  GemvGroup G{};
+  G.n = n;
+  G.gxl = (int)ceil_div(ngrp, plan.q);
+  for (int i = 0; i < n; ++i) { G.w[i] = ws[i]; G.y[i] = (__half*)ys[i]; }
+  const unsigned gx = (unsigned)(n * G.gxl);
   const unsigned gy = (unsigned)ceil_div(B, NB);
   const size_t smem = smem_best;
   if (getenv("MXQ_GEMV_VERBOSE"))
@@ -686,31 +710,45 @@ int launch_gemv(const __half* x, const mxq_packed_t& w, __half* y, int B, int IC
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemv_mxq_kernel<NB>, x, w, y, B, IC, OC, plan);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemv_mxq_kernel<NB>, x, G, B, IC, OC, plan);
   return e == cudaSuccess ? MXQ_OK : (int)e;
 }
 
 }  // namespace
 
-extern "C" int mxq_gemv_ex(const void* x, mxq_packed_t w, void* y, int64_t B, int64_t IC,
-                           int64_t OC, unsigned flags, void* stream) {
-  if (B < 0 || IC < 0 || OC < 0) return MXQ_E_SHAPE;
-  if (B == 0 || OC == 0) return MXQ_OK;
-  MXQ_CHECK_PTR(x);
-  MXQ_CHECK_PTR(y);
+static int gemv_check_packed(const mxq_packed_t& w) {
   MXQ_CHECK_PTR(w.weight);
   if (!w.weight_last || !w.zeros_and_scales || !w.zeros_2nd || !w.scales_2nd || !w.scales_4b ||
       !w.zeros_4b)
     return MXQ_E_NULL;
+  return MXQ_OK;
+}
+
+extern "C" int mxq_gemv_grouped(const void* x, const mxq_packed_t* w, void* const* y, int n, int64_t B,
+                                int64_t IC, int64_t OC, unsigned flags, void* stream) {
+  if (B < 0 || IC < 0 || OC < 0 || n < 0 || n > kGemvMaxGroup) return MXQ_E_SHAPE;
+  if (B == 0 || OC == 0 || n == 0) return MXQ_OK;
+  MXQ_CHECK_PTR(x);
+  if (!w || !y) return MXQ_E_NULL;
+  for (int i = 0; i < n; ++i) {
+    MXQ_CHECK_PTR(y[i]);
+    const int rc = gemv_check_packed(w[i]);
+    if (rc) return rc;
+  }
   if (IC % 64 || OC % 8 || IC == 0 || IC > (1 << 24) || OC > INT32_MAX || B > 65535 * 4)
     return MXQ_E_SHAPE;
   cudaStream_t st = as_stream(stream);
   const __half* xh = (const __half*)x;
-  __half* yh = (__half*)y;
   const bool pdl = !(flags & MXQ_GEMV_NO_PDL);
-  if (B == 1) return launch_gemv<1>(xh, w, yh, (int)B, (int)IC, (int)OC, pdl, st);
-  if (B == 2) return launch_gemv<2>(xh, w, yh, (int)B, (int)IC, (int)OC, pdl, st);
-  return launch_gemv<4>(xh, w, yh, (int)B, (int)IC, (int)OC, pdl, st);
+  if (B == 1) return launch_gemv<1>(xh, w, y, n, (int)B, (int)IC, (int)OC, pdl, st);
+  if (B == 2) return launch_gemv<2>(xh, w, y, n, (int)B, (int)IC, (int)OC, pdl, st);
+  return launch_gemv<4>(xh, w, y, n, (int)B, (int)IC, (int)OC, pdl, st);
+}
+
+extern "C" int mxq_gemv_ex(const void* x, mxq_packed_t w, void* y, int64_t B, int64_t IC,
+                           int64_t OC, unsigned flags, void* stream) {
+  void* ys[1] = {y};
+  return mxq_gemv_grouped(x, &w, ys, 1, B, IC, OC, flags, stream);
 }
 
 // profiling aid, not part of the documented surface: copies the stamps of the last traced launch

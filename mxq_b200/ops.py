@@ -293,6 +293,30 @@ def gemv(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, validate: bo
     return out
 
 
+def gemv_grouped(x: torch.Tensor, ps: list, outs: list | None = None, pdl: bool = True, validate: bool = True):
+    """Decode GEMV of up to 4 packed linears of one shape sharing the activation x (q/k/v, gate/up)
+    in ONE launch.  Returns the list of fp16 [B, OC] outputs."""
+    import ctypes as C
+    if not 1 <= len(ps) <= 4:
+        raise ValueError("gemv_grouped takes 1..4 packed linears")
+    dims = [(_check_packed(p) if validate else _packed_dims(p)) for p in ps]
+    if len(set(dims)) != 1:
+        raise ValueError("all linears of a group must have the same [OC, IC]")
+    OC, IC = dims[0]
+    L.require_cuda(x)
+    if x.dtype != torch.float16 or x.dim() != 2 or x.shape[1] != IC:
+        raise ValueError(f"x must be fp16 [B, {IC}]")
+    x = x.contiguous()
+    B = x.shape[0]
+    if outs is None:
+        outs = [torch.empty((B, OC), dtype=torch.float16, device=x.device) for _ in ps]
+    warr = (L.PackedC * len(ps))(*[L.packed_struct(p) for p in ps])
+    yarr = (C.c_void_p * len(ps))(*[o.data_ptr() for o in outs])
+    rc = L.lib().mxq_gemv_grouped(L.ptr(x), warr, yarr, len(ps), B, IC, OC, 0 if pdl else 1, L.stream())
+    L.check(rc, "mxq_gemv_grouped")
+    return outs
+
+
 def gemm(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, workspace=None,
          validate: bool = True):
     """Prefill: y[M, OC] = x[M, IC] @ dequant(W)^T on tcgen05/TMEM, fp16 in/out, fp32 accumulate."""

@@ -177,3 +177,24 @@ def test_matches_reference_cuda_kernel(cuda):
     assert y.shape == y_ref.shape
     err = (y.float() - y_ref.float()).abs().max() / y_ref.float().abs().max()
     assert float(err) <= TOL
+
+
+@pytest.mark.parametrize("OC,IC,n,B", [(4096, 4096, 3, 1), (11008, 4096, 2, 1), (512, 1024, 4, 2), (1192, 64, 3, 1),
+                                       (4096, 4096, 2, 4), (64, 11008, 3, 1)])
+def test_gemv_grouped_shared_activation(cuda, OC, IC, n, B):
+    """Grouped decode GEMV (q/k/v, gate/up in one launch) equals the oracle for every member and
+    the per-linear GEMV up to the order of the K-slice reduction."""
+    from mxq_b200 import ops
+    ps = [O.random_packed(OC, IC, seed=OC + IC + 17 * i) for i in range(n)]
+    x = np.random.default_rng(B + n).standard_normal((B, IC)).astype(np.float16)
+    xd = torch.from_numpy(x).to(cuda)
+    pd = [packed_to_dev(p, cuda) for p in ps]
+    ys = ops.gemv_grouped(xd, pd)
+    assert len(ys) == n
+    for p, pdev, y in zip(ps, pd, ys):
+        ref = O.gemm_mxq_f32(x, p)
+        assert _rel_err(y.cpu().numpy(), ref) <= TOL
+        single = ops.gemv(xd, pdev).float()
+        assert float((y.float() - single).abs().max()) <= 2e-3 * float(np.abs(ref).max())
+    with pytest.raises(ValueError):
+        ops.gemv_grouped(xd, pd + [packed_to_dev(O.random_packed(OC + 8, IC, seed=1), cuda)][:1] if n < 4 else pd * 2)
