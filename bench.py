@@ -124,6 +124,7 @@ def workload_config(n):
                         "synthetic 128x2048-token calibration per distinct linear input",
             "hidden": HIDDEN, "intermediate": INTER, "layers": LAYERS, "nsamples": NSAMPLES, "seqlen": SEQLEN,
             "sharding": f"layer % {n} (no data-path collective)",
+            "schedule": "statistics of layer i+1 on the main stream overlap quantize+pack of layer i on a side stream",
             "l2": "inputs larger than L2: 12.2 GB of calibration activations + 0.4 GB of weights stream per layer"}
 
 
@@ -137,6 +138,7 @@ def main():
     ap.add_argument("--workload", default="ptq", choices=["ptq", "gemm70b", "qat"])
     ap.add_argument("--no-components", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="one stream: statistics then quantize, layer by layer")
     ap.add_argument("--layers", type=int, default=LAYERS, help="(debug) fewer layers; default is the named config")
     ap.add_argument("--nsamples", type=int, default=NSAMPLES, help="(debug) fewer calibration samples")
     args = ap.parse_args()
@@ -218,8 +220,13 @@ def main():
             cursor["i"] += 1
 
     def step():
-        for l in my_layers:
-            ptq.run(weights[l], calib, args.nsamples, on_stat=on_stat)
+        if args.serial:
+            for l in my_layers:
+                ptq.run(weights[l], calib, args.nsamples, on_stat=on_stat)
+        else:
+            # statistics of layer i+1 (HBM-bound) overlap quantize+pack of layer i (issue-bound)
+            ptq.run_pipelined(((weights[l], calib) for l in my_layers), args.nsamples, on_stat=on_stat,
+                              ctas_per_sm=int(os.environ.get("MXQ_STAT_CTAS", "8")))
 
     for _ in range(args.warmup):
         step()

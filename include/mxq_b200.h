@@ -90,6 +90,13 @@ MXQ_API int mxq_colsumsq(const void* X, int64_t tokens, int64_t cols, int dtype,
                  float prev_scale, float add_scale, int accumulate, void* workspace,
                  size_t workspace_bytes, void* stream);
 
+/* Same with an occupancy cap: at most ctas_per_sm (1..8) CTAs of the streaming kernel per SM, so a
+ * compute-bound kernel on another stream (the previous layer's quantize+pack) can share the SMs
+ * while this one saturates HBM.  ctas_per_sm = 8 is mxq_colsumsq.  Same workspace size. */
+MXQ_API int mxq_colsumsq_ex(const void* X, int64_t tokens, int64_t cols, int dtype, float* out,
+                    float prev_scale, float add_scale, int accumulate, int ctas_per_sm, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 /* Wanda metric |W| * sqrt(scaler_row)   mxq_quant/lib/prune.py:177.   W: dtype [rows, cols],
  * scaler_row: fp32[cols], out: fp32 [rows, cols]. */
 MXQ_API int mxq_wanda_metric(const void* W, const float* scaler_row, float* out, int64_t rows,

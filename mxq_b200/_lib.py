@@ -22,7 +22,7 @@ _DTYPE = {torch.float32: MXQ_F32, torch.float16: MXQ_F16, torch.bfloat16: MXQ_BF
 SYMBOLS = [
     "mxq_version", "mxq_error_string", "mxq_fakequant_fwd", "mxq_ste_bwd",
     "mxq_segquant_workspace_bytes", "mxq_segquant_fwd",
-    "mxq_colsumsq_workspace_bytes", "mxq_colsumsq", "mxq_wanda_metric",
+    "mxq_colsumsq_workspace_bytes", "mxq_colsumsq", "mxq_colsumsq_ex", "mxq_wanda_metric",
     "mxq_allocate_bits_workspace_bytes", "mxq_allocate_bits",
     "mxq_ptq_workspace_bytes", "mxq_ptq_quant", "mxq_rowquant",
     "mxq_pack_workspace_bytes", "mxq_pack", "mxq_ptq_quant_pack", "mxq_unpack", "mxq_gemv", "mxq_gemv_ex", "mxq_gemv_grouped", "mxq_awq_gemv",
@@ -61,6 +61,7 @@ def lib() -> C.CDLL:
     L.mxq_colsumsq_workspace_bytes.restype = sz
     L.mxq_colsumsq_workspace_bytes.argtypes = [i64, i64]
     L.mxq_colsumsq.argtypes = [vp, i64, i64, i32, vp, f32, f32, i32, vp, sz, vp]
+    L.mxq_colsumsq_ex.argtypes = [vp, i64, i64, i32, vp, f32, f32, i32, i32, vp, sz, vp]
     L.mxq_wanda_metric.argtypes = [vp, vp, vp, i64, i64, i32, vp]
     L.mxq_allocate_bits_workspace_bytes.restype = sz
     L.mxq_allocate_bits_workspace_bytes.argtypes = [i64]

@@ -155,9 +155,9 @@ __global__ void alloc_bits_kernel(const unsigned long long* __restrict__ colabs,
   for (int k = 0; k < 4; ++k) group_bits[blk * 4 + k] = (uint8_t)(k == arg ? (MXQ_POOL_FLAG | 4) : low_bits);
 }
 
-static int slabs_for(int64_t tokens, int cpr) {
+static int slabs_for(int64_t tokens, int cpr, int ctas_per_sm = 8) {
   const int col_tiles = (int)ceil_div(cpr, kCSThreads);
-  int slabs = (kNumSMs * 8) / col_tiles;  // ~8 CTAs of 256 threads per SM
+  int slabs = (kNumSMs * ctas_per_sm) / col_tiles;  // ~8 CTAs of 256 threads per SM (one wave)
   if (slabs < 1) slabs = 1;
   const int64_t max_slabs = ceil_div(tokens, 64);
   if (slabs > max_slabs) slabs = (int)(max_slabs > 0 ? max_slabs : 1);
@@ -171,13 +171,19 @@ using namespace mxq;
 extern "C" size_t mxq_colsumsq_workspace_bytes(int64_t tokens, int64_t cols) {
   if (tokens <= 0 || cols <= 0) return 16;
   const int cpr_min = (int)(cols / 8) > 0 ? (int)(cols / 8) : 1;  // fp32 has more chunks -> fewer slabs
-  return (size_t)slabs_for(tokens, cpr_min) * (size_t)cols * sizeof(float) + 16;
+  // sized for the largest slab count mxq_colsumsq_ex may use (ctas_per_sm = 32)
+  return (size_t)slabs_for(tokens, cpr_min, 32) * (size_t)cols * sizeof(float) + 16;
 }
 
-extern "C" int mxq_colsumsq(const void* X, int64_t tokens, int64_t cols, int dtype, float* out,
-                            float prev_scale, float add_scale, int accumulate, void* workspace,
-                            size_t workspace_bytes, void* stream) {
-  if (tokens < 0 || cols <= 0) return MXQ_E_SHAPE;
+// ctas_per_sm: CTAs of the partial kernel per SM.  8 (= mxq_colsumsq) is one full wave.  Smaller
+// values are enforced with an unused dynamic shared-memory reservation and leave registers / thread
+// slots free; larger values (up to 32) split the rows into more, shorter slabs = several waves, so
+// CTAs retire continuously and a concurrent kernel on another (higher-priority) stream -- the PTQ
+// tile kernel of the previous layer -- keeps getting SM slots.
+extern "C" int mxq_colsumsq_ex(const void* X, int64_t tokens, int64_t cols, int dtype, float* out,
+                               float prev_scale, float add_scale, int accumulate, int ctas_per_sm,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  if (tokens < 0 || cols <= 0 || ctas_per_sm < 1 || ctas_per_sm > 32) return MXQ_E_SHAPE;
   MXQ_CHECK_PTR(out);
   if (dtype != MXQ_F32 && dtype != MXQ_F16 && dtype != MXQ_BF16) return MXQ_E_DTYPE;
   const int esize = dtype == MXQ_F32 ? 4 : 2;
@@ -188,23 +194,39 @@ extern "C" int mxq_colsumsq(const void* X, int64_t tokens, int64_t cols, int dty
   if (tokens > 0) {
     MXQ_CHECK_PTR(X);
     MXQ_CHECK_PTR(workspace);
-    slabs = slabs_for(tokens, cpr);
+    slabs = slabs_for(tokens, cpr, ctas_per_sm);
     if (workspace_bytes < (size_t)slabs * cols * sizeof(float)) return MXQ_E_WORKSPACE;
     const int rows_per_slab = (int)ceil_div(tokens, slabs);
     slabs = (int)ceil_div(tokens, rows_per_slab);
     dim3 grid((unsigned)ceil_div(cpr, kCSThreads), (unsigned)slabs);
     float* part = (float*)workspace;
     const uint8_t* Xb = (const uint8_t*)X;
-    if (dtype == MXQ_F32)
-      colsumsq_partial_kernel<float><<<grid, kCSThreads, 0, st>>>(Xb, part, tokens, (int)cols, cpr, rows_per_slab);
-    else if (dtype == MXQ_F16)
-      colsumsq_partial_kernel<__half><<<grid, kCSThreads, 0, st>>>(Xb, part, tokens, (int)cols, cpr, rows_per_slab);
-    else
-      colsumsq_partial_kernel<__nv_bfloat16><<<grid, kCSThreads, 0, st>>>(Xb, part, tokens, (int)cols, cpr, rows_per_slab);
+    // n CTAs per SM: n * (pad + 1 KB) <= 228 KB < (n + 1) * (pad + 1 KB)
+    size_t pad = 0;
+    if (ctas_per_sm < 8) pad = ((size_t)233472 / ctas_per_sm - 1024) & ~(size_t)1023;
+    auto launch = [&](auto kern) -> cudaError_t {
+      if (pad > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+        if (e != cudaSuccess) return e;
+      }
+      kern<<<grid, kCSThreads, pad, st>>>(Xb, part, tokens, (int)cols, cpr, rows_per_slab);
+      return cudaSuccess;
+    };
+    cudaError_t e = dtype == MXQ_F32   ? launch(colsumsq_partial_kernel<float>)
+                    : dtype == MXQ_F16 ? launch(colsumsq_partial_kernel<__half>)
+                                       : launch(colsumsq_partial_kernel<__nv_bfloat16>);
+    if (e != cudaSuccess) return (int)e;
   }
   colsumsq_final_kernel<<<(unsigned)ceil_div(cols, 32), dim3(32, 32), 0, st>>>(
       (const float*)workspace, out, (int)cols, slabs, prev_scale, add_scale, accumulate);
   MXQ_LAUNCH_RESULT();
+}
+
+extern "C" int mxq_colsumsq(const void* X, int64_t tokens, int64_t cols, int dtype, float* out,
+                            float prev_scale, float add_scale, int accumulate, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  return mxq_colsumsq_ex(X, tokens, cols, dtype, out, prev_scale, add_scale, accumulate, 8, workspace,
+                         workspace_bytes, stream);
 }
 
 extern "C" int mxq_wanda_metric(const void* W, const float* scaler_row, float* out, int64_t rows,

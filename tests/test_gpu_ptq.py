@@ -151,3 +151,50 @@ def test_allocate_group_bits_bit_exact(cuda, shape):
         out = ops.fakequant_fwd(W.to(cuda).float(), group_bits=gb)
         want = O.fakequant_fwd(W.float().numpy(), "fp32", 2, group_bits=want_gb)
         assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+def test_pipelined_layers_equal_serial(cuda):
+    """LlamaLayerPTQ.run_pipelined (statistics of layer i+1 on the current stream, capped at 5 CTAs per
+    SM, overlapping quantize+pack of layer i on a side stream) == run() layer by layer, bit for bit,
+    including the double-buffered statistics (dead column differs per layer)."""
+    from mxq_b200 import prune
+    hidden, inter, tokens, nl = 256, 512, 1024, 5
+    ptq = prune.LlamaLayerPTQ(hidden, inter, cuda, tokens)
+    lin = prune.llama_linears(hidden, inter)
+    g = torch.Generator(device=cuda).manual_seed(0)
+    layers = []
+    for l in range(nl):
+        calib = {}
+        for key, d in (("attn_in", hidden), ("o_in", hidden), ("mlp_in", hidden), ("down_in", inter)):
+            X = torch.randn((tokens, d), generator=g, device=cuda, dtype=torch.float16)
+            X[:, 3 + l] = 0
+            calib[key] = X
+        weights = {name: (torch.randn((oc, ic), generator=g, device=cuda) * 0.02).half() for name, (oc, ic, _) in lin.items()}
+        layers.append((weights, calib))
+
+    def collect(runner):
+        got = []
+        def sink(name, Wq, packed):
+            got.append((name, Wq.clone(), {k: v.clone() for k, v in packed.items()}))
+        runner(sink)
+        torch.cuda.synchronize()
+        return got
+
+    serial = collect(lambda sink: [ptq.run(w, c, 8, sink=sink) for w, c in layers])
+    piped = collect(lambda sink: ptq.run_pipelined(layers, 8, sink=sink))
+    assert len(serial) == len(piped) == nl * 7
+    for (n0, w0, p0), (n1, w1, p1) in zip(serial, piped):
+        assert n0 == n1 and torch.equal(w0, w1)
+        for k in p0:
+            assert torch.equal(p0[k], p1[k]), (n0, k)
+    # the occupancy-capped statistics kernel gives the same sums as the default one
+    X = layers[0][1]["down_in"]
+    from mxq_b200 import ops
+    ref = ops.colsumsq(X)
+    for ctas in (1, 3, 5, 7):
+        out = torch.empty_like(ref)
+        ws = torch.empty(ops.L.lib().mxq_colsumsq_workspace_bytes(X.shape[0], X.shape[1]), dtype=torch.uint8, device=cuda)
+        rc = ops.L.lib().mxq_colsumsq_ex(X.data_ptr(), X.shape[0], X.shape[1], ops.L.MXQ_F16, out.data_ptr(), 0.0, 1.0, 0,
+                                         ctas, ws.data_ptr(), ws.numel(), ops.L.stream())
+        assert rc == 0
+        assert torch.allclose(out, ref, rtol=1e-5, atol=0)
