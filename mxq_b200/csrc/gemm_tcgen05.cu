@@ -221,21 +221,24 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_mxq_kernel(const __grid_const
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(128, BN);
+      const uint32_t desc_hi = (uint32_t)(make_smem_desc(0) >> 32);
+      const uint32_t a_lo0 = (smem_u32(smem_a) & 0x3FFFF) >> 4, b_lo0 = (smem_u32(smem_b) & 0x3FFFF) >> 4;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&full_a[s], ph);
         mbar_wait(&full_b[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem_a + s * A_STAGE_BYTES);
-        const uint32_t b_addr = smem_u32(smem_b + s * B_STAGE_BYTES);
+        // descriptors = {address >> 4 + immediate, constant high word}: the issuing thread shares
+        // its scheduler with dequantizer warps, its instruction count is on the critical path
+        const uint32_t a_lo = a_lo0 + s * (A_STAGE_BYTES >> 4), b_lo = b_lo0 + s * (B_STAGE_BYTES >> 4);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if ((p.dbg & 1) && h == 1) break;       // profiling: half the MMAs
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t ad = make_smem_desc(a_addr + h * (128 * BK * 2) + k * (UMMA_K * 2));
-            const uint64_t bd = make_smem_desc(b_addr + k * (UMMA_K * 2));
+            const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + ((h * (128 * BK * 2) + k * (UMMA_K * 2)) >> 4));
+            const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_lo + ((k * (UMMA_K * 2)) >> 4));
             umma_f16(tmem_base + h * BN, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
         }
