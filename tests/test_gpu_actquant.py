@@ -105,3 +105,29 @@ def test_argument_errors(cuda):
         ops.segquant_fwd(torch.randn(4, 8), "asym", 4, 4, 8)               # CPU tensor
     e = ops.segquant_fwd(torch.empty(0, 8, device=cuda), "asym", 4, 0, 8)
     assert e.numel() == 0
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("mode", ["sym", "asym"])
+def test_non_finite_inputs_follow_ieee(cuda, dtype, mode):
+    """inf / nan / huge / subnormal-tiny values take the guarded IEEE path and still equal the
+    op-by-op oracle (NaNs in the same places): 2-D groups and 3-D per-token segments."""
+    from mxq_b200 import AsymQuantizer, SymQuantizer
+    g = torch.Generator().manual_seed(11)
+    for shape in ((160, 256), (1, 160, 512)):
+        x = torch.randn(*shape, generator=g)
+        flat = x.view(-1, shape[-1])
+        flat[1, 3] = float("inf")
+        flat[2, 5] = float("-inf")
+        flat[3, 7] = float("nan")
+        flat[4, :] *= 1e30 if dtype != "fp16" else 6e3
+        flat[5, :] *= 1e-38 if dtype == "fp32" else 1e-7
+        flat[6, 0:8] = 0.0
+        xt = x.to(TD[dtype])
+        bits = 8 if mode == "sym" else 4
+        fn_o = O.sym_quant if mode == "sym" else O.asym_quant
+        with np.errstate(all="ignore"):
+            want = fn_o(xt.float().numpy(), dtype, bits, False)
+        fn = SymQuantizer if mode == "sym" else AsymQuantizer
+        got = fn.apply(xt.to(cuda), torch.tensor([-2.0, 2.0]), bits, False)
+        assert bits_equal(to_np(got), want), (mode, dtype, shape)
