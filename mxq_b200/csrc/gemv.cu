@@ -591,40 +591,91 @@ __device__ __forceinline__ float sum_halves(const uint32_t* x) {
 // ---------------------------------------------------------------------------------------------
 // AWQ uniform 4-bit GEMV (gemv_cuda.cu:45-242): kernel[OC, IC/8] (nibble j of word i = column
 // 8i+j), zeros[OC, zw] 4-bit per group (8 groups per word), scales fp16 [OC, zw*8]
-// w = scale * (q - zero).   One warp per output row, lanes stride over 16-byte weight chunks.
+// w = scale * (q - zero).
+// CTA = 8 warps x 2 rows.  The activation row is staged once per CTA in shared memory, chunk-
+// transposed (the j-th 16-byte piece of every 32-column chunk is contiguous, so a warp's LDS.128
+// is conflict-free), together with the fp32 sum of every chunk -- sum_j (16 + q_j - 16 - z) x_j =
+// sum_j (16 + q_j) x_j - (16 + z) * sum_j x_j needs the chunk sum once, not once per row.  A lane
+// owns 32-column chunks (one 128-bit weight load per row, 512 contiguous bytes per warp and row)
+// and keeps two chunks x two rows of loads in flight.
 // ---------------------------------------------------------------------------------------------
+constexpr int kAwqRows = 2;
 __global__ void __launch_bounds__(256) awq_gemv_kernel(const __half* __restrict__ x,
                                                        const uint32_t* __restrict__ kernel,
                                                        const __half* __restrict__ scales,
                                                        const uint32_t* __restrict__ zeros,
                                                        __half* __restrict__ y, int IC, int OC,
                                                        int G, int zw) {
-  const int lane = threadIdx.x & 31;
-  const int oc = blockIdx.x * 8 + (threadIdx.x >> 5);
+  extern __shared__ __align__(16) unsigned char awq_smem[];
+  const int nch = IC / 32;                                    // 32-column chunks
+  uint4* xs4 = reinterpret_cast<uint4*>(awq_smem);            // [4][nch]
+  float* xsum = reinterpret_cast<float*>(awq_smem + (size_t)nch * 64);   // [nch]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
-  if (oc >= OC) return;
-  const int ww = IC / 8;
-  float acc = 0.f;
-  for (int c = lane; c < ww / 4; c += 32) {  // 4 words = 32 columns per chunk
-    const uint4 wv = ld_stream(kernel + (size_t)oc * ww + (size_t)c * 4);
-    const int g = (c * 32) / G;
-    const uint32_t z = (zeros[(size_t)oc * zw + (g >> 3)] >> (4 * (g & 7))) & 0xF;
-    const float sc = __half2float(scales[(size_t)oc * zw * 8 + g]);
-    const float zb = __uint_as_float(0x41800000u + (z << 19));   // 16 + zero
+  for (int c = threadIdx.x; c < nch; c += 256) {
     const uint4* xp = reinterpret_cast<const uint4*>(x + (size_t)b * IC + (size_t)c * 32);
-    const uint32_t wd[4] = {wv.x, wv.y, wv.z, wv.w};
-    float p = 0.f, xs = 0.f;
+    float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint4 xv = __ldg(xp + i);
-      const uint32_t xr[4] = {xv.x, xv.y, xv.z, xv.w};
-      p = dot_word_4b(wd[i], xr, p);
-      xs += sum_halves<4>(xr);
+    for (int j = 0; j < 4; ++j) {
+      const uint4 v = __ldg(xp + j);
+      xs4[j * nch + c] = v;
+      const uint32_t xr[4] = {v.x, v.y, v.z, v.w};
+      sum += sum_halves<4>(xr);
     }
-    acc = fmaf(sc, fmaf(-zb, xs, p), acc);
+    xsum[c] = sum;
   }
-  acc = warp_sum(acc);
-  if (lane == 0) y[(size_t)b * OC + oc] = __float2half_rn(acc);
+  __syncthreads();
+  const int ww = IC / 8;
+  const int row0 = (blockIdx.x * 8 + warp) * kAwqRows;
+  float acc[kAwqRows];
+#pragma unroll
+  for (int i = 0; i < kAwqRows; ++i) acc[i] = 0.f;
+  auto chunk = [&](int c, const uint4* wv) {
+    uint32_t xr[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 v = xs4[j * nch + c];
+      xr[j][0] = v.x; xr[j][1] = v.y; xr[j][2] = v.z; xr[j][3] = v.w;
+    }
+    const float xsc = xsum[c];
+    const int g = (c * 32) / G;
+#pragma unroll
+    for (int i = 0; i < kAwqRows; ++i) {
+      const int oc = min(row0 + i, OC - 1);
+      const uint32_t z = (__ldg(zeros + (size_t)oc * zw + (g >> 3)) >> (4 * (g & 7))) & 0xF;
+      const float sc = __half2float(__ldg(scales + (size_t)oc * zw * 8 + g));
+      const float zb = __uint_as_float(0x41800000u + (z << 19));   // 16 + zero
+      const uint32_t wd[4] = {wv[i].x, wv[i].y, wv[i].z, wv[i].w};
+      float p = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) p = dot_word_4b(wd[j], xr[j], p);
+      acc[i] = fmaf(sc, fmaf(-zb, xsc, p), acc[i]);
+    }
+  };
+  int c = lane;
+  for (; c + 32 < nch; c += 64) {               // two chunks x two rows of weight loads in flight
+    uint4 w0[kAwqRows], w1[kAwqRows];
+#pragma unroll
+    for (int i = 0; i < kAwqRows; ++i) {
+      const size_t ro = (size_t)min(row0 + i, OC - 1) * ww;
+      w0[i] = ld_stream(kernel + ro + (size_t)c * 4);
+      w1[i] = ld_stream(kernel + ro + (size_t)(c + 32) * 4);
+    }
+    chunk(c, w0);
+    chunk(c + 32, w1);
+  }
+  for (; c < nch; c += 32) {
+    uint4 w0[kAwqRows];
+#pragma unroll
+    for (int i = 0; i < kAwqRows; ++i)
+      w0[i] = ld_stream(kernel + (size_t)min(row0 + i, OC - 1) * ww + (size_t)c * 4);
+    chunk(c, w0);
+  }
+#pragma unroll
+  for (int i = 0; i < kAwqRows; ++i) {
+    const float v = warp_sum(acc[i]);
+    if (lane == 0 && row0 + i < OC) y[(size_t)b * OC + row0 + i] = __float2half_rn(v);
+  }
 }
 
 }  // namespace mxq
@@ -778,7 +829,13 @@ extern "C" int mxq_awq_gemv(const void* x, const int32_t* kernel, const void* sc
   // g32 variant indexes scales/zeros inconsistently, :70-71, and is not reproduced).
   const int rnd = group_size == 128 ? 1 : (group_size == 64 ? 2 : 4);
   const int zw = (int)(ceil_div(ceil_div(IC / group_size, 8), rnd) * rnd);
-  awq_gemv_kernel<<<dim3((unsigned)ceil_div(OC, 8), (unsigned)B), 256, 0, as_stream(stream)>>>(
+  const size_t smem = (size_t)(IC / 32) * (64 + 4);
+  if (smem > 200 * 1024) return MXQ_E_SHAPE;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(awq_gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  awq_gemv_kernel<<<dim3((unsigned)ceil_div(OC, 8 * kAwqRows), (unsigned)B), 256, smem, as_stream(stream)>>>(
       (const __half*)x, (const uint32_t*)kernel, (const __half*)scales, (const uint32_t*)zeros,
       (__half*)y, (int)IC, (int)OC, group_size, zw);
   MXQ_LAUNCH_RESULT();
