@@ -354,7 +354,7 @@ def run_gemm70b(args):
         ocl = oc // world
         p = rand_packed(ocl, ic)
         x = torch.randn(M, ic, device=dev).half()
-        ws = torch.zeros(4096, dtype=torch.uint8, device=dev)
+        ws = ops.gemm_workspace(M, ic, ocl, dev)
         y = torch.empty(M, ocl, device=dev, dtype=torch.float16)
         flops = 2.0 * M * oc * ic
         r = {"flops": flops}
@@ -666,7 +666,7 @@ def run_components(torch, dev, pk):
         for (oc, ic), p in zip(shapes[3:6:2] + shapes[6:], (packs[0][3], packs[0][5], packs[0][6])):
             x = torch.randn(M, ic, device=dev).half()
             y = torch.empty(M, oc, device=dev, dtype=torch.float16)
-            ws = torch.zeros(4096, dtype=torch.uint8, device=dev)
+            ws = ops.gemm_workspace(M, ic, oc, dev)
             ms = timeit(lambda i: ops.gemm(x, p, out=y, workspace=ws, validate=False), 10)
             tf = 2.0 * M * oc * ic / ms / 1e9
             # same-shape dense fp16 comparator: cuBLAS through torch.matmul (library GEMM, no dequant)

@@ -201,8 +201,10 @@ MXQ_API int mxq_awq_gemv(const void* x, const int32_t* kernel, const void* scale
 /* ---- prefill: packed dequant-GEMM on tcgen05/TMEM (no reference kernel exists for the mixed
  * layout; gemm_cuda_gen.cu:424-478 is the un-built AWQ 4-bit analogue) --------------------------
  * y[m, oc] = sum_k x[m, k] * dequant(W)[oc, k]; x fp16 [M, IC], y fp16 [M, OC].
- * workspace: mxq_gemm_workspace_bytes(M, IC, OC) (TMA descriptors live in kernel params; the
- * workspace holds the tile scheduler counter). */
+ * workspace: mxq_gemm_workspace_bytes(M, IC, OC), uninitialised.  When the tiles (512 tokens x 256
+ * rows) do not fill a whole number of waves of SM pairs, the tiles of the last wave are cut along K
+ * and their fp32 partials meet in the workspace (a second small kernel adds them in a fixed order:
+ * results are reproducible).  A NULL or too small workspace is legal: whole tiles only. */
 MXQ_API size_t mxq_gemm_workspace_bytes(int64_t M, int64_t IC, int64_t OC);
 MXQ_API int mxq_gemm(const void* x, mxq_packed_t w, void* y, int64_t M, int64_t IC, int64_t OC,
              void* workspace, size_t workspace_bytes, void* stream);

@@ -158,6 +158,11 @@ struct Params {
   int M, IC, OC;
   int dbg;                   // profiling only (MXQ_GEMM_DBG): 1 = one M half, 2 = no TMA after the first ring fill
   unsigned long long* dbg_host;   // debugging only (MXQ_GEMM_DBG_PTR): pinned host memory for watchdog records
+  // CTA-pair kernel tile schedule (pair::Plan): clusters [0, full) compute one whole 512 x 256 tile;
+  // the remaining tiles -- the ones that would form a partly filled last wave -- are cut into
+  // `split` K slices, one cluster each, reduced through fp32 partials in the workspace
+  int mt, full, split;
+  float4* partial;           // [tail tiles * split][2 ranks][8 * 8 * 256] float4, summed by gemm_split_reduce_kernel
 };
 
 template <bool kDenseB>
@@ -546,7 +551,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 __device__ __noinline__ void wd_record(unsigned long long* h, int site, int kb) {
   if (h) {
     const unsigned long long v = ((unsigned long long)site << 48) | ((unsigned long long)(kb & 0xFFFF) << 32) |
-                                 ((unsigned long long)(blockIdx.y & 0xFF) << 24) | ((unsigned long long)(blockIdx.x & 0xFF) << 16) |
+                                 ((unsigned long long)(blockIdx.x & 0xFFFF) << 16) |
                                  (threadIdx.x & 0xFFFF);
     const unsigned slot = atomicAdd((unsigned*)h, 1u);
     if (slot < 60) h[1 + slot] = v;
@@ -564,6 +569,53 @@ __device__ __forceinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, un
       const long long t1 = clock64();
       while (clock64() - t1 < 200000000LL) {}
       __trap();
+    }
+  }
+}
+
+// Second pass of the K-split tail tiles (Plan): the clusters that ran a K slice left their fp32
+// accumulators in the exchange buffer, thread-major -- 16-byte chunk c (columns 4 c .. 4 c + 3 of
+// the tile) of epilogue thread t at [c * 256 + t] of the CTA's slot -- so that both the writes of
+// the GEMM epilogue and the reads here are coalesced.  One thread adds the slices of 32 columns of
+// one token in slice order (deterministic) and stores 64 contiguous bytes of fp16.
+constexpr int SLOT_F4 = (BN / 4) * 256;                // float4 per CTA partial (256 KB)
+__global__ void __launch_bounds__(256) gemm_split_reduce_kernel(const float4* __restrict__ partial, __half* __restrict__ y,
+                                                                int split, int full, int mt, int M, int OC, int ldy,
+                                                                int col0) {
+  const int t = threadIdx.x;
+  const int cb = blockIdx.x & 7, rank = (blockIdx.x >> 3) & 1, tail = blockIdx.x >> 4;
+  const int tile = full + tail;
+  const int m0 = (2 * (tile % mt) + rank) * BM, n0 = (tile / mt) * BN;
+  // epilogue thread t = 32 * dw + lane of the GEMM: token half dw >> 2, TMEM lane quarter (dw + 2) & 3
+  const int dw = t >> 5, lane = t & 31;
+  const int token = m0 + (dw >> 2) * 128 + ((dw + 2) & 3) * 32 + lane;
+  const float4* src = partial + ((size_t)(tail * split) * 2 + rank) * SLOT_F4 + cb * 8 * 256 + t;
+  float4 acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = __ldcs(src + j * 256);
+  for (int sl = 1; sl < split; ++sl) {
+    src += 2 * SLOT_F4;
+    float4 f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = __ldcs(src + j * 256);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j].x += f[j].x; acc[j].y += f[j].y; acc[j].z += f[j].z; acc[j].w += f[j].w;
+    }
+  }
+  if (token < M) {
+    __half* dst = y + (size_t)token * ldy + col0 + n0 + cb * 32;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (n0 + cb * 32 + q * 8 + 8 <= OC) {
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+        oh[0] = __floats2half2_rn(acc[2 * q].x, acc[2 * q].y);
+        oh[1] = __floats2half2_rn(acc[2 * q].z, acc[2 * q].w);
+        oh[2] = __floats2half2_rn(acc[2 * q + 1].x, acc[2 * q + 1].y);
+        oh[3] = __floats2half2_rn(acc[2 * q + 1].z, acc[2 * q + 1].w);
+        *reinterpret_cast<uint4*>(dst + q * 8) = o;
+      }
     }
   }
 }
@@ -592,10 +644,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  // tile schedule: 1-D grid of clusters, M tile fastest (consecutive clusters share weight rows)
+  const int cid = blockIdx.x >> 1;
+  int tile = cid, slice = 0, kb_begin = 0, num_kb = p.IC / BK;
+  const bool partial = cid >= p.full;
+  if (partial) {
+    const int u = cid - p.full;
+    const int ng = num_kb >> 2;                    // split only when IC % 256 == 0
+    tile = p.full + u / p.split;
+    slice = u % p.split;
+    kb_begin = 4 * ((ng * slice) / p.split);
+    num_kb = 4 * ((ng * (slice + 1)) / p.split) - kb_begin;
+  }
+  const int m0 = (2 * (tile % p.mt) + (int)rank) * BM, n0 = (tile / p.mt) * BN;
   const int nrow0 = n0 + (int)rank * BNH;          // first weight row this CTA dequantizes
-  const int num_kb = p.IC / BK;
-  // K block kb is dequantized by set (kb >> 2) & 1 and is the (kb >> 3)-th block of that set in its
+  // K blocks are numbered locally (kb = 0 is global block kb_begin).  Local block kb is dequantized
+  // by set (kb >> 2) & 1 and is the (kb >> 3)-th block of that set in its
   // stage; its consumption completes phase (kb >> 3) of empty[set][kb % STAGES]
   const bool direct = !(p.dbg & 16);   // MXQ_GEMM_DBG=16: publish rank 1's half through the relay thread
   auto empty_of = [&](int kb) { return &empty[((kb >> 2) & 1) * STAGES + (kb % STAGES)]; };
@@ -634,9 +698,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
           mbar_arrive_expect_tx(&full_a[s], 2 * A_STAGE_BYTES);
           if (kDenseB) mbar_arrive_expect_tx(&full_b[s], 2 * B_STAGE_BYTES);
         }
-        tma_load_2d_pair(smem_a + s * A_STAGE_BYTES, &tmap_x, kb * BK, m0, smem_u32(&full_a[s]) & kPeerBitMask);
+        tma_load_2d_pair(smem_a + s * A_STAGE_BYTES, &tmap_x, (kb_begin + kb) * BK, m0, smem_u32(&full_a[s]) & kPeerBitMask);
         if (kDenseB)
-          tma_load_2d_pair(smem_b + s * B_STAGE_BYTES, &tmap_w, kb * BK, nrow0, smem_u32(&full_b[s]) & kPeerBitMask);
+          tma_load_2d_pair(smem_b + s * B_STAGE_BYTES, &tmap_w, (kb_begin + kb) * BK, nrow0, smem_u32(&full_b[s]) & kPeerBitMask);
       }
     }
   } else if (warp == 1) {
@@ -680,7 +744,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         umma2_commit_both(empty_of(kb));   // frees the stage in both CTAs
       }
       umma2_commit_both(tmem_full);        // accumulators of both CTAs complete
-      if (p.dbg_host && blockIdx.x == 0 && blockIdx.y == 0) {
+      if (p.dbg_host && blockIdx.x == 0) {
         volatile unsigned long long* hv = p.dbg_host;
         hv[61] = (unsigned long long)wait_a;
         hv[62] = (unsigned long long)wait_b;
@@ -706,7 +770,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
     if (!kDenseB) {
       const bool row_ok = oc < p.OC;
       const int ocs = row_ok ? oc : 0;
-      const int nblk = num_kb;
+      const int nblk = p.IC / BK;                   // blocks per weight row (num_kb of them are this cluster's)
       const int nchunk = (nblk + 63) >> 6;
       const uint4* wrow = reinterpret_cast<const uint4*>(p.w.weight + (size_t)ocs * nblk * 4);
       const int32_t* wlrow = p.w.weight_last + (size_t)ocs * nblk;
@@ -764,7 +828,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 
       if ((nblk & 3) == 0) {
         uint8_t* stg = stage_base + dw * (32 * STG_PITCH);
-        const int ngroups = nblk >> 2;
+        const int ngroups = num_kb >> 2;          // local groups; global group = g0 + g
+        const int g0 = kb_begin >> 2;
         const int q = lane & 3, r8 = lane >> 2;
         const uint4* wbase[4];
 #pragma unroll
@@ -779,7 +844,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         const uint2* s2v2 = reinterpret_cast<const uint2*>(s2row);
         uint4 pw[4], pwl, pzs, pz2;
         uint2 ps2[3];
-        auto fetch = [&](int g) {
+        auto fetch = [&](int gl) {
+          const int g = g0 + gl;
 #pragma unroll
           for (int i = 0; i < 4; ++i) pw[i] = __ldg(wbase[i] + 4 * g);
           pwl = __ldg(wl4 + g);
@@ -803,7 +869,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
           for (int kk = 0; kk < 4; ++kk) wq[kk] = *reinterpret_cast<const uint4*>(stg + lane * STG_PITCH + kk * 16);
           __syncwarp();
           if (g + 2 < ngroups && !(p.dbg & 64)) fetch(g + 2);   // dbg 64: profiling, reuse the first group's words
-          const int hsh = (((4 * g) & 63) >> 5) * 16;
+          const int hsh = (((4 * (g0 + g)) & 63) >> 5) * 16;
           const uint32_t wlw[4] = {cwl.x, cwl.y, cwl.z, cwl.w};
           const uint32_t zsv[4] = {czs.x, czs.y, czs.z, czs.w};
           const uint32_t z2v[4] = {cz2.x, cz2.y, cz2.z, cz2.w};
@@ -837,19 +903,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
         }
       }
     }
-    // ===== epilogue: TMEM -> registers -> fp16 -> global =====
+    // ===== epilogue: TMEM -> registers -> fp16 -> global (K slice: fp32 -> exchange buffer) =====
     mbar_wait_dbg(tmem_full, 0, p.dbg_host, 7, 0, true);
     tc_fence_after();
     const int half = dw >> 2;                 // accumulator (token half)
     const int quad = warp & 3;                // TMEM lane quarter this warp may access
     const int token = m0 + half * 128 + quad * 32 + lane;
     const size_t yoff = (size_t)token * p.ldy + p.col0 + n0;
+    float4* mine = partial ? p.partial + ((size_t)((tile - p.full) * p.split + slice) * 2 + rank) * SLOT_F4 + (threadIdx.x - 64)
+                           : nullptr;
 #pragma unroll 1
     for (int cb = 0; cb < BN / 32; ++cb) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + half * BN + cb * 32, v);
       tmem_ld_wait();
-      if (token < p.M) {
+      if (partial) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          __stcg(mine + (cb * 8 + j) * 256, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                        __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+      } else if (token < p.M) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int col = n0 + cb * 32 + q * 8;
@@ -900,9 +973,56 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
   return r == CUDA_SUCCESS ? MXQ_OK : MXQ_E_UNSUPPORTED;
 }
 
-// CTA-pair kernel: grid.x = 2 * ceil(M / 512) (cluster of 2 along x), grid.y = ceil(OC / 256)
+// Tile schedule of the CTA-pair kernel.  Tiles are 512 tokens x 256 weight rows, one cluster each,
+// dispatched M-fastest.  With T tiles on P SM pairs the last T % P tiles would run as a partly
+// filled wave while the other pairs idle (11008 x 4096 at M = 2048: 172 tiles on 74 pairs = 2.3
+// waves that cost 3).  Those tail tiles are cut along K into `split` slices so that the last wave
+// is full and 1 / split as long; the slices leave fp32 partials in an exchange buffer (L2-resident)
+// that a second, GPU-wide kernel adds up (an in-kernel "last arriver reduces" fix-up was measured
+// first: one CTA reading (split - 1) x 256 KB is bound by its own SM's L2 bandwidth and cost as
+// much as the wave it saved).
+struct Plan {
+  int mt, nt, tiles, full, split;
+  size_t partial_bytes;
+};
+constexpr size_t kPartialSlotBytes = (size_t)pair::BM * pair::BN * 4;   // one CTA's fp32 accumulators
+static Plan make_plan(int M, int IC, int OC, bool allow_split) {
+  Plan pl{};
+  pl.mt = ceil_div(M, 2 * pair::BM);
+  pl.nt = ceil_div(OC, pair::BN);
+  pl.tiles = pl.mt * pl.nt;
+  pl.full = pl.tiles;
+  pl.split = 1;
+  if (allow_split && IC % (4 * BK) == 0) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms >= 2) {
+      const int pairs = sms / 2;
+      const int tail = pl.tiles % pairs;
+      const int groups = IC / (4 * BK);
+      if (tail > 0) {
+        int s = pairs / tail;
+        if (s > groups / 4) s = groups / 4;      // a slice keeps >= 16 K blocks of main loop
+        if (s > 8) s = 8;
+        if (const char* e = getenv("MXQ_GEMM_SPLIT")) s = atoi(e) < s ? atoi(e) : s;   // profiling knob
+        if (s >= 2) {
+          pl.split = s;
+          pl.full = pl.tiles - tail;
+          pl.partial_bytes = (size_t)tail * s * 2 * kPartialSlotBytes;
+        }
+      }
+    }
+  }
+  return pl;
+}
+static size_t plan_workspace_bytes(const Plan& pl) {
+  return pl.split > 1 ? 256 + pl.partial_bytes : 256;
+}
+
+// CTA-pair kernel: 1-D grid of clusters of 2 (see Plan); workspace (optional) enables the K split
 template <bool kDenseB>
-static int launch_pair(const void* x, const Params& p, cudaStream_t st) {
+static int launch_pair(const void* x, const Params& p, cudaStream_t st, void* workspace = nullptr,
+                       size_t workspace_bytes = 0) {
   CUtensorMap mx, mw;
   int rc = make_map(&mx, x, p.M, p.IC, pair::BM);
   if (rc) return rc;
@@ -915,20 +1035,37 @@ static int launch_pair(const void* x, const Params& p, cudaStream_t st) {
   auto k = pair::gemm_mxq_pair_kernel<kDenseB>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
-  dim3 grid(2u * (unsigned)ceil_div(p.M, 2 * pair::BM), (unsigned)ceil_div(p.OC, pair::BN));
   Params pp = p;
+  Plan pl = make_plan(p.M, p.IC, p.OC, workspace != nullptr && p.npeers == 1);
+  if (pl.split > 1) {
+    const uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
+    if (base + pl.partial_bytes > reinterpret_cast<uintptr_t>(workspace) + workspace_bytes)
+      pl = make_plan(p.M, p.IC, p.OC, false);          // workspace too small: whole tiles only
+    else
+      pp.partial = reinterpret_cast<float4*>(base);
+  }
+  pp.mt = pl.mt; pp.full = pl.full; pp.split = pl.split;
+  const unsigned clusters = (unsigned)(pl.full + (pl.tiles - pl.full) * pl.split);
+  dim3 grid(2u * clusters);
   pp.dbg = 0;
   pp.dbg_host = nullptr;
   if (const char* e = getenv("MXQ_GEMM_DBG")) pp.dbg = atoi(e);
   if (const char* e = getenv("MXQ_GEMM_DBG_PTR")) pp.dbg_host = (unsigned long long*)strtoull(e, nullptr, 0);
   k<<<grid, THREADS, pair::SMEM_BYTES, st>>>(mx, mw, pp);
+  if (pl.split > 1) {
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    pair::gemm_split_reduce_kernel<<<(unsigned)(pl.tiles - pl.full) * 16u, 256, 0, st>>>(
+        pp.partial, pp.y[0], pl.split, pl.full, pl.mt, pp.M, pp.OC, pp.ldy, pp.col0);
+  }
   MXQ_LAUNCH_RESULT();
 }
 
 template <bool kDenseB>
-static int launch(const void* x, const Params& p, cudaStream_t st) {
+static int launch(const void* x, const Params& p, cudaStream_t st, void* workspace = nullptr,
+                  size_t workspace_bytes = 0) {
   // More than one M tile: CTA pairs (M = 256 MMAs).  MXQ_GEMM_SINGLE forces the one-CTA kernel.
-  if (p.M > BM && !getenv("MXQ_GEMM_SINGLE")) return launch_pair<kDenseB>(x, p, st);
+  if (p.M > BM && !getenv("MXQ_GEMM_SINGLE")) return launch_pair<kDenseB>(x, p, st, workspace, workspace_bytes);
   CUtensorMap mx, mw;
   int rc = make_map(&mx, x, p.M, p.IC, BM);
   if (rc) return rc;
@@ -954,11 +1091,13 @@ static int launch(const void* x, const Params& p, cudaStream_t st) {
 
 using namespace mxq;
 
-extern "C" size_t mxq_gemm_workspace_bytes(int64_t, int64_t, int64_t) { return 256; }
+extern "C" size_t mxq_gemm_workspace_bytes(int64_t M, int64_t IC, int64_t OC) {
+  if (M <= gemm::BM || IC <= 0 || OC <= 0 || M > INT32_MAX || OC > INT32_MAX || IC > (1 << 24)) return 256;
+  return gemm::plan_workspace_bytes(gemm::make_plan((int)M, (int)IC, (int)OC, true));
+}
 
 extern "C" int mxq_gemm(const void* x, mxq_packed_t w, void* y, int64_t M, int64_t IC, int64_t OC,
                         void* workspace, size_t workspace_bytes, void* stream) {
-  (void)workspace; (void)workspace_bytes;
   if (M < 0 || IC < 0 || OC < 0) return MXQ_E_SHAPE;
   if (M == 0 || OC == 0) return MXQ_OK;
   MXQ_CHECK_PTR(x);
@@ -970,7 +1109,7 @@ extern "C" int mxq_gemm(const void* x, mxq_packed_t w, void* y, int64_t M, int64
   gemm::Params p{};
   p.w = w; p.y[0] = (__half*)y; p.npeers = 1; p.ldy = (int)OC; p.col0 = 0;
   p.M = (int)M; p.IC = (int)IC; p.OC = (int)OC;
-  return gemm::launch<false>(x, p, as_stream(stream));
+  return gemm::launch<false>(x, p, as_stream(stream), workspace, workspace_bytes);
 }
 
 extern "C" int mxq_gemm_scatter(const void* x, mxq_packed_t w, void* const* y_peers, int npeers,

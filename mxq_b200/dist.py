@@ -87,8 +87,9 @@ class ColumnShardedMXQLinear:
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         ops = self.ops
         M = x.shape[0]
-        if self._ws is None:
-            self._ws = torch.zeros(4096, dtype=torch.uint8, device=x.device)
+        need = ops.gemm_workspace_bytes(M, x.shape[1], self.OC_local)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
         if self.world == 1:
             return ops.gemm(x, self.p, workspace=self._ws, validate=False)
         if self.mode == "p2p":

@@ -317,6 +317,16 @@ def gemv_grouped(x: torch.Tensor, ps: list, outs: list | None = None, pdl: bool 
     return outs
 
 
+def gemm_workspace_bytes(M: int, IC: int, OC: int) -> int:
+    return max(int(L.lib().mxq_gemm_workspace_bytes(M, IC, OC)), 16)
+
+
+def gemm_workspace(M: int, IC: int, OC: int, device) -> torch.Tensor:
+    """Workspace for `gemm` at this shape: the fp32 exchange buffer of the K-split tail tiles
+    (mxq_gemm_workspace_bytes; need not be initialised)."""
+    return _ws(gemm_workspace_bytes(M, IC, OC), device)
+
+
 def gemm(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, workspace=None,
          validate: bool = True):
     """Prefill: y[M, OC] = x[M, IC] @ dequant(W)^T on tcgen05/TMEM, fp16 in/out, fp32 accumulate."""
@@ -330,7 +340,7 @@ def gemm(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, workspace=No
         out = torch.empty((M, OC), dtype=torch.float16, device=x.device)
     need = L.lib().mxq_gemm_workspace_bytes(M, IC, OC)
     if workspace is None or workspace.numel() < need:
-        workspace = torch.zeros(max(int(need), 16), dtype=torch.uint8, device=x.device)
+        workspace = _ws(need, x.device)
     rc = L.lib().mxq_gemm(L.ptr(x), L.packed_struct(p), L.ptr(out), M, IC, OC, L.ptr(workspace),
                           workspace.numel(), L.stream())
     L.check(rc, "mxq_gemm")

@@ -60,8 +60,9 @@ class MXQLinear(nn.Module):
         if x2.shape[0] <= self.GEMV_MAX_TOKENS:
             y = ops.gemv(x2, self.packed, validate=False)
         else:
-            if self._ws is None or self._ws.device != x2.device:
-                self._ws = torch.zeros(4096, dtype=torch.uint8, device=x2.device)
+            need = ops.gemm_workspace_bytes(x2.shape[0], self.in_features, self.out_features)
+            if self._ws is None or self._ws.device != x2.device or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=x2.device)
             y = ops.gemm(x2, self.packed, workspace=self._ws, validate=False)
         return y.reshape(*lead, self.out_features)
 

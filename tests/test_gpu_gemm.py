@@ -55,3 +55,46 @@ def test_full_size_vs_unpack_matmul(cuda):
     assert float((y - ref).abs().max() / ref.abs().max()) <= TOL
     yv = ops.gemv(x[:4].contiguous(), p).float()
     assert float((yv - y[:4]).abs().max() / ref.abs().max()) <= TOL
+
+
+# K-split tail tiles (pair::Plan): tiles % SM-pairs != 0 and IC >= 2048 cut the last wave's tiles into
+# K slices that meet in the fp32 exchange workspace
+@pytest.mark.parametrize("M,OC,IC", [(512, 2560, 2048), (1000, 1304, 4096), (512, 520, 8192), (2048, 11008, 2048)])
+def test_packed_split_k_tail(cuda, M, OC, IC):
+    from mxq_b200 import ops
+    assert ops.gemm_workspace_bytes(M, IC, OC) > 4096, "shape was meant to exercise the K split"
+    p = O.random_packed(OC, IC, seed=M + OC + IC)
+    rng = np.random.default_rng(M)
+    x = rng.standard_normal((M, IC)).astype(np.float16)
+    ref = O.gemm_mxq_f32(x, p)
+    pd = packed_to_dev(p, cuda)
+    xd = torch.from_numpy(x).to(cuda)
+    ws = ops.gemm_workspace(M, IC, OC, cuda)
+    ws.fill_(0xFF)                      # the workspace need not be initialised
+    y1 = ops.gemm(xd, pd, workspace=ws)
+    assert _rel(y1.cpu().numpy(), ref) <= TOL
+    # slices are added in slice order: bit-identical from run to run
+    for _ in range(3):
+        y2 = ops.gemm(xd, pd, workspace=ws)
+        assert torch.equal(y1, y2)
+    y3 = ops.gemm(xd, pd, workspace=None)
+    assert torch.equal(y1, y3)
+    # a workspace that is too small falls back to whole tiles
+    small = torch.empty(4096, dtype=torch.uint8, device=cuda)
+    from mxq_b200 import _lib as L
+    out = torch.empty_like(y1)
+    rc = L.lib().mxq_gemm(L.ptr(xd), L.packed_struct(pd), L.ptr(out), M, IC, OC, L.ptr(small), small.numel(), L.stream())
+    assert rc == 0
+    assert _rel(out.cpu().numpy(), ref) <= TOL
+
+
+def test_split_k_mlp_shape_vs_unpack_matmul(cuda):
+    """Llama-2-7B gate/up shape at M = 2048 (172 tiles on 74 SM pairs: 24 tail tiles x 3 K slices)."""
+    from mxq_b200 import ops
+    torch.manual_seed(1)
+    W = (torch.randn(11008, 4096, device=cuda) * 0.02).half()
+    p = ops.pack(W)
+    x = torch.randn(2048, 4096, device=cuda).half()
+    y = ops.gemm(x, p).float()
+    ref = x.float() @ ops.unpack(p).T
+    assert float((y - ref).abs().max() / ref.abs().max()) <= TOL
