@@ -218,6 +218,15 @@ MXQ_API int mxq_gemm_scatter(const void* x, mxq_packed_t w, void* const* y_peers
                              int64_t M, int64_t IC, int64_t OC, int64_t ldy, int64_t col0,
                              void* stream);
 
+/* Same exchange through an NVSwitch multicast mapping: `y_multicast` is the multicast address of a
+ * symmetric [M, ldy] fp16 buffer (e.g. torch symmetric memory `multicast_ptr`); the epilogue issues
+ * ONE multimem.st per 16 bytes and the switch replicates it into every rank's buffer, so a rank's
+ * NVLink egress is its tile once instead of once per peer.  The caller synchronises the ranks
+ * afterwards.  MXQ_E_UNSUPPORTED is never returned here: whether the address is a multicast
+ * mapping is the caller's contract. */
+MXQ_API int mxq_gemm_multicast(const void* x, mxq_packed_t w, void* y_multicast, int64_t M, int64_t IC,
+                               int64_t OC, int64_t ldy, int64_t col0, void* stream);
+
 /* Diagnostic: the same tcgen05/TMA pipeline with a dense fp16 B operand W[OC, IC] loaded by TMA
  * instead of dequantized in registers (y = x @ W^T).  Separates UMMA-descriptor errors from
  * dequant/swizzle errors in tests; not part of the reference surface. */

@@ -148,12 +148,20 @@ __device__ __forceinline__ uint4 dequant_4b(uint32_t w, uint32_t zmagic, uint32_
   return make_uint4(prmt(h[0], h[1], 0x5410), prmt(h[2], h[3], 0x5410), prmt(h[0], h[1], 0x7632), prmt(h[2], h[3], 0x7632));
 }
 
+// 16 bytes to an NVSwitch multicast address: the switch replicates the store into the buffer of
+// every GPU bound to the multicast object (the type only names the vector shape)
+__device__ __forceinline__ void multimem_st_16(void* mc_addr, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+               ::"l"(mc_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 constexpr int MAX_PEERS = 8;
 struct Params {
   mxq_packed_t w;
   const __half* wdense;      // dense-B debug path only
   __half* y[MAX_PEERS];      // output base pointers: [0] local; > 1 entries = peers' buffers mapped
   int npeers;                //   over NVLink (fused column all-gather: every tile is stored to all)
+  int mc;                    // y[0] is an NVLink multicast address: one multimem.st reaches every rank's buffer
   int ldy, col0;             // output row stride (elements) and first output column of this shard
   int M, IC, OC;
   int dbg;                   // profiling only (MXQ_GEMM_DBG): 1 = one M half, 2 = no TMA after the first ring fill
@@ -912,6 +920,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
     const size_t yoff = (size_t)token * p.ldy + p.col0 + n0;
     float4* mine = partial ? p.partial + ((size_t)((tile - p.full) * p.split + slice) * 2 + rank) * SLOT_F4 + (threadIdx.x - 64)
                            : nullptr;
+    if (p.mc || p.npeers > 1) {
+      // Exchange epilogue (fused column all-gather).  A thread owns a token row, so direct stores
+      // are 64-byte pieces, one NVLink packet per 16 bytes.  The operand ring is free once
+      // tmem_full has fired: each warp transposes its 32 rows x 512 B through it and stores whole
+      // 512-byte row segments -- to every peer, or once to the multicast address.
+      constexpr int PITCH = BN * 2 + 16;
+      uint8_t* stg = smem + dw * (32 * PITCH);
+#pragma unroll 1
+      for (int cb = 0; cb < BN / 32; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + half * BN + cb * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            oh[e] = __floats2half2_rn(__uint_as_float(v[q * 8 + 2 * e]), __uint_as_float(v[q * 8 + 2 * e + 1]));
+          *reinterpret_cast<uint4*>(stg + lane * PITCH + cb * 64 + q * 16) = o;
+        }
+      }
+      __syncwarp();
+      const int tok0 = m0 + half * 128 + quad * 32;
+      const int col = n0 + lane * 8;
+      if (col + 8 <= p.OC) {
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          if (tok0 + r >= p.M) break;
+          const uint4 o = *reinterpret_cast<const uint4*>(stg + r * PITCH + lane * 16);
+          const size_t off = (size_t)(tok0 + r) * p.ldy + p.col0 + col;
+          if (p.mc) {
+            multimem_st_16(p.y[0] + off, o);
+          } else {
+            for (int pe = 0; pe < p.npeers; ++pe) *reinterpret_cast<uint4*>(p.y[pe] + off) = o;
+          }
+        }
+      }
+    } else
 #pragma unroll 1
     for (int cb = 0; cb < BN / 32; ++cb) {
       uint32_t v[32];
@@ -932,8 +979,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 #pragma unroll
             for (int e = 0; e < 4; ++e)
               oh[e] = __floats2half2_rn(__uint_as_float(v[q * 8 + 2 * e]), __uint_as_float(v[q * 8 + 2 * e + 1]));
-            for (int pe = 0; pe < p.npeers; ++pe)
-              *reinterpret_cast<uint4*>(p.y[pe] + yoff + cb * 32 + q * 8) = o;
+            *reinterpret_cast<uint4*>(p.y[0] + yoff + cb * 32 + q * 8) = o;
           }
         }
       }
@@ -1132,6 +1178,24 @@ extern "C" int mxq_gemm_scatter(const void* x, mxq_packed_t w, void* const* y_pe
   p.npeers = npeers; p.ldy = (int)ldy; p.col0 = (int)col0;
   p.M = (int)M; p.IC = (int)IC; p.OC = (int)OC;
   return gemm::launch<false>(x, p, as_stream(stream));
+}
+
+extern "C" int mxq_gemm_multicast(const void* x, mxq_packed_t w, void* y_multicast, int64_t M, int64_t IC,
+                                  int64_t OC, int64_t ldy, int64_t col0, void* stream) {
+  if (M < 0 || IC < 0 || OC < 0) return MXQ_E_SHAPE;
+  if (M == 0 || OC == 0) return MXQ_OK;
+  MXQ_CHECK_PTR(x);
+  MXQ_CHECK_PTR(y_multicast);
+  MXQ_CHECK_PTR(w.weight);
+  if (!w.weight_last || !w.zeros_and_scales || !w.zeros_2nd || !w.scales_2nd || !w.scales_4b || !w.zeros_4b)
+    return MXQ_E_NULL;
+  if (IC % 64 || IC == 0 || OC % 8 || ldy % 8 || col0 % 8 || col0 + OC > ldy || ldy > INT32_MAX) return MXQ_E_SHAPE;
+  if (M > INT32_MAX || IC > (1 << 24)) return MXQ_E_SHAPE;
+  gemm::Params p{};
+  p.w = w; p.y[0] = (__half*)y_multicast; p.npeers = 1; p.mc = 1; p.ldy = (int)ldy; p.col0 = (int)col0;
+  p.M = (int)M; p.IC = (int)IC; p.OC = (int)OC;
+  // the CTA-pair kernel carries the multicast epilogue; short M runs it too (rows beyond M are masked)
+  return gemm::launch_pair<false>(x, p, as_stream(stream));
 }
 
 extern "C" int mxq_gemm_dense(const void* x, const void* W, void* y, int64_t M, int64_t IC, int64_t OC,

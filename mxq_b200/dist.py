@@ -5,7 +5,9 @@
 * dequant-GEMM (70B)  : output columns (= weight rows with all their per-row / 4-row / 8-row
                         metadata) are sharded, x is replicated, the [M, N/W] tiles are exchanged:
                         either NCCL all-gather, or the GEMM epilogue stores its tile straight into
-                        every peer's output buffer over NVLink (symmetric memory, `mode="p2p"`).
+                        every peer's output buffer over NVLink (symmetric memory, `mode="p2p"`),
+                        or into all of them at once through the NVSwitch multicast mapping of
+                        that buffer (`mode="mc"`: one multimem.st, egress = the tile once).
 * QAT                 : data parallel, NCCL gradient all-reduce (torch DDP around QuantizeLinear).
 """
 from __future__ import annotations
@@ -92,6 +94,14 @@ class ColumnShardedMXQLinear:
             self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
         if self.world == 1:
             return ops.gemm(x, self.p, workspace=self._ws, validate=False)
+        if self.mode == "mc":
+            out, hdl = self._symm_out(M, x.device)
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            if not mc:
+                raise RuntimeError("symmetric memory has no multicast mapping on this system (mode='mc')")
+            ops.gemm_multicast(x, self.p, mc, ldy=self.OC_total, col0=self.rank * self.OC_local)
+            hdl.barrier(channel=0)          # every rank's multicast stores have landed everywhere
+            return out
         if self.mode == "p2p":
             out, hdl = self._symm_out(M, x.device)
             ptrs = [int(p) for p in hdl.buffer_ptrs]

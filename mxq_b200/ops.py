@@ -328,8 +328,10 @@ def gemm_workspace(M: int, IC: int, OC: int, device) -> torch.Tensor:
 
 
 def gemm(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, workspace=None,
-         validate: bool = True):
-    """Prefill: y[M, OC] = x[M, IC] @ dequant(W)^T on tcgen05/TMEM, fp16 in/out, fp32 accumulate."""
+         validate: bool = True, split_k: bool = True):
+    """Prefill: y[M, OC] = x[M, IC] @ dequant(W)^T on tcgen05/TMEM, fp16 in/out, fp32 accumulate.
+    split_k=False passes no workspace: whole tiles only, i.e. every output element is one
+    K-ordered fp32 accumulation (bit-identical to the sharded / fused-exchange paths)."""
     OC, IC = _check_packed(p) if validate else _packed_dims(p)
     L.require_cuda(x)
     if x.dtype != torch.float16 or x.dim() != 2 or x.shape[1] != IC:
@@ -338,11 +340,14 @@ def gemm(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, workspace=No
     M = x.shape[0]
     if out is None:
         out = torch.empty((M, OC), dtype=torch.float16, device=x.device)
-    need = L.lib().mxq_gemm_workspace_bytes(M, IC, OC)
-    if workspace is None or workspace.numel() < need:
-        workspace = _ws(need, x.device)
-    rc = L.lib().mxq_gemm(L.ptr(x), L.packed_struct(p), L.ptr(out), M, IC, OC, L.ptr(workspace),
-                          workspace.numel(), L.stream())
+    if split_k:
+        need = L.lib().mxq_gemm_workspace_bytes(M, IC, OC)
+        if workspace is None or workspace.numel() < need:
+            workspace = _ws(need, x.device)
+        wptr, wbytes = L.ptr(workspace), workspace.numel()
+    else:
+        wptr, wbytes = None, 0
+    rc = L.lib().mxq_gemm(L.ptr(x), L.packed_struct(p), L.ptr(out), M, IC, OC, wptr, wbytes, L.stream())
     L.check(rc, "mxq_gemm")
     return out
 
@@ -358,6 +363,20 @@ def gemm_scatter(x: torch.Tensor, p: dict, peer_ptrs: list, ldy: int, col0: int)
     rc = L.lib().mxq_gemm_scatter(L.ptr(x), L.packed_struct(p), arr, len(peer_ptrs), x.shape[0], IC, OC,
                                   ldy, col0, L.stream())
     L.check(rc, "mxq_gemm_scatter")
+
+
+def gemm_multicast(x: torch.Tensor, p: dict, multicast_ptr: int, ldy: int, col0: int):
+    """Column-sharded GEMM whose epilogue stores the [M, OC_local] tile at column `col0` of the
+    symmetric [M, ldy] fp16 buffer behind the NVSwitch multicast address `multicast_ptr`: one
+    multimem.st per 16 bytes lands in every rank's copy."""
+    OC, IC = _packed_dims(p)
+    L.require_cuda(x)
+    if not multicast_ptr:
+        raise RuntimeError("gemm_multicast needs a multicast mapping (symmetric memory without NVSwitch multicast support)")
+    x = x.contiguous()
+    rc = L.lib().mxq_gemm_multicast(L.ptr(x), L.packed_struct(p), int(multicast_ptr), x.shape[0], IC, OC,
+                                    ldy, col0, L.stream())
+    L.check(rc, "mxq_gemm_multicast")
 
 
 def gemm_dense(x: torch.Tensor, W: torch.Tensor) -> torch.Tensor:

@@ -1,5 +1,5 @@
 """GPU, world_size 2 (skipped on a 1-GPU box): column-sharded dequant-GEMM, NCCL all-gather and the
-fused peer-store epilogue, against the single-GPU GEMM on the unsharded tensors."""
+fused peer-store / multicast-store epilogues, against the single-GPU GEMM on the unsharded tensors."""
 import os
 import socket
 
@@ -31,15 +31,20 @@ def _worker(rank, world, port, q):
         OC, IC, M = 1024, 4096, 512
         p = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in O.random_packed(OC, IC, seed=5).items()}
         x = torch.from_numpy(np.random.default_rng(1).standard_normal((M, IC)).astype(np.float16)).to(dev)
-        ref = ops.gemm(x, p)
+        ref = ops.gemm(x, p, split_k=False)       # one K-ordered accumulation per element
         local = mdist.shard_packed_rows(p, world, rank)
         res = {}
-        for mode in ("nccl", "p2p"):
+        for mode in ("nccl", "p2p", "mc"):
             try:
                 lin = mdist.ColumnShardedMXQLinear(local, OC, mode=mode)
                 y = lin(x)
                 torch.cuda.synchronize()
-                res[mode] = bool(torch.equal(y, ref))
+                # the fused epilogues run whole tiles: bit-identical; the NCCL mode may cut tail
+                # tiles along K (fp32 partials added in slice order): within the GEMM tolerance
+                if mode == "nccl":
+                    res[mode] = bool(float((y.float() - ref.float()).abs().max() / ref.float().abs().max()) <= 1e-3)
+                else:
+                    res[mode] = bool(torch.equal(y, ref))
             except Exception as e:  # report, the parent decides
                 res[mode] = repr(e)[:300]
         dist.barrier()
@@ -65,3 +70,5 @@ def test_world2_sharded_gemm(cuda):
         assert p.exitcode == 0
     assert res["nccl"] is True, res
     assert res["p2p"] is True, res
+    # multicast needs an NVSwitch multicast mapping; where the system has none the mode reports it
+    assert res["mc"] is True or "multicast" in str(res["mc"]), res
