@@ -213,10 +213,11 @@ MXQ_API int mxq_gemm(const void* x, mxq_packed_t w, void* y, int64_t M, int64_t 
  * [col0, col0 + OC) of a [M, ldy] result; the epilogue stores every tile into each of the `npeers`
  * output buffers in y_peers (host array of device pointers: the local buffer and the peers'
  * buffers mapped into this process over NVLink, e.g. torch symmetric memory).  The caller
- * synchronises the ranks afterwards (the library never does). */
+ * synchronises the ranks afterwards (the library never does).  workspace as for mxq_gemm (the
+ * second pass of K-split tiles then carries the exchange stores); NULL is legal. */
 MXQ_API int mxq_gemm_scatter(const void* x, mxq_packed_t w, void* const* y_peers, int npeers,
                              int64_t M, int64_t IC, int64_t OC, int64_t ldy, int64_t col0,
-                             void* stream);
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* Same exchange through an NVSwitch multicast mapping: `y_multicast` is the multicast address of a
  * symmetric [M, ldy] fp16 buffer (e.g. torch symmetric memory `multicast_ptr`); the epilogue issues
@@ -225,7 +226,8 @@ MXQ_API int mxq_gemm_scatter(const void* x, mxq_packed_t w, void* const* y_peers
  * afterwards.  MXQ_E_UNSUPPORTED is never returned here: whether the address is a multicast
  * mapping is the caller's contract. */
 MXQ_API int mxq_gemm_multicast(const void* x, mxq_packed_t w, void* y_multicast, int64_t M, int64_t IC,
-                               int64_t OC, int64_t ldy, int64_t col0, void* stream);
+                               int64_t OC, int64_t ldy, int64_t col0, void* workspace,
+                               size_t workspace_bytes, void* stream);
 
 /* Diagnostic: the same tcgen05/TMA pipeline with a dense fp16 B operand W[OC, IC] loaded by TMA
  * instead of dequantized in registers (y = x @ W^T).  Separates UMMA-descriptor errors from

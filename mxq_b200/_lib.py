@@ -83,8 +83,8 @@ def lib() -> C.CDLL:
     L.mxq_gemm_workspace_bytes.argtypes = [i64, i64, i64]
     L.mxq_gemm.argtypes = [vp, PackedC, vp, i64, i64, i64, vp, sz, vp]
     L.mxq_gemm_dense.argtypes = [vp, vp, vp, i64, i64, i64, vp]
-    L.mxq_gemm_scatter.argtypes = [vp, PackedC, C.POINTER(vp), i32, i64, i64, i64, i64, i64, vp]
-    L.mxq_gemm_multicast.argtypes = [vp, PackedC, vp, i64, i64, i64, i64, i64, vp]
+    L.mxq_gemm_scatter.argtypes = [vp, PackedC, C.POINTER(vp), i32, i64, i64, i64, i64, i64, vp, sz, vp]
+    L.mxq_gemm_multicast.argtypes = [vp, PackedC, vp, i64, i64, i64, i64, i64, vp, sz, vp]
     for name in SYMBOLS:
         if getattr(L, name).restype is C.c_int:
             pass

@@ -583,21 +583,28 @@ __device__ __forceinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, un
 
 // Second pass of the K-split tail tiles (Plan): the clusters that ran a K slice left their fp32
 // accumulators in the exchange buffer, thread-major -- 16-byte chunk c (columns 4 c .. 4 c + 3 of
-// the tile) of epilogue thread t at [c * 256 + t] of the CTA's slot -- so that both the writes of
-// the GEMM epilogue and the reads here are coalesced.  One thread adds the slices of 32 columns of
-// one token in slice order (deterministic) and stores 64 contiguous bytes of fp16.
+// the tile) of epilogue thread t at [c * 256 + t] of the CTA's slot -- so that the writes of the
+// GEMM epilogue and the reads here are coalesced.  A block takes the 32 tokens of one epilogue
+// warp: warp w adds the slices of columns 32 w .. 32 w + 31 in slice order (deterministic), the
+// fp16 rows are transposed through shared memory and leave as whole 512-byte row segments -- to
+// the local buffer, to every peer, or once to the multicast address (fused column all-gather).
 constexpr int SLOT_F4 = (BN / 4) * 256;                // float4 per CTA partial (256 KB)
-__global__ void __launch_bounds__(256) gemm_split_reduce_kernel(const float4* __restrict__ partial, __half* __restrict__ y,
+struct OutPtrs {
+  __half* y[MAX_PEERS];
+  int npeers, mc;
+};
+__global__ void __launch_bounds__(256) gemm_split_reduce_kernel(const float4* __restrict__ partial, const OutPtrs out,
                                                                 int split, int full, int mt, int M, int OC, int ldy,
                                                                 int col0) {
-  const int t = threadIdx.x;
-  const int cb = blockIdx.x & 7, rank = (blockIdx.x >> 3) & 1, tail = blockIdx.x >> 4;
+  constexpr int PITCH = BN * 2 + 16;
+  __shared__ __align__(16) uint8_t rows[32 * PITCH];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dwi = blockIdx.x & 7, rank = (blockIdx.x >> 3) & 1, tail = blockIdx.x >> 4;
   const int tile = full + tail;
   const int m0 = (2 * (tile % mt) + rank) * BM, n0 = (tile / mt) * BN;
   // epilogue thread t = 32 * dw + lane of the GEMM: token half dw >> 2, TMEM lane quarter (dw + 2) & 3
-  const int dw = t >> 5, lane = t & 31;
-  const int token = m0 + (dw >> 2) * 128 + ((dw + 2) & 3) * 32 + lane;
-  const float4* src = partial + ((size_t)(tail * split) * 2 + rank) * SLOT_F4 + cb * 8 * 256 + t;
+  const int tok0 = m0 + (dwi >> 2) * 128 + ((dwi + 2) & 3) * 32;
+  const float4* src = partial + ((size_t)(tail * split) * 2 + rank) * SLOT_F4 + (8 * w) * 256 + dwi * 32 + lane;
   float4 acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = __ldcs(src + j * 256);
@@ -611,19 +618,29 @@ __global__ void __launch_bounds__(256) gemm_split_reduce_kernel(const float4* __
       acc[j].x += f[j].x; acc[j].y += f[j].y; acc[j].z += f[j].z; acc[j].w += f[j].w;
     }
   }
-  if (token < M) {
-    __half* dst = y + (size_t)token * ldy + col0 + n0 + cb * 32;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (n0 + cb * 32 + q * 8 + 8 <= OC) {
-        uint4 o;
-        __half2* oh = reinterpret_cast<__half2*>(&o);
-        oh[0] = __floats2half2_rn(acc[2 * q].x, acc[2 * q].y);
-        oh[1] = __floats2half2_rn(acc[2 * q].z, acc[2 * q].w);
-        oh[2] = __floats2half2_rn(acc[2 * q + 1].x, acc[2 * q + 1].y);
-        oh[3] = __floats2half2_rn(acc[2 * q + 1].z, acc[2 * q + 1].w);
-        *reinterpret_cast<uint4*>(dst + q * 8) = o;
-      }
+  for (int q = 0; q < 4; ++q) {
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+    oh[0] = __floats2half2_rn(acc[2 * q].x, acc[2 * q].y);
+    oh[1] = __floats2half2_rn(acc[2 * q].z, acc[2 * q].w);
+    oh[2] = __floats2half2_rn(acc[2 * q + 1].x, acc[2 * q + 1].y);
+    oh[3] = __floats2half2_rn(acc[2 * q + 1].z, acc[2 * q + 1].w);
+    *reinterpret_cast<uint4*>(rows + lane * PITCH + w * 64 + q * 16) = o;
+  }
+  __syncthreads();
+  const int col = n0 + lane * 8;
+  if (col + 8 > OC) return;
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int r = 4 * w + rr;
+    if (tok0 + r >= M) break;
+    const uint4 o = *reinterpret_cast<const uint4*>(rows + r * PITCH + lane * 16);
+    const size_t off = (size_t)(tok0 + r) * ldy + col0 + col;
+    if (out.mc) {
+      multimem_st_16(out.y[0] + off, o);
+    } else {
+      for (int pe = 0; pe < out.npeers; ++pe) *reinterpret_cast<uint4*>(out.y[pe] + off) = o;
     }
   }
 }
@@ -920,7 +937,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
     const size_t yoff = (size_t)token * p.ldy + p.col0 + n0;
     float4* mine = partial ? p.partial + ((size_t)((tile - p.full) * p.split + slice) * 2 + rank) * SLOT_F4 + (threadIdx.x - 64)
                            : nullptr;
-    if (p.mc || p.npeers > 1) {
+    if (!partial && (p.mc || p.npeers > 1)) {
       // Exchange epilogue (fused column all-gather).  A thread owns a token row, so direct stores
       // are 64-byte pieces, one NVLink packet per 16 bytes.  The operand ring is free once
       // tmem_full has fired: each warp transposes its 32 rows x 512 B through it and stores whole
@@ -1082,7 +1099,7 @@ static int launch_pair(const void* x, const Params& p, cudaStream_t st, void* wo
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
   Params pp = p;
-  Plan pl = make_plan(p.M, p.IC, p.OC, workspace != nullptr && p.npeers == 1);
+  Plan pl = make_plan(p.M, p.IC, p.OC, workspace != nullptr);
   if (pl.split > 1) {
     const uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
     if (base + pl.partial_bytes > reinterpret_cast<uintptr_t>(workspace) + workspace_bytes)
@@ -1101,8 +1118,11 @@ static int launch_pair(const void* x, const Params& p, cudaStream_t st, void* wo
   if (pl.split > 1) {
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
+    pair::OutPtrs out{};
+    for (int i = 0; i < pp.npeers; ++i) out.y[i] = pp.y[i];
+    out.npeers = pp.npeers; out.mc = pp.mc;
     pair::gemm_split_reduce_kernel<<<(unsigned)(pl.tiles - pl.full) * 16u, 256, 0, st>>>(
-        pp.partial, pp.y[0], pl.split, pl.full, pl.mt, pp.M, pp.OC, pp.ldy, pp.col0);
+        pp.partial, out, pl.split, pl.full, pl.mt, pp.M, pp.OC, pp.ldy, pp.col0);
   }
   MXQ_LAUNCH_RESULT();
 }
@@ -1160,7 +1180,7 @@ extern "C" int mxq_gemm(const void* x, mxq_packed_t w, void* y, int64_t M, int64
 
 extern "C" int mxq_gemm_scatter(const void* x, mxq_packed_t w, void* const* y_peers, int npeers,
                                 int64_t M, int64_t IC, int64_t OC, int64_t ldy, int64_t col0,
-                                void* stream) {
+                                void* workspace, size_t workspace_bytes, void* stream) {
   if (M < 0 || IC < 0 || OC < 0) return MXQ_E_SHAPE;
   if (M == 0 || OC == 0) return MXQ_OK;
   MXQ_CHECK_PTR(x);
@@ -1177,11 +1197,12 @@ extern "C" int mxq_gemm_scatter(const void* x, mxq_packed_t w, void* const* y_pe
   }
   p.npeers = npeers; p.ldy = (int)ldy; p.col0 = (int)col0;
   p.M = (int)M; p.IC = (int)IC; p.OC = (int)OC;
-  return gemm::launch<false>(x, p, as_stream(stream));
+  return gemm::launch<false>(x, p, as_stream(stream), workspace, workspace_bytes);
 }
 
 extern "C" int mxq_gemm_multicast(const void* x, mxq_packed_t w, void* y_multicast, int64_t M, int64_t IC,
-                                  int64_t OC, int64_t ldy, int64_t col0, void* stream) {
+                                  int64_t OC, int64_t ldy, int64_t col0, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
   if (M < 0 || IC < 0 || OC < 0) return MXQ_E_SHAPE;
   if (M == 0 || OC == 0) return MXQ_OK;
   MXQ_CHECK_PTR(x);
@@ -1195,7 +1216,7 @@ extern "C" int mxq_gemm_multicast(const void* x, mxq_packed_t w, void* y_multica
   p.w = w; p.y[0] = (__half*)y_multicast; p.npeers = 1; p.mc = 1; p.ldy = (int)ldy; p.col0 = (int)col0;
   p.M = (int)M; p.IC = (int)IC; p.OC = (int)OC;
   // the CTA-pair kernel carries the multicast epilogue; short M runs it too (rows beyond M are masked)
-  return gemm::launch_pair<false>(x, p, as_stream(stream));
+  return gemm::launch_pair<false>(x, p, as_stream(stream), workspace, workspace_bytes);
 }
 
 extern "C" int mxq_gemm_dense(const void* x, const void* W, void* y, int64_t M, int64_t IC, int64_t OC,

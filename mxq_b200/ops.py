@@ -352,7 +352,7 @@ def gemm(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, workspace=No
     return out
 
 
-def gemm_scatter(x: torch.Tensor, p: dict, peer_ptrs: list, ldy: int, col0: int):
+def gemm_scatter(x: torch.Tensor, p: dict, peer_ptrs: list, ldy: int, col0: int, workspace=None):
     """Column-sharded GEMM whose epilogue stores the [M, OC_local] tile at column `col0` of every
     [M, ldy] fp16 buffer in `peer_ptrs` (device addresses; peers mapped over NVLink)."""
     import ctypes as C
@@ -361,11 +361,12 @@ def gemm_scatter(x: torch.Tensor, p: dict, peer_ptrs: list, ldy: int, col0: int)
     x = x.contiguous()
     arr = (C.c_void_p * len(peer_ptrs))(*[int(a) for a in peer_ptrs])
     rc = L.lib().mxq_gemm_scatter(L.ptr(x), L.packed_struct(p), arr, len(peer_ptrs), x.shape[0], IC, OC,
-                                  ldy, col0, L.stream())
+                                  ldy, col0, L.ptr(workspace), 0 if workspace is None else workspace.numel(),
+                                  L.stream())
     L.check(rc, "mxq_gemm_scatter")
 
 
-def gemm_multicast(x: torch.Tensor, p: dict, multicast_ptr: int, ldy: int, col0: int):
+def gemm_multicast(x: torch.Tensor, p: dict, multicast_ptr: int, ldy: int, col0: int, workspace=None):
     """Column-sharded GEMM whose epilogue stores the [M, OC_local] tile at column `col0` of the
     symmetric [M, ldy] fp16 buffer behind the NVSwitch multicast address `multicast_ptr`: one
     multimem.st per 16 bytes lands in every rank's copy."""
@@ -375,7 +376,8 @@ def gemm_multicast(x: torch.Tensor, p: dict, multicast_ptr: int, ldy: int, col0:
         raise RuntimeError("gemm_multicast needs a multicast mapping (symmetric memory without NVSwitch multicast support)")
     x = x.contiguous()
     rc = L.lib().mxq_gemm_multicast(L.ptr(x), L.packed_struct(p), int(multicast_ptr), x.shape[0], IC, OC,
-                                    ldy, col0, L.stream())
+                                    ldy, col0, L.ptr(workspace), 0 if workspace is None else workspace.numel(),
+                                    L.stream())
     L.check(rc, "mxq_gemm_multicast")
 
 
