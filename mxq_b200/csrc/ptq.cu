@@ -183,13 +183,24 @@ __global__ void __launch_bounds__(256) ptq_pack_tile_kernel(const TileParams p) 
         const float rc = __frcp_rn(sc);
         float o[16];
         uint32_t cw[4] = {0, 0, 0, 0};
+        // two elements per instruction (FMUL2 / FFMA2 / FADD2 are IEEE-RN per lane: bit-identical to
+        // the scalar chain).  clamp(v, 0, maxq) + M == clamp(v + M, M, M + maxq) because v -> RN(v + M)
+        // is monotone and exact at the integer bounds; NaN / inf end at the same bound either way.
+        const f32x2 nsc2 = pk2(-sc, -sc), rc2 = pk2(rc, rc), zp2 = pk2(zero[i], zero[i]);
+        const f32x2 M2 = pk2(12582912.0f, 12582912.0f), nM2 = pk2(-12582912.0f, -12582912.0f), sq2 = pk2(sq, sq);
+        const float m_hi = __fadd_rn(12582912.0f, maxq);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float v = clampf(__fadd_rn(div_rn_by(x[i][e], sc, rc), zero[i]), 0.f, maxq);
-          int qi;
-          const float q = rint_magic(v, qi);
-          o[e] = __fmul_rn(sq, __fsub_rn(q, zero[i]));
-          if (kCodes) cw[e >> 2] |= (uint32_t)(qi & 0xFF) << (8 * (e & 3));
+        for (int e = 0; e < 16; e += 2) {
+          const f32x2 m2 = add2(add2(div2_rn_by(pk2(x[i][e], x[i][e + 1]), nsc2, rc2), zp2), M2);
+          float m0, m1;
+          upk2(m2, m0, m1);
+          m0 = fminf(fmaxf(m0, 12582912.0f), m_hi);
+          m1 = fminf(fmaxf(m1, 12582912.0f), m_hi);
+          if (kCodes) {
+            cw[e >> 2] |= (uint32_t)(__float_as_int(m0) & 0xFF) << (8 * (e & 3));
+            cw[e >> 2] |= (uint32_t)(__float_as_int(m1) & 0xFF) << (8 * ((e + 1) & 3));
+          }
+          upk2(mul2(sq2, sub2(add2(pk2(m0, m1), nM2), zp2)), o[e], o[e + 1]);
         }
         const size_t off = (size_t)(tile * 16 + rr + 8 * i) * p.cols + col0;
         *reinterpret_cast<uint4*>(p.Wq + off) = DT<__half>::pack(o);
@@ -231,14 +242,20 @@ __global__ void __launch_bounds__(256) ptq_pack_tile_kernel(const TileParams p) 
         const float rS = __frcp_rn(S);
         const float m_lo = 12582912.0f, m_hi = __fadd_rn(12582912.0f, maxq);
         uint32_t acc_lo = 0, acc_hi = 0;                 // codes 0..7 and 8..15 of this slot
+        const f32x2 nS2 = pk2(-S, -S), rS2 = pk2(rS, rS), Mp2 = pk2(12582912.0f, 12582912.0f), zz2 = pk2(z, z);
 #pragma unroll
-        for (int e = 7; e >= 0; --e) {
+        for (int e = 6; e >= 0; e -= 2) {
           // code = clamp(rint(w / S) + z, 0, maxq), evaluated in the 1.5*2^23 "integer" domain:
-          // (v + M) holds rint(v) exactly, adding the integer z and clamping stay exact
-          const float ma = __fadd_rn(__fadd_rn(div_rn_by(x[i][e], S, rS), 12582912.0f), z);
-          const float mb = __fadd_rn(__fadd_rn(div_rn_by(x[i][e + 8], S, rS), 12582912.0f), z);
-          acc_lo = acc_lo * radix + __float_as_uint(fminf(fmaxf(ma, m_lo), m_hi));
-          acc_hi = acc_hi * radix + __float_as_uint(fminf(fmaxf(mb, m_lo), m_hi));
+          // (v + M) holds rint(v) exactly, adding the integer z and clamping stay exact.  Elements
+          // e and e + 1 share a packed instruction (the same pairing as the quantizer above, so the
+          // register pairs are formed once).
+          float a0, a1, b0, b1;
+          upk2(add2(add2(div2_rn_by(pk2(x[i][e], x[i][e + 1]), nS2, rS2), Mp2), zz2), a0, a1);
+          upk2(add2(add2(div2_rn_by(pk2(x[i][e + 8], x[i][e + 9]), nS2, rS2), Mp2), zz2), b0, b1);
+          acc_lo = acc_lo * radix + __float_as_uint(fminf(fmaxf(a1, m_lo), m_hi));
+          acc_lo = acc_lo * radix + __float_as_uint(fminf(fmaxf(a0, m_lo), m_hi));
+          acc_hi = acc_hi * radix + __float_as_uint(fminf(fmaxf(b1, m_lo), m_hi));
+          acc_hi = acc_hi * radix + __float_as_uint(fminf(fmaxf(b0, m_lo), m_hi));
         }
         acc_lo -= horner_bias;
         acc_hi -= horner_bias;
