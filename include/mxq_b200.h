@@ -204,7 +204,8 @@ MXQ_API int mxq_awq_gemv(const void* x, const int32_t* kernel, const void* scale
  * workspace: mxq_gemm_workspace_bytes(M, IC, OC), uninitialised.  When the tiles (512 tokens x 256
  * rows) do not fill a whole number of waves of SM pairs, the tiles of the last wave are cut along K
  * and their fp32 partials meet in the workspace (a second small kernel adds them in a fixed order:
- * results are reproducible).  A NULL or too small workspace is legal: whole tiles only. */
+ * results are reproducible).  A NULL or too small workspace is legal: whole tiles only.  Calls that
+ * may run concurrently (different streams) need separate workspaces. */
 MXQ_API size_t mxq_gemm_workspace_bytes(int64_t M, int64_t IC, int64_t OC);
 MXQ_API int mxq_gemm(const void* x, mxq_packed_t w, void* y, int64_t M, int64_t IC, int64_t OC,
              void* workspace, size_t workspace_bytes, void* stream);

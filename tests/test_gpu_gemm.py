@@ -79,9 +79,17 @@ def test_packed_split_k_tail(cuda, M, OC, IC):
         assert torch.equal(y1, y2)
     y3 = ops.gemm(xd, pd, workspace=None)
     assert torch.equal(y1, y3)
+    # guard bands: nothing is written past the declared workspace size or outside the output
+    need = ops.gemm_workspace_bytes(M, IC, OC)
+    wsg = torch.full((need + 8192,), 0xAB, dtype=torch.uint8, device=cuda)
+    yg = torch.full((M + 2, OC), 7.0, dtype=torch.float16, device=cuda)
+    from mxq_b200 import _lib as L
+    rc = L.lib().mxq_gemm(L.ptr(xd), L.packed_struct(pd), yg[1:M + 1].data_ptr(), M, IC, OC, wsg.data_ptr(), need, L.stream())
+    assert rc == 0
+    assert torch.equal(yg[1:M + 1], y1)
+    assert bool((wsg[need:] == 0xAB).all()) and bool((yg[0] == 7.0).all()) and bool((yg[M + 1] == 7.0).all())
     # a workspace that is too small falls back to whole tiles
     small = torch.empty(4096, dtype=torch.uint8, device=cuda)
-    from mxq_b200 import _lib as L
     out = torch.empty_like(y1)
     rc = L.lib().mxq_gemm(L.ptr(xd), L.packed_struct(pd), L.ptr(out), M, IC, OC, L.ptr(small), small.numel(), L.stream())
     assert rc == 0
