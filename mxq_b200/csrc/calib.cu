@@ -9,15 +9,20 @@
 // slab of rows with 8 independent 128-bit loads in flight; a warp reads 512 contiguous bytes per
 // row.  Partial sums go to workspace[slab][col] and a second tiny kernel folds the slabs in a
 // fixed order (deterministic, no atomics).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mxq {
 
 constexpr int kCSThreads = 256;
-constexpr int kCSUnroll = 8;
 
-template <typename T>
-__global__ void __launch_bounds__(kCSThreads) colsumsq_partial_kernel(
+// kMinBlocks is a register budget (launch bounds).  8 (32 registers): ptxas keeps ~3 loads in flight
+// per thread and the kernel relies on full occupancy (8 CTAs / SM) for its memory parallelism.
+// 4 or 2: all kCSUnroll loads are front-loaded (56 registers at 8, 96 at 16), so 3 CTAs / SM keep as
+// many bytes in flight and leave room for a co-resident kernel.
+template <typename T, int kCSUnroll = 8, int kMinBlocks = 8>
+__global__ void __launch_bounds__(kCSThreads, kMinBlocks) colsumsq_partial_kernel(
     const uint8_t* __restrict__ X, float* __restrict__ partial, int64_t tokens, int cols, int cpr,
     int rows_per_slab) {
   using D = DT<T>;
@@ -57,6 +62,92 @@ __global__ void __launch_bounds__(kCSThreads) colsumsq_partial_kernel(
 #pragma unroll
   for (int e = 0; e < EPC; e += 4)
     *reinterpret_cast<float4*>(dst + e) = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Same statistic, bytes in flight held in SHARED memory instead of registers: one CTA per SM takes a
+// slab of whole rows; R consecutive rows are one contiguous byte range, fetched by ONE 1-D TMA bulk
+// copy (cp.async.bulk + mbarrier tx-count) into a ring of up to 8 stages (<= 192 KB per SM in
+// flight).  Thread t owns 16-byte column chunks t, t + 256, ... (conflict-free LDS.128) and keeps
+// their sums in registers.  The CTA needs ~10 K registers and a few issue slots, so the issue-bound
+// quantize+pack tile kernel of the previous layer runs ALONGSIDE on the same SMs (two of its CTAs
+// fit) instead of taking turns with it -- the register-buffered kernel above needs every warp slot
+// of the SM for its memory parallelism (32 registers, ~3 loads in flight per thread).
+// ---------------------------------------------------------------------------------------------
+constexpr int kRingStageMax = 32 * 1024;
+constexpr int kRingBytesMax = 192 * 1024;
+constexpr int kRingStagesMax = 8;
+
+template <typename T, int CH>
+__global__ void __launch_bounds__(kCSThreads, 1) colsumsq_ring_kernel(
+    const uint8_t* __restrict__ X, float* __restrict__ partial, int64_t tokens, int cols, int cpr,
+    int rows_per_slab, int rows_per_stage, int nstages) {
+  using D = DT<T>;
+  constexpr int EPC = D::EPC;
+  extern __shared__ __align__(128) uint8_t ring[];
+  __shared__ uint64_t full[kRingStagesMax], empty[kRingStagesMax];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_slab;
+  const int64_t r1 = r0 + rows_per_slab < tokens ? r0 + rows_per_slab : tokens;
+  const size_t row_bytes = (size_t)cols * sizeof(T);
+  const uint32_t stage_bytes = (uint32_t)(rows_per_stage * row_bytes);
+  const int nfill = r1 > r0 ? (int)((r1 - r0 + rows_per_stage - 1) / rows_per_stage) : 0;
+  auto fill = [&](int f) {      // thread 0: rows [r0 + f R, ...) -> stage f % nstages
+    const int64_t ra = r0 + (int64_t)f * rows_per_stage;
+    const int64_t rb = ra + rows_per_stage < r1 ? ra + rows_per_stage : r1;
+    const uint32_t bytes = (uint32_t)((rb - ra) * row_bytes);
+    uint64_t* bar = &full[f % nstages];
+    mbar_arrive_expect_tx(bar, bytes);
+    bulk_g2s(ring + (size_t)(f % nstages) * stage_bytes, X + (size_t)ra * row_bytes, bytes, bar);
+  };
+  if (tid == 0) {
+    for (int i = 0; i < nstages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kCSThreads / 32); }
+    mbar_fence_init();
+    for (int f = 0; f < nstages && f < nfill; ++f) fill(f);
+  }
+  __syncthreads();
+  float acc[CH][EPC];
+#pragma unroll
+  for (int j = 0; j < CH; ++j)
+#pragma unroll
+    for (int e = 0; e < EPC; ++e) acc[j][e] = 0.f;
+  for (int f = 0; f < nfill; ++f) {
+    const int s = f % nstages;
+    const uint32_t ph = (uint32_t)(f / nstages) & 1u;
+    mbar_wait(&full[s], ph);
+    const int64_t ra = r0 + (int64_t)f * rows_per_stage;
+    const int nr = (int)((ra + rows_per_stage < r1 ? ra + rows_per_stage : r1) - ra);
+    const uint8_t* st = ring + (size_t)s * stage_bytes + (size_t)tid * 16;
+    for (int r = 0; r < nr; ++r) {
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        if (tid + j * kCSThreads < cpr) {
+          float v[EPC];
+          D::unpack(*reinterpret_cast<const uint4*>(st + (size_t)r * row_bytes + (size_t)j * (kCSThreads * 16)), v);
+#pragma unroll
+          for (int e = 0; e < EPC; ++e) acc[j][e] = fmaf(v[e], v[e], acc[j][e]);
+        }
+      }
+    }
+    // this warp is done with the stage; the producer refills it once all 8 warps are
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    if (tid == 0 && f + nstages < nfill) {
+      mbar_wait(&empty[s], ph);
+      fill(f + nstages);
+    }
+  }
+  float* dst = partial + (size_t)blockIdx.x * cols;
+#pragma unroll
+  for (int j = 0; j < CH; ++j) {
+    const int c = tid + j * kCSThreads;
+    if (c < cpr) {
+#pragma unroll
+      for (int e = 0; e < EPC; e += 4)
+        *reinterpret_cast<float4*>(dst + (size_t)c * EPC + e) =
+            make_float4(acc[j][e], acc[j][e + 1], acc[j][e + 2], acc[j][e + 3]);
+    }
+  }
 }
 
 // fold the slabs: block = 32 columns x 32 slab lanes (coalesced 128-byte rows of `partial`), fixed
@@ -175,7 +266,9 @@ extern "C" size_t mxq_colsumsq_workspace_bytes(int64_t tokens, int64_t cols) {
   return (size_t)slabs_for(tokens, cpr_min, 32) * (size_t)cols * sizeof(float) + 16;
 }
 
-// ctas_per_sm: CTAs of the partial kernel per SM.  8 (= mxq_colsumsq) is one full wave.  Smaller
+// ctas_per_sm = 0: the shared-memory ring kernel (one CTA per SM; made to share the SMs with the PTQ
+// tile kernel of another stream), falling back to 8 for shapes it does not cover.
+// ctas_per_sm >= 1: CTAs of the register-buffered partial kernel per SM.  8 (= mxq_colsumsq) is one full wave.  Smaller
 // values are enforced with an unused dynamic shared-memory reservation and leave registers / thread
 // slots free; larger values (up to 32) split the rows into more, shorter slabs = several waves, so
 // CTAs retire continuously and a concurrent kernel on another (higher-priority) stream -- the PTQ
@@ -183,7 +276,7 @@ extern "C" size_t mxq_colsumsq_workspace_bytes(int64_t tokens, int64_t cols) {
 extern "C" int mxq_colsumsq_ex(const void* X, int64_t tokens, int64_t cols, int dtype, float* out,
                                float prev_scale, float add_scale, int accumulate, int ctas_per_sm,
                                void* workspace, size_t workspace_bytes, void* stream) {
-  if (tokens < 0 || cols <= 0 || ctas_per_sm < 1 || ctas_per_sm > 32) return MXQ_E_SHAPE;
+  if (tokens < 0 || cols <= 0 || ctas_per_sm < 0 || ctas_per_sm > 32) return MXQ_E_SHAPE;
   MXQ_CHECK_PTR(out);
   if (dtype != MXQ_F32 && dtype != MXQ_F16 && dtype != MXQ_BF16) return MXQ_E_DTYPE;
   const int esize = dtype == MXQ_F32 ? 4 : 2;
@@ -194,6 +287,40 @@ extern "C" int mxq_colsumsq_ex(const void* X, int64_t tokens, int64_t cols, int 
   if (tokens > 0) {
     MXQ_CHECK_PTR(X);
     MXQ_CHECK_PTR(workspace);
+    const size_t row_bytes = (size_t)cols * esize;
+    const int ch = (int)ceil_div(cpr, kCSThreads);
+    const char* re = getenv("MXQ_STAT_RING");                 // profiling knob: 0 forces the register kernel
+    const bool ring = ctas_per_sm == 0 ? true : (re && atoi(re) == 1);
+    const int ring_rows_per_slab = (int)ceil_div(tokens, kNumSMs);
+    const int ring_slabs = (int)ceil_div(tokens, ring_rows_per_slab);
+    if (ring && row_bytes <= (size_t)kRingStageMax * 2 && ch <= 8 && tokens >= kNumSMs && !(re && atoi(re) == 0) &&
+        workspace_bytes >= (size_t)ring_slabs * cols * sizeof(float)) {
+      // one CTA per SM, whole rows, TMA bulk ring (colsumsq_ring_kernel)
+      const int rps = row_bytes >= (size_t)kRingStageMax ? 1 : (int)(kRingStageMax / row_bytes);
+      const size_t stage_bytes = (size_t)rps * row_bytes;
+      int nst = (int)(kRingBytesMax / stage_bytes);
+      if (nst > kRingStagesMax) nst = kRingStagesMax;
+      slabs = ring_slabs;
+      const int rows_per_slab = ring_rows_per_slab;
+      const size_t smem = (size_t)nst * stage_bytes;
+      float* part = (float*)workspace;
+      const uint8_t* Xb = (const uint8_t*)X;
+      auto launch_ring = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)slabs, kCSThreads, smem, st>>>(Xb, part, tokens, (int)cols, cpr, rows_per_slab, rps, nst);
+        return cudaSuccess;
+      };
+      auto by_ch = [&](auto tag) -> cudaError_t {
+        using TT = decltype(tag);
+        return ch <= 1 ? launch_ring(colsumsq_ring_kernel<TT, 1>) : ch <= 2 ? launch_ring(colsumsq_ring_kernel<TT, 2>)
+             : ch <= 4 ? launch_ring(colsumsq_ring_kernel<TT, 4>) : ch <= 6 ? launch_ring(colsumsq_ring_kernel<TT, 6>)
+                       : launch_ring(colsumsq_ring_kernel<TT, 8>);
+      };
+      cudaError_t e = dtype == MXQ_F32 ? by_ch(float{}) : dtype == MXQ_F16 ? by_ch(__half{}) : by_ch(__nv_bfloat16{});
+      if (e != cudaSuccess) return (int)e;
+    } else {
+    if (ctas_per_sm == 0) ctas_per_sm = 8;
     slabs = slabs_for(tokens, cpr, ctas_per_sm);
     if (workspace_bytes < (size_t)slabs * cols * sizeof(float)) return MXQ_E_WORKSPACE;
     const int rows_per_slab = (int)ceil_div(tokens, slabs);
@@ -201,9 +328,10 @@ extern "C" int mxq_colsumsq_ex(const void* X, int64_t tokens, int64_t cols, int 
     dim3 grid((unsigned)ceil_div(cpr, kCSThreads), (unsigned)slabs);
     float* part = (float*)workspace;
     const uint8_t* Xb = (const uint8_t*)X;
-    // n CTAs per SM: n * (pad + 1 KB) <= 228 KB < (n + 1) * (pad + 1 KB)
+    // n CTAs per SM: n * (pad + 1 KB) <= 220 KB < (n + 1) * (pad + 1 KB); the last 8 KB stay free for
+    // the CTAs (1 KB of reserved shared memory each) of a kernel that is meant to run alongside
     size_t pad = 0;
-    if (ctas_per_sm < 8) pad = ((size_t)233472 / ctas_per_sm - 1024) & ~(size_t)1023;
+    if (ctas_per_sm < 8) pad = (((size_t)233472 - 8192) / ctas_per_sm - 1024) & ~(size_t)1023;
     auto launch = [&](auto kern) -> cudaError_t {
       if (pad > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
@@ -212,11 +340,18 @@ extern "C" int mxq_colsumsq_ex(const void* X, int64_t tokens, int64_t cols, int 
       kern<<<grid, kCSThreads, pad, st>>>(Xb, part, tokens, (int)cols, cpr, rows_per_slab);
       return cudaSuccess;
     };
-    cudaError_t e = dtype == MXQ_F32   ? launch(colsumsq_partial_kernel<float>)
-                    : dtype == MXQ_F16 ? launch(colsumsq_partial_kernel<__half>)
-                                       : launch(colsumsq_partial_kernel<__nv_bfloat16>);
+    // capped occupancy -> the variant whose threads really keep 8 (or, MXQ_STAT_UNROLL=16, 16) loads in flight
+    const char* ue = getenv("MXQ_STAT_UNROLL");
+    const int variant = ue ? atoi(ue) : (ctas_per_sm < 8 ? 8 : 0);
+    cudaError_t e;
+    if (dtype == MXQ_F32) e = launch(colsumsq_partial_kernel<float>);
+    else if (dtype == MXQ_BF16) e = variant == 8 ? launch(colsumsq_partial_kernel<__nv_bfloat16, 8, 4>) : launch(colsumsq_partial_kernel<__nv_bfloat16>);
+    else e = variant == 16  ? launch(colsumsq_partial_kernel<__half, 16, 2>)
+             : variant == 8 ? launch(colsumsq_partial_kernel<__half, 8, 4>)
+                            : launch(colsumsq_partial_kernel<__half>);
     if (e != cudaSuccess) return (int)e;
   }
+    }
   colsumsq_final_kernel<<<(unsigned)ceil_div(cols, 32), dim3(32, 32), 0, st>>>(
       (const float*)workspace, out, (int)cols, slabs, prev_scale, add_scale, accumulate);
   MXQ_LAUNCH_RESULT();

@@ -191,10 +191,34 @@ def test_pipelined_layers_equal_serial(cuda):
     X = layers[0][1]["down_in"]
     from mxq_b200 import ops
     ref = ops.colsumsq(X)
-    for ctas in (1, 3, 5, 7):
+    for ctas in (0, 1, 3, 5, 7):      # 0 = the shared-memory ring kernel
         out = torch.empty_like(ref)
         ws = torch.empty(ops.L.lib().mxq_colsumsq_workspace_bytes(X.shape[0], X.shape[1]), dtype=torch.uint8, device=cuda)
         rc = ops.L.lib().mxq_colsumsq_ex(X.data_ptr(), X.shape[0], X.shape[1], ops.L.MXQ_F16, out.data_ptr(), 0.0, 1.0, 0,
                                          ctas, ws.data_ptr(), ws.numel(), ops.L.stream())
         assert rc == 0
         assert torch.allclose(out, ref, rtol=1e-5, atol=0)
+
+
+def test_colsumsq_ring_kernel(cuda):
+    """mxq_colsumsq_ex(ctas_per_sm=0): TMA bulk ring, one CTA per SM -- same sums as the oracle for every
+    chunk count (1..8 chunks per thread), ragged last stages, rows of one stage or several."""
+    from mxq_b200 import ops
+    rng = np.random.default_rng(3)
+    L = ops.L
+    for dt, code, shape in ((torch.float16, L.MXQ_F16, (3000, 4096)), (torch.bfloat16, L.MXQ_BF16, (777, 11008)),
+                            (torch.float32, L.MXQ_F32, (1000, 1024)), (torch.float32, L.MXQ_F32, (2500, 8192)),
+                            (torch.float16, L.MXQ_F16, (149, 64)), (torch.float16, L.MXQ_F16, (4099, 16384)),
+                            (torch.float16, L.MXQ_F16, (32768, 4096))):
+        X = torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).to(dt)
+        X[:, 7] = 0
+        Xd = X.to(cuda)
+        out = torch.full((shape[1],), -1.0, dtype=torch.float32, device=cuda)
+        ws = torch.empty(L.lib().mxq_colsumsq_workspace_bytes(shape[0], shape[1]), dtype=torch.uint8, device=cuda)
+        rc = L.lib().mxq_colsumsq_ex(Xd.data_ptr(), shape[0], shape[1], code, out.data_ptr(), 0.0, 1.0, 0, 0,
+                                     ws.data_ptr(), ws.numel(), L.stream())
+        assert rc == 0
+        ref = O.colsumsq(X.float().numpy())
+        got = out.cpu().numpy()
+        assert np.abs(got - ref).max() <= 1e-5 * ref.max(), (dt, shape)
+        assert got[7] == 0.0 and np.array_equal(got == 0, O.dead_columns(X.float().numpy()))
