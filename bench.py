@@ -224,9 +224,11 @@ def main():
             for l in my_layers:
                 ptq.run(weights[l], calib, args.nsamples, on_stat=on_stat)
         else:
-            # statistics of layer i+1 (HBM-bound) overlap quantize+pack of layer i (issue-bound)
+            # statistics of layer i+1 (HBM-bound) overlap quantize+pack of layer i (issue-bound);
+            # 3 = the statistics variant with 16 loads in flight per thread, 2 CTAs resident per SM, 1.5
+            # waves: 69.7 ms per pass against 71.4 for the full-occupancy kernel (profiles/r1_sweep_stat_overlap.txt)
             ptq.run_pipelined(((weights[l], calib) for l in my_layers), args.nsamples, on_stat=on_stat,
-                              ctas_per_sm=int(os.environ.get("MXQ_STAT_CTAS", "8")))
+                              ctas_per_sm=int(os.environ.get("MXQ_STAT_CTAS", "3")))
 
     for _ in range(args.warmup):
         step()
@@ -258,6 +260,7 @@ def main():
                 # profiles/r1c_ncu_full_bench_kernels.csv (2.152 GB + 4.9 MB for the 2.147 GB input,
                 # 5.77 GB + 7.9 MB for the 5.771 GB one): no re-reads
                 "traffic": 1.0025 * dom_bytes, "traffic_source": "profiles/r1c_ncu_full_bench_kernels.csv",
+                "note": "timed inside the step, where the quantize+pack kernel of the previous layer shares the SMs with it; alone (--serial) it runs at 0.97",
                 "bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
                 "share_of_step": sum(stat_ms) / max(args.steps, 1) / ms_step if ms_step > 0 else None}
 

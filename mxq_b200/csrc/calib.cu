@@ -340,12 +340,15 @@ extern "C" int mxq_colsumsq_ex(const void* X, int64_t tokens, int64_t cols, int 
       kern<<<grid, kCSThreads, pad, st>>>(Xb, part, tokens, (int)cols, cpr, rows_per_slab);
       return cudaSuccess;
     };
-    // capped occupancy -> the variant whose threads really keep 8 (or, MXQ_STAT_UNROLL=16, 16) loads in flight
+    // capped occupancy -> the variant whose threads really keep 16 loads in flight (96 registers: two
+    // CTAs resident per SM hold 128 KB in flight); MXQ_STAT_UNROLL = 0 / 8 / 16 overrides (profiling)
     const char* ue = getenv("MXQ_STAT_UNROLL");
-    const int variant = ue ? atoi(ue) : (ctas_per_sm < 8 ? 8 : 0);
+    const int variant = ue ? atoi(ue) : (ctas_per_sm < 8 ? 16 : 0);
     cudaError_t e;
     if (dtype == MXQ_F32) e = launch(colsumsq_partial_kernel<float>);
-    else if (dtype == MXQ_BF16) e = variant == 8 ? launch(colsumsq_partial_kernel<__nv_bfloat16, 8, 4>) : launch(colsumsq_partial_kernel<__nv_bfloat16>);
+    else if (dtype == MXQ_BF16) e = variant == 16  ? launch(colsumsq_partial_kernel<__nv_bfloat16, 16, 2>)
+                                    : variant == 8 ? launch(colsumsq_partial_kernel<__nv_bfloat16, 8, 4>)
+                                                   : launch(colsumsq_partial_kernel<__nv_bfloat16>);
     else e = variant == 16  ? launch(colsumsq_partial_kernel<__half, 16, 2>)
              : variant == 8 ? launch(colsumsq_partial_kernel<__half, 8, 4>)
                             : launch(colsumsq_partial_kernel<__half>);

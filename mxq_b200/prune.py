@@ -185,12 +185,14 @@ class LlamaLayerPTQ:
         self.statistics(calib, nsamples, on_stat)
         self.quantize(weights, sink)
 
-    def run_pipelined(self, layers, nsamples: int, sink=None, on_stat=None, ctas_per_sm: int = 8):
+    def run_pipelined(self, layers, nsamples: int, sink=None, on_stat=None, ctas_per_sm: int = 3):
         """Several decoder layers back to back: `layers` = iterable of (weights, calib).  The
         HBM-bound statistics of layer i+1 run on the current stream while the issue-bound
         quantize+pack of layer i runs on a high-priority side stream and takes the SM slots the
         statistics CTAs free up (`ctas_per_sm` shapes the statistics grid, see mxq_colsumsq_ex; measured
-        on B200: 8 = one wave 71.7 ms / pass, 16 = 71.3, 5 = 74.0, serial 78.4); statistics are
+        on B200: 8 = the full-occupancy kernel, one wave, 71.4 ms / pass; 16 = 71.3; 3 = the variant with
+        16 loads in flight per thread, two CTAs resident per SM, 69.7 ms; 0 = shared-memory ring kernel
+        92 ms; serial 78.4); statistics are
         double-buffered, the quantizer's output
         buffers are reused layer after layer exactly as in run() (a sink must consume them on the
         side stream)."""
