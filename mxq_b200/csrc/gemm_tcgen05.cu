@@ -1131,7 +1131,14 @@ template <bool kDenseB>
 static int launch(const void* x, const Params& p, cudaStream_t st, void* workspace = nullptr,
                   size_t workspace_bytes = 0) {
   // More than one M tile: CTA pairs (M = 256 MMAs).  MXQ_GEMM_SINGLE forces the one-CTA kernel.
-  if (p.M > BM && !getenv("MXQ_GEMM_SINGLE")) return launch_pair<kDenseB>(x, p, st, workspace, workspace_bytes);
+  // M <= 256 has only OC / 256 tiles (16 for a 4096-row linear): with a workspace the pair kernel cuts
+  // them along K and fills the machine (half of each M = 256 MMA is padding there, the K split is
+  // worth more: profiles/r1_probe_gemm_smallm.txt).
+  if (!getenv("MXQ_GEMM_SINGLE")) {
+    if (p.M > BM) return launch_pair<kDenseB>(x, p, st, workspace, workspace_bytes);
+    if (!kDenseB && workspace && make_plan(p.M, p.IC, p.OC, true).split >= 2)
+      return launch_pair<kDenseB>(x, p, st, workspace, workspace_bytes);
+  }
   CUtensorMap mx, mw;
   int rc = make_map(&mx, x, p.M, p.IC, BM);
   if (rc) return rc;
@@ -1158,7 +1165,7 @@ static int launch(const void* x, const Params& p, cudaStream_t st, void* workspa
 using namespace mxq;
 
 extern "C" size_t mxq_gemm_workspace_bytes(int64_t M, int64_t IC, int64_t OC) {
-  if (M <= gemm::BM || IC <= 0 || OC <= 0 || M > INT32_MAX || OC > INT32_MAX || IC > (1 << 24)) return 256;
+  if (M <= 0 || IC <= 0 || OC <= 0 || M > INT32_MAX || OC > INT32_MAX || IC > (1 << 24)) return 256;
   return gemm::plan_workspace_bytes(gemm::make_plan((int)M, (int)IC, (int)OC, true));
 }
 
