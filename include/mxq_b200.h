@@ -209,6 +209,9 @@ MXQ_API int mxq_awq_gemv(const void* x, const int32_t* kernel, const void* scale
 MXQ_API size_t mxq_gemm_workspace_bytes(int64_t M, int64_t IC, int64_t OC);
 MXQ_API int mxq_gemm(const void* x, mxq_packed_t w, void* y, int64_t M, int64_t IC, int64_t OC,
              void* workspace, size_t workspace_bytes, void* stream);
+/* The tile schedule mxq_gemm would use on a device with `sms` SMs (pure host arithmetic, no device
+ * needed): out5 = {M tiles, N tiles, tiles, whole tiles, K slices per remaining tile}. */
+MXQ_API int mxq_gemm_plan(int64_t M, int64_t IC, int64_t OC, int sms, int32_t* out5, size_t* workspace_bytes);
 
 /* Column-sharded GEMM fused with its all-gather: this rank owns output columns
  * [col0, col0 + OC) of a [M, ldy] result; the epilogue stores every tile into each of the `npeers`

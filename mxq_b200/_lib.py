@@ -26,7 +26,7 @@ SYMBOLS = [
     "mxq_allocate_bits_workspace_bytes", "mxq_allocate_bits",
     "mxq_ptq_workspace_bytes", "mxq_ptq_quant", "mxq_rowquant",
     "mxq_pack_workspace_bytes", "mxq_pack", "mxq_ptq_quant_pack", "mxq_unpack", "mxq_gemv", "mxq_gemv_ex", "mxq_gemv_grouped", "mxq_awq_gemv",
-    "mxq_gemm_workspace_bytes", "mxq_gemm", "mxq_gemm_scatter", "mxq_gemm_multicast", "mxq_gemm_dense",
+    "mxq_gemm_workspace_bytes", "mxq_gemm", "mxq_gemm_plan", "mxq_gemm_scatter", "mxq_gemm_multicast", "mxq_gemm_dense",
 ]
 
 
@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
     L.mxq_gemm.argtypes = [vp, PackedC, vp, i64, i64, i64, vp, sz, vp]
     L.mxq_gemm_dense.argtypes = [vp, vp, vp, i64, i64, i64, vp]
     L.mxq_gemm_scatter.argtypes = [vp, PackedC, C.POINTER(vp), i32, i64, i64, i64, i64, i64, vp, sz, vp]
+    L.mxq_gemm_plan.argtypes = [i64, i64, i64, i32, C.POINTER(C.c_int32), C.POINTER(sz)]
     L.mxq_gemm_multicast.argtypes = [vp, PackedC, vp, i64, i64, i64, i64, i64, vp, sz, vp]
     for name in SYMBOLS:
         if getattr(L, name).restype is C.c_int:

@@ -1049,34 +1049,37 @@ struct Plan {
   size_t partial_bytes;
 };
 constexpr size_t kPartialSlotBytes = (size_t)pair::BM * pair::BN * 4;   // one CTA's fp32 accumulators
-static Plan make_plan(int M, int IC, int OC, bool allow_split) {
+static Plan make_plan_for(int M, int IC, int OC, int sms, bool allow_split) {
   Plan pl{};
   pl.mt = ceil_div(M, 2 * pair::BM);
   pl.nt = ceil_div(OC, pair::BN);
   pl.tiles = pl.mt * pl.nt;
   pl.full = pl.tiles;
   pl.split = 1;
-  if (allow_split && IC % (4 * BK) == 0) {
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms >= 2) {
-      const int pairs = sms / 2;
-      const int tail = pl.tiles % pairs;
-      const int groups = IC / (4 * BK);
-      if (tail > 0) {
-        int s = pairs / tail;
-        if (s > groups / 4) s = groups / 4;      // a slice keeps >= 16 K blocks of main loop
-        if (s > 8) s = 8;
-        if (const char* e = getenv("MXQ_GEMM_SPLIT")) s = atoi(e) < s ? atoi(e) : s;   // profiling knob
-        if (s >= 2) {
-          pl.split = s;
-          pl.full = pl.tiles - tail;
-          pl.partial_bytes = (size_t)tail * s * 2 * kPartialSlotBytes;
-        }
+  if (allow_split && IC % (4 * BK) == 0 && sms >= 2) {
+    const int pairs = sms / 2;
+    const int tail = pl.tiles % pairs;
+    const int groups = IC / (4 * BK);
+    if (tail > 0) {
+      int s = pairs / tail;
+      if (s > groups / 4) s = groups / 4;      // a slice keeps >= 16 K blocks of main loop
+      if (s > 8) s = 8;
+      if (const char* e = getenv("MXQ_GEMM_SPLIT")) s = atoi(e) < s ? atoi(e) : s;   // profiling knob
+      if (s >= 2) {
+        pl.split = s;
+        pl.full = pl.tiles - tail;
+        pl.partial_bytes = (size_t)tail * s * 2 * kPartialSlotBytes;
       }
     }
   }
   return pl;
+}
+static Plan make_plan(int M, int IC, int OC, bool allow_split) {
+  int dev = 0, sms = 0;
+  if (!allow_split || cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    sms = 0;
+  return make_plan_for(M, IC, OC, sms, allow_split);
 }
 static size_t plan_workspace_bytes(const Plan& pl) {
   return pl.split > 1 ? 256 + pl.partial_bytes : 256;
@@ -1167,6 +1170,15 @@ using namespace mxq;
 extern "C" size_t mxq_gemm_workspace_bytes(int64_t M, int64_t IC, int64_t OC) {
   if (M <= 0 || IC <= 0 || OC <= 0 || M > INT32_MAX || OC > INT32_MAX || IC > (1 << 24)) return 256;
   return gemm::plan_workspace_bytes(gemm::make_plan((int)M, (int)IC, (int)OC, true));
+}
+
+extern "C" int mxq_gemm_plan(int64_t M, int64_t IC, int64_t OC, int sms, int32_t* out5, size_t* workspace_bytes) {
+  if (M <= 0 || IC <= 0 || OC <= 0 || IC % 64 || M > INT32_MAX || OC > INT32_MAX || IC > (1 << 24) || sms < 0) return MXQ_E_SHAPE;
+  if (!out5) return MXQ_E_NULL;
+  const gemm::Plan pl = gemm::make_plan_for((int)M, (int)IC, (int)OC, sms, true);
+  out5[0] = pl.mt; out5[1] = pl.nt; out5[2] = pl.tiles; out5[3] = pl.full; out5[4] = pl.split;
+  if (workspace_bytes) *workspace_bytes = gemm::plan_workspace_bytes(pl);
+  return MXQ_OK;
 }
 
 extern "C" int mxq_gemm(const void* x, mxq_packed_t w, void* y, int64_t M, int64_t IC, int64_t OC,

@@ -126,3 +126,41 @@ def test_segquant_plan_follows_reference_slicing():
     assert ops.segquant_plan((2, 20, 16), "asym", False) == (40, 16, 20, 16)
     assert ops.segquant_plan((2, 3, 8, 16), "sym", False) == (6, 128, 1, 1)
     assert ops.segquant_plan((4, 256), "asym", True) == (1, 1024, 1, 1)
+
+
+def test_gemm_tile_plan_host_arithmetic():
+    """mxq_gemm_plan (no device needed): whole tiles + K-split tail tiles of the CTA-pair GEMM on a
+    148-SM part -- the tail is cut so that its clusters fit one wave, slices keep >= 16 K blocks, and
+    the workspace holds one fp32 accumulator slot per (tail tile, slice, CTA of the pair)."""
+    import ctypes as C
+    L = _lib.lib()
+
+    def plan(M, IC, OC, sms=148):
+        out = (C.c_int32 * 5)()
+        ws = C.c_size_t(0)
+        assert L.mxq_gemm_plan(M, IC, OC, sms, out, C.byref(ws)) == 0
+        return list(out), ws.value
+
+    slot = 256 * 256 * 4
+    # Llama-2-7B at M = 2048: 4096^2 = 64 tiles (one partial wave, nothing to cut) ...
+    assert plan(2048, 4096, 4096) == ([4, 16, 64, 64, 1], 256)
+    # ... gate/up 11008 x 4096 = 172 tiles = 2 waves of 74 + 24 tail tiles x 3 K slices
+    p, ws = plan(2048, 4096, 11008)
+    assert p == [4, 43, 172, 148, 3] and ws == 256 + 24 * 3 * 2 * slot
+    # short M: 16 tiles x 4 slices (K = 4096 allows at most 4 slices of 16 K blocks)
+    assert plan(128, 4096, 4096)[0] == [1, 16, 16, 0, 4]
+    assert plan(128, 8192, 1024)[0] == [1, 4, 4, 0, 8]          # capped at 8 slices
+    assert plan(2048, 1024, 4096)[0][4] == 1                     # K too short to cut
+    assert plan(2048, 4096 + 64, 11008)[0][4] == 1               # IC % 256 != 0: generic K path, no cut
+    for M, IC, OC in ((2048, 8192, 28672), (512, 4096, 2560), (1000, 4096, 1304), (2048, 28672, 1024)):
+        (mt, nt, tiles, full, split), ws = plan(M, IC, OC)
+        tail = tiles - full
+        assert tiles == mt * nt and 0 <= full <= tiles and 1 <= split <= 8
+        if split > 1:
+            assert tail * split <= 74 and full % 74 == 0 and (IC // 64) // split >= 16
+            assert ws == 256 + tail * split * 2 * slot
+        else:
+            assert full == tiles and ws == 256
+    # another part: 132 SMs
+    assert plan(2048, 4096, 11008, sms=132)[0] == [4, 43, 172, 172, 1]     # 40 tail tiles on 66 pairs: no cut
+    assert L.mxq_gemm_plan(0, 4096, 4096, 148, (C.c_int32 * 5)(), None) != 0
