@@ -68,15 +68,35 @@ __global__ void __launch_bounds__(256) pool_prepass_kernel(const __half* __restr
   if (row < rows) {
     const size_t roff = (size_t)row * cols;
     const int npc = kRef ? nchunks / 4 : nchunks;
-    for (int m = lane; m < npc; m += 32) {
-      const int c = kRef ? ((m >> 1) * 4 + 3) * 2 + (m & 1) : m;
-      if (!kRef && !(gbits[c >> 1] & MXQ_POOL_FLAG)) continue;
+    auto take = [&](const uint4& wv, const uint2& dm) {
       float f[8];
-      DT<__half>::unpack(*reinterpret_cast<const uint4*>(W + roff + c * 8), f);
-      const uint2 dm = *reinterpret_cast<const uint2*>(dead + c * 8);
+      DT<__half>::unpack(wv, f);
       apply_dead8(dm.x, dm.y, f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) { mn = fminf(mn, f[e]); mx = fmaxf(mx, f[e]); }
+    };
+    int m = lane;
+    if (kRef) {
+      // four chunks per lane in flight: a row's pooled quarter is 1 KB (4096 columns) to 2.7 KB, and a
+      // warp walking it one load at a time is a chain of DRAM latencies
+      for (; m + 96 < npc; m += 128) {
+        uint4 wv[4];
+        uint2 dm[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int mm = m + 32 * u;
+          const int c = ((mm >> 1) * 4 + 3) * 2 + (mm & 1);
+          wv[u] = ld_stream(W + roff + c * 8);
+          dm[u] = *reinterpret_cast<const uint2*>(dead + c * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) take(wv[u], dm[u]);
+      }
+    }
+    for (; m < npc; m += 32) {
+      const int c = kRef ? ((m >> 1) * 4 + 3) * 2 + (m & 1) : m;
+      if (!kRef && !(gbits[c >> 1] & MXQ_POOL_FLAG)) continue;
+      take(*reinterpret_cast<const uint4*>(W + roff + c * 8), *reinterpret_cast<const uint2*>(dead + c * 8));
     }
   }
   mn = warp_min(mn);
