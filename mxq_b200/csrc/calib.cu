@@ -69,10 +69,11 @@ __global__ void __launch_bounds__(kCSThreads, kMinBlocks) colsumsq_partial_kerne
 // slab of whole rows; R consecutive rows are one contiguous byte range, fetched by ONE 1-D TMA bulk
 // copy (cp.async.bulk + mbarrier tx-count) into a ring of up to 8 stages (<= 192 KB per SM in
 // flight).  Thread t owns 16-byte column chunks t, t + 256, ... (conflict-free LDS.128) and keeps
-// their sums in registers.  The CTA needs ~10 K registers and a few issue slots, so the issue-bound
-// quantize+pack tile kernel of the previous layer runs ALONGSIDE on the same SMs (two of its CTAs
-// fit) instead of taking turns with it -- the register-buffered kernel above needs every warp slot
-// of the SM for its memory parallelism (32 registers, ~3 loads in flight per thread).
+// their sums in registers.  The CTA needs ~10 K registers, so the issue-bound quantize+pack tile
+// kernel of the previous layer can run ALONGSIDE on the same SMs (two of its CTAs fit).  Measured: it
+// does, but this kernel is then -- and even alone, 5.0 TB/s -- bound by its 8 consumer warps
+// (LDS -> convert -> FMA chains, 2 warps per scheduler), not by the ring; kept as the measured
+// alternative (mxq_colsumsq_ex ctas_per_sm = 0), not used by default.
 // ---------------------------------------------------------------------------------------------
 constexpr int kRingStageMax = 32 * 1024;
 constexpr int kRingBytesMax = 192 * 1024;
@@ -363,8 +364,10 @@ extern "C" int mxq_colsumsq_ex(const void* X, int64_t tokens, int64_t cols, int 
 extern "C" int mxq_colsumsq(const void* X, int64_t tokens, int64_t cols, int dtype, float* out,
                             float prev_scale, float add_scale, int accumulate, void* workspace,
                             size_t workspace_bytes, void* stream) {
-  return mxq_colsumsq_ex(X, tokens, cols, dtype, out, prev_scale, add_scale, accumulate, 8, workspace,
-                         workspace_bytes, stream);
+  // 3 = sixteen loads in flight per thread, two CTAs resident per SM, 1.5 waves: 6.8 TB/s on a 2.1 GB
+  // fp16 input against 6.4 TB/s for the full-occupancy variant (8); fp32 inputs only have that one
+  return mxq_colsumsq_ex(X, tokens, cols, dtype, out, prev_scale, add_scale, accumulate, dtype == MXQ_F32 ? 8 : 3,
+                         workspace, workspace_bytes, stream);
 }
 
 extern "C" int mxq_wanda_metric(const void* W, const float* scaler_row, float* out, int64_t rows,
