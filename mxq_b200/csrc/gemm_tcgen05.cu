@@ -1061,9 +1061,13 @@ static Plan make_plan_for(int M, int IC, int OC, int sms, bool allow_split) {
     const int tail = pl.tiles % pairs;
     const int groups = IC / (4 * BK);
     if (tail > 0) {
+      int smax = groups / 4;                   // a slice keeps >= 16 K blocks of main loop
+      if (smax > 8) smax = 8;
       int s = pairs / tail;
-      if (s > groups / 4) s = groups / 4;      // a slice keeps >= 16 K blocks of main loop
-      if (s > 8) s = 8;
+      if (s > smax) s = smax;
+      // (More than half a wave of tiles, e.g. 43 on 74 pairs, cut 3 ways = 2 waves of a third was
+      // measured too: 62-66 us against 52-55 us whole -- 66 MB of partials cost more than the idle
+      // pairs.  Only tails whose slices fit ONE wave are cut.)
       if (const char* e = getenv("MXQ_GEMM_SPLIT")) s = atoi(e) < s ? atoi(e) : s;   // profiling knob
       if (s >= 2) {
         pl.split = s;

@@ -152,6 +152,9 @@ def test_gemm_tile_plan_host_arithmetic():
     assert plan(128, 8192, 1024)[0] == [1, 4, 4, 0, 8]          # capped at 8 slices
     assert plan(2048, 1024, 4096)[0][4] == 1                     # K too short to cut
     assert plan(2048, 4096 + 64, 11008)[0][4] == 1               # IC % 256 != 0: generic K path, no cut
+    # 43 tiles (more than half a wave): cutting them 3 ways was measured slower than whole tiles
+    assert plan(512, 4096, 11008)[0] == [1, 43, 43, 43, 1]
+    assert plan(2048, 8192, 3584)[0][4] == 1                    # 56 tiles, K = 8192: nothing gained
     for M, IC, OC in ((2048, 8192, 28672), (512, 4096, 2560), (1000, 4096, 1304), (2048, 28672, 1024)):
         (mt, nt, tiles, full, split), ws = plan(M, IC, OC)
         tail = tiles - full
