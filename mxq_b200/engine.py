@@ -5,7 +5,6 @@ binding: any in_features % 64 == 0 (not only 4096), shape/dtype/device are check
 kernels run on torch's current stream instead of the legacy default stream."""
 from __future__ import annotations
 
-import torch
 
 from . import ops
 

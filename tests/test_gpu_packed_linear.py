@@ -1,6 +1,5 @@
 """GPU: packed-checkpoint path: MXQLinear routes to the GEMV / tcgen05 GEMM kernels
 and equals x @ decode(pack(W))^T; save/load round trip is bit-exact."""
-import numpy as np
 import pytest
 import torch
 import torch.nn as nn
