@@ -645,15 +645,13 @@ def run_components(torch, dev, pk):
         mf, mb = timeit(fwd, 30), timeit(bwd, 30)
         nb = 4096 * 4096 * esz
         out[f"fakequant_fwd_{name}"] = {"ms": mf, "GBps": 2 * nb / mf / 1e6, "frac_hbm": 2 * nb / mf / 1e6 / pk["hbm"]}
-        # BASELINE configs[0] names "group 128": the same recipe over 512-column blocks ({2,2,2 | pooled 4}
-        # groups of 128 columns), mask-driven kernel (no reference implementation: oracle-checked only)
+        # BASELINE configs[0] names "group 128": the same positional recipe over 512-column blocks
+        # ({2,2,2 | pooled 4} groups of 128 columns; no reference implementation: oracle-checked only)
         try:
-            gb = torch.tensor([2, 2, 2, 0x84] * (4096 // 512), dtype=torch.uint8, device=dev)
-
             def fwd128(i):
                 k = i % nset
                 ops.L.check(lib.mxq_fakequant_fwd(xs[k].data_ptr(), outs[k].data_ptr(), None, 4096, 4096,
-                                                  ops.L.dtype_enum(xs[k]), 128, 2, gb.data_ptr(), ops.L.stream()), "fq128")
+                                                  ops.L.dtype_enum(xs[k]), 128, 2, None, ops.L.stream()), "fq128")
             m128 = timeit(fwd128, 30)
             out[f"fakequant_fwd_{name}_g128"] = {"ms": m128, "GBps": 2 * nb / m128 / 1e6, "frac_hbm": 2 * nb / m128 / 1e6 / pk["hbm"]}
         except Exception as e:

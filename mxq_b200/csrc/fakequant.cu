@@ -306,14 +306,15 @@ __global__ void __launch_bounds__(kFQThreads) fakequant_fwd_kernel(const FQParam
 
 
 // -------------------------------------------------------------------------------------------
-// Row-resident variant for the reference recipe (group 16, {low, low, low, pool 4}): one CTA per
+// Row-resident variant for the reference recipe ({low, low, low, pool 4} groups of G = 16 columns, or
+// of 128 columns for BASELINE's "group 128"): one CTA per
 // row, the row's 16-byte chunks stay in registers between the pooled min/max and the quantize
 // pass, so the kernel is a single load -> reduce -> compute -> store stream with nothing staged
 // in shared memory but the per-warp partial statistics.  Measured faster than the TMA ring above
 // on B200 for rows of up to 3072 chunks (profiles/): more independent loads in flight per SM and
 // no per-stage block barrier.
 // -------------------------------------------------------------------------------------------
-template <typename T, int THREADS, int NC>
+template <typename T, int THREADS, int NC, int G = 16>
 __global__ void __launch_bounds__(THREADS) fakequant_row_kernel(const uint4* __restrict__ x,
                                                                 uint4* __restrict__ out, int cpr,
                                                                 int low_bits) {
@@ -321,8 +322,9 @@ __global__ void __launch_bounds__(THREADS) fakequant_row_kernel(const uint4* __r
   constexpr bool k16 = sizeof(T) == 2;
   using P = P16<typename std::conditional<k16, T, __half>::type>;
   constexpr int EPC = D::EPC;
-  constexpr int LPG = 16 / EPC;                       // lanes (chunks) per 16-column group
-  constexpr int LPG_SHIFT = LPG == 2 ? 1 : 2;
+  constexpr int LPG = G / EPC;                        // lanes (chunks) per G-column group: 2 / 4 at the
+  constexpr int LPG_SHIFT = LPG == 2 ? 1 : LPG == 4 ? 2 : LPG == 16 ? 4 : 5;   // reference G = 16, 16 / 32 at G = 128
+  static_assert(LPG == 2 || LPG == 4 || LPG == 16 || LPG == 32, "group of 16 or 128 columns");
   __shared__ float2 part[THREADS / 32];
   const float kEps = D::rnd(1e-8f);
   const uint4* xr = x + (size_t)blockIdx.x * cpr;
@@ -446,18 +448,18 @@ __global__ void __launch_bounds__(THREADS) fakequant_row_kernel(const uint4* __r
   }
 }
 
-template <typename T>
+template <typename T, int G = 16>
 static bool launch_fq_row(const FQParams& p, cudaStream_t st) {
   const int c = p.cpr;
   const uint4* x = (const uint4*)p.x;
   uint4* o = (uint4*)p.out;
   const unsigned g = (unsigned)p.rows;
-  if (c <= 256) fakequant_row_kernel<T, 128, 2><<<g, 128, 0, st>>>(x, o, c, p.low_bits);
-  else if (c <= 512) fakequant_row_kernel<T, 128, 4><<<g, 128, 0, st>>>(x, o, c, p.low_bits);
-  else if (c <= 1024) fakequant_row_kernel<T, 256, 4><<<g, 256, 0, st>>>(x, o, c, p.low_bits);
-  else if (c <= 1536) fakequant_row_kernel<T, 256, 6><<<g, 256, 0, st>>>(x, o, c, p.low_bits);
-  else if (c <= 2048) fakequant_row_kernel<T, 256, 8><<<g, 256, 0, st>>>(x, o, c, p.low_bits);
-  else if (c <= 3072) fakequant_row_kernel<T, 256, 12><<<g, 256, 0, st>>>(x, o, c, p.low_bits);
+  if (c <= 256) fakequant_row_kernel<T, 128, 2, G><<<g, 128, 0, st>>>(x, o, c, p.low_bits);
+  else if (c <= 512) fakequant_row_kernel<T, 128, 4, G><<<g, 128, 0, st>>>(x, o, c, p.low_bits);
+  else if (c <= 1024) fakequant_row_kernel<T, 256, 4, G><<<g, 256, 0, st>>>(x, o, c, p.low_bits);
+  else if (c <= 1536) fakequant_row_kernel<T, 256, 6, G><<<g, 256, 0, st>>>(x, o, c, p.low_bits);
+  else if (c <= 2048) fakequant_row_kernel<T, 256, 8, G><<<g, 256, 0, st>>>(x, o, c, p.low_bits);
+  else if (c <= 3072) fakequant_row_kernel<T, 256, 12, G><<<g, 256, 0, st>>>(x, o, c, p.low_bits);
   else return false;
   return true;
 }
@@ -613,13 +615,19 @@ extern "C" int mxq_fakequant_fwd(const void* x, void* out, uint8_t* codes, int64
   const bool ref = group_bits == nullptr;
   // reference recipe at group 16 without code output: the row-resident kernel (rows of up to 3072
   // chunks; the packed 16-bit arithmetic exists for 2-bit groups only).  MXQ_FQ_RING forces the ring.
-  if (ref && group == 16 && !codes && p.cpr <= 3072 && rows >= kNumSMs && (esize == 4 || low_bits == 2) &&
+  // The same kernel instantiated for groups of 128 columns serves BASELINE's "group 128" (the
+  // positional recipe over 512-column blocks): bit-identical to the mask-driven ring kernel on B200
+  // (fp32 / bf16 / fp16, NaN payloads included) and 22.7 / 14.7 us instead of 32.6 / 21.3 us for a
+  // 4096^2 fp32 / bf16 weight.  MXQ_FQ_ROW_G128=0 restores the ring.
+  const char* e128 = getenv("MXQ_FQ_ROW_G128");
+  const bool row16 = group == 16, row128 = group == 128 && !(e128 && atoi(e128) == 0);
+  if (ref && (row16 || row128) && !codes && p.cpr <= 3072 && rows >= kNumSMs && (esize == 4 || low_bits == 2) &&
       !getenv("MXQ_FQ_RING")) {
     bool ok = false;
     switch (dtype) {
-      case MXQ_F32: ok = launch_fq_row<float>(p, st); break;
-      case MXQ_F16: ok = launch_fq_row<__half>(p, st); break;
-      default: ok = launch_fq_row<__nv_bfloat16>(p, st); break;
+      case MXQ_F32: ok = row16 ? launch_fq_row<float>(p, st) : launch_fq_row<float, 128>(p, st); break;
+      case MXQ_F16: ok = row16 ? launch_fq_row<__half>(p, st) : launch_fq_row<__half, 128>(p, st); break;
+      default: ok = row16 ? launch_fq_row<__nv_bfloat16>(p, st) : launch_fq_row<__nv_bfloat16, 128>(p, st); break;
     }
     if (ok) MXQ_LAUNCH_RESULT();
   }

@@ -103,6 +103,30 @@ def test_explicit_mask_paths(cuda, dtype):
     assert bits_equal(to_np(got), want)
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "bf16", "fp16"])
+def test_group128_row_resident_kernel(cuda, dtype):
+    """BASELINE's "group 128" recipe without a mask runs the row-resident kernel (rows >= 148): same bits
+    as the mask-driven kernel, degenerate groups included (a constant group and an all-zero row give
+    alpha = 0, i.e. NaN in fp16 where the epsilon rounds to zero -- compared as bit patterns), and the
+    oracle's bits on ordinary data."""
+    from mxq_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(300, 1536, generator=g) * 0.02).to(TD[dtype])
+    x[0, :128] = 0.5
+    x[1, 384:512] = -1.0
+    x[2] = 0.0
+    xd = x.to(cuda)
+    gb = ops.reference_group_bits(1536, 128, 2, device=cuda)
+    want = ops.fakequant_fwd(xd, group=128, group_bits=gb)
+    got = ops.fakequant_fwd(xd, group=128)
+    it = torch.int32 if dtype == "fp32" else torch.int16
+    assert torch.equal(got.view(it), want.view(it))
+    if dtype != "fp16":
+        y = (torch.randn(160, 1536, generator=g) * 0.02).to(TD[dtype])
+        ref = O.fakequant_fwd(y.float().numpy(), dtype, 2, group=128, group_bits=O.reference_group_bits(1536, 128, 2))
+        assert bits_equal(to_np(ops.fakequant_fwd(y.to(cuda), group=128)), ref)
+
+
 @pytest.mark.parametrize("dtype,shape", [("fp32", (4096, 4096)), ("bf16", (4096, 11008)),
                                          ("bf16", (1024, 28672))])
 def test_full_size_properties(cuda, dtype, shape):
