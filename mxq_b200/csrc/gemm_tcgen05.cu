@@ -19,6 +19,13 @@
 //                 packed words are prefetched into registers.  Afterwards the same warps run
 //                 the epilogue: tcgen05.ld 32x32b.x32 -> fp16 -> 128-bit global stores.
 // The dequantized operand never touches HBM: weights cost 0.3756 B each per M tile.
+//
+// M > 256 (and M <= 256 when a workspace allows a K split) runs the CTA-pair variant further down
+// (cta_group::2, one M = 256 MMA per K step across two SMs).  Its tile schedule (pair::Plan) cuts the
+// tiles of a partly filled last wave along K and adds the fp32 partials in a second pass
+// (gemm_split_reduce_kernel); for the column-sharded multi-GPU case the epilogue -- or that second
+// pass -- stores whole 512-byte row segments into every peer's buffer or once into the buffer's
+// NVSwitch multicast mapping (mxq_gemm_scatter / mxq_gemm_multicast).
 #include <cuda.h>
 
 #include <cstdlib>
