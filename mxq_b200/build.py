@@ -27,6 +27,7 @@ SOURCES = {
     "ptq.cu": ["-fmad=false"],
     "pack.cu": ["-fmad=false"],
     "gemv.cu": [],
+    "gemv_mma.cu": [],
     "gemm_tcgen05.cu": [],
 }
 

@@ -775,8 +775,10 @@ static int gemv_check_packed(const mxq_packed_t& w) {
   return MXQ_OK;
 }
 
-extern "C" int mxq_gemv_grouped(const void* x, const mxq_packed_t* w, void* const* y, int n, int64_t B,
-                                int64_t IC, int64_t OC, unsigned flags, void* stream) {
+// Generic-shape path (any IC % 64 == 0) behind mxq_gemv_grouped (gemv_mma.cu dispatches).
+namespace mxq {
+int gemv_ring_grouped(const void* x, const mxq_packed_t* w, void* const* y, int n, int64_t B, int64_t IC,
+                      int64_t OC, unsigned flags, void* stream) {
   if (B < 0 || IC < 0 || OC < 0 || n < 0 || n > kGemvMaxGroup) return MXQ_E_SHAPE;
   if (B == 0 || OC == 0 || n == 0) return MXQ_OK;
   MXQ_CHECK_PTR(x);
@@ -795,21 +797,11 @@ extern "C" int mxq_gemv_grouped(const void* x, const mxq_packed_t* w, void* cons
   if (B == 2) return launch_gemv<2>(xh, w, y, n, (int)B, (int)IC, (int)OC, pdl, st);
   return launch_gemv<4>(xh, w, y, n, (int)B, (int)IC, (int)OC, pdl, st);
 }
-
-extern "C" int mxq_gemv_ex(const void* x, mxq_packed_t w, void* y, int64_t B, int64_t IC,
-                           int64_t OC, unsigned flags, void* stream) {
-  void* ys[1] = {y};
-  return mxq_gemv_grouped(x, &w, ys, 1, B, IC, OC, flags, stream);
-}
+}  // namespace mxq
 
 // profiling aid, not part of the documented surface: copies the stamps of the last traced launch
 extern "C" __attribute__((visibility("default"))) int mxq_debug_gemv_trace(unsigned long long* host_out) {
   return (int)cudaMemcpyFromSymbol(host_out, g_gemv_trace, sizeof(unsigned long long) * 4 * 160);
-}
-
-extern "C" int mxq_gemv(const void* x, mxq_packed_t w, void* y, int64_t B, int64_t IC, int64_t OC,
-                        void* stream) {
-  return mxq_gemv_ex(x, w, y, B, IC, OC, 0u, stream);
 }
 
 extern "C" int mxq_awq_gemv(const void* x, const int32_t* kernel, const void* scales,
