@@ -86,9 +86,6 @@ def lib() -> C.CDLL:
     L.mxq_gemm_scatter.argtypes = [vp, PackedC, C.POINTER(vp), i32, i64, i64, i64, i64, i64, vp, sz, vp]
     L.mxq_gemm_plan.argtypes = [i64, i64, i64, i32, C.POINTER(C.c_int32), C.POINTER(sz)]
     L.mxq_gemm_multicast.argtypes = [vp, PackedC, vp, i64, i64, i64, i64, i64, vp, sz, vp]
-    for name in SYMBOLS:
-        if getattr(L, name).restype is C.c_int:
-            pass
     _lib = L
     return L
 
@@ -107,9 +104,40 @@ def dtype_enum(t: torch.Tensor) -> int:
 
 
 def require_cuda(*tensors: torch.Tensor) -> None:
+    """Every tensor of a call must live on ONE CUDA device (the kernels take raw pointers)."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("mxq_b200 kernels need CUDA tensors (no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"mxq_b200: tensors of one call live on different devices ({dev} and {t.device})")
+
+
+class on:
+    """`with on(tensor) as stream:` -- makes the tensor's device current for the launch (the reference
+    model may be spread over GPUs by `hf_device_map`, mxq_quant/lib/prune.py:371-378) and yields
+    torch's current stream ON THAT DEVICE; a no-op switch when it already is the current device."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, t: torch.Tensor):
+        if not t.is_cuda:
+            raise RuntimeError("mxq_b200 kernels need CUDA tensors (no CPU fallback)")
+        self.idx = t.device.index
+
+    def __enter__(self) -> int:
+        self.prev = torch.cuda.current_device()
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.idx)
+        return torch.cuda.current_stream(self.idx).cuda_stream
+
+    def __exit__(self, *exc):
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def ptr(t) -> int | None:

@@ -64,10 +64,12 @@ struct Plan {
   int gxl;      // CTAs per linear
   int ximg;     // bytes of one batch row's activation image
   int dbg;      // profiling only (MXQ_GEMV_DBG & 8): per-CTA %globaltimer stamps
+  int early;    // griddepcontrol.launch_dependents at the top of the kernel instead of after the wait
 };
 
 // Profiling only: {start, copies issued, waited, staged, loop done, done} per CTA.
 __device__ unsigned long long g_trace[6 * 160];
+__device__ long long g_itrace[8 * 16 * 6];     // [warp][iteration][stamp] clock64 of CTA 1 (MXQ_GEMV_DBG & 64)
 __device__ __forceinline__ unsigned long long gtimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_mma_kernel(const __half* __r
   const uint32_t ring_s = smem_u32(ring);
   const bool trace = kDbg && (plan.dbg & 8) && threadIdx.x == 0 && blockIdx.x < 160 && blockIdx.y == 0;
   if (trace) g_trace[blockIdx.x * 6 + 0] = gtimer_ns();
+  if (plan.early) griddep_launch_dependents();
 
   // ---- copy pattern: per-lane byte offsets relative to (first row group of the tile, ks = 0) ----
   const uint32_t w_row = (uint32_t)nblk * 16, wl_row = (uint32_t)nblk * 4, zs_row = (uint32_t)nchunk * 128,
@@ -284,8 +287,8 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_mma_kernel(const __half* __r
       ++issued;
       if (++i_ks == nqb) { i_ks = 0; ++i_tile; }
       if (++i_slot == kRing) i_slot = 0;
+      cp_async_commit();
     }
-    cp_async_commit();
   };
 
   // ---- prologue: weights only (allowed before the dependency wait) -----------------------------
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_mma_kernel(const __half* __r
 
   if (trace) g_trace[blockIdx.x * 6 + 1] = gtimer_ns();
   griddep_wait();
-  griddep_launch_dependents();
+  if (!plan.early) griddep_launch_dependents();
   if (trace) g_trace[blockIdx.x * 6 + 2] = gtimer_ns();
 #pragma unroll
   for (int i = 0; i < kRing; ++i) if (i >= pre) issue();
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_mma_kernel(const __half* __r
     }
     if (threadIdx.x < NB * 4) reinterpret_cast<uint32_t*>(ximg + (size_t)(threadIdx.x >> 2) * plan.ximg)[threadIdx.x & 3] = 0u;
   }
-  cp_async_wait<kRing>();                                    // this thread's piece of the row tables
+  if (issued - u_begin >= kRing) cp_async_wait<kRing>(); else cp_async_wait<0>();   // this thread's piece of the row tables
   __syncthreads();
   if (trace) g_trace[blockIdx.x * 6 + 3] = gtimer_ns();
 
@@ -370,9 +373,16 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_mma_kernel(const __half* __r
   };
   if (u_begin < u_end) tile_params(tile);
 
+  const bool itrace = kDbg && (plan.dbg & 64) && blockIdx.x == 1 && blockIdx.y == 0 && lane == 0;
   for (int u = u_begin; u < u_end; ++u) {
-    cp_async_wait<kRing - 1>();
+    long long* it = g_itrace + ((size_t)warp * 16 + min(u - u_begin, 15)) * 6;
+    if (itrace) it[0] = clock64();
+    // groups of this thread, oldest first: row tables, then one per issued unit.  While units are
+    // still being issued exactly kRing - 1 younger groups follow the one consumed now; afterwards
+    // everything outstanding is awaited at once (at most kRing - 1 units, all needed soon).
+    if (issued < u_end) cp_async_wait<kRing - 1>(); else cp_async_wait<0>();
     __syncwarp();
+    if (itrace) it[1] = clock64();
     const unsigned char* s = ring + (size_t)slot * kUnitBytes;
     const int p = (ks >> 3) & 1;                             // half-word / byte of the metadata words
     // A side
@@ -390,6 +400,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_mma_kernel(const __half* __r
     const int blk = ks * 4 + t;
     const uint32_t xoff = bact ? (uint32_t)(16 + blk * 128 + (g & 1) * 16) : 0u;
     const uint32_t xstep = bact ? 32u : 0u;
+    if (itrace) it[2] = clock64() + ((wa.x ^ wb.w ^ wla ^ wlb ^ zs[0] ^ zs[1] ^ z2 ^ s2h[2]) == 0x12345u);
     if (kDbg && (plan.dbg & 1)) {                            // profiling: data movement only
       acc[0][0] += __uint_as_float(wa.x ^ wa.y ^ wa.z ^ wa.w ^ wb.x ^ wb.y ^ wb.z ^ wb.w ^ wla ^ wlb ^ zs[0] ^ zs[1] ^ z2 ^
                                    s2h[0] ^ s2h[1] ^ s2h[2]);
@@ -437,8 +448,10 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_mma_kernel(const __half* __r
         }
       }
     }
+    if (itrace) it[3] = clock64() + (acc[0][0] == 1.2345f);
     __syncwarp();                                            // every lane is done with the slot
     issue();
+    if (itrace) it[4] = clock64();
     if (++slot == kRing) slot = 0;
     if (++ks == nqb) {                                       // tile finished (for this warp)
       flush(tile);
@@ -448,6 +461,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_mma_kernel(const __half* __r
     } else if (u + 1 == u_end) {
       flush(tile);
     }
+    if (itrace) it[5] = clock64();
   }
   __syncthreads();
   if (trace) g_trace[blockIdx.x * 6 + 4] = gtimer_ns();
@@ -470,9 +484,18 @@ constexpr size_t kSmemPerSM = 227 * 1024, kSmemCtaReserve = 1024;
 template <int NB, bool kDbg>
 int launch_k(const __half* x, const Group& G, int n, int B, int IC, int OC, bool pdl, const Plan& plan, size_t smem,
              cudaStream_t st) {
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(gemv_mma_kernel<NB, kDbg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // One shared-memory configuration for every shape: the opt-in limit is raised once to half an SM
+  // and the carve-out is pinned to "max shared", so consecutive GEMVs of different shapes never make
+  // the SM re-partition L1 / shared memory (which would serialise them under PDL).
+  static bool configured = false;                    // benign race: idempotent attribute writes
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemv_mma_kernel<NB, kDbg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(kSmemPerSM - kSmemCtaReserve));
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(gemv_mma_kernel<NB, kDbg>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n * plan.gxl), (unsigned)ceil_div(B, NB));
@@ -502,6 +525,8 @@ int launch(const __half* x, const mxq_packed_t* ws, void* const* ys, int n, int 
   plan.ximg = ((16 + ng * 32 + ng * 8) + 127) & ~127;
   plan.dbg = 0;
   if (const char* e = getenv("MXQ_GEMV_DBG")) plan.dbg = atoi(e);
+  plan.early = 0;
+  if (const char* e = getenv("MXQ_GEMV_EARLY")) plan.early = atoi(e);
   const int rows_cta = plan.q * 4;
   const size_t rowtab = (size_t)((rows_cta * 2 + (rows_cta / 8 + 2) * 4 + 15) & ~15);
   const size_t smem = (size_t)kWarps * kRing * kUnitBytes + rowtab + (size_t)NB * plan.ximg +
@@ -544,10 +569,14 @@ extern "C" int mxq_gemv_grouped(const void* x, const mxq_packed_t* w, void* cons
     if (rc) return rc;
   }
   if (IC % 64 || OC % 8 || IC == 0 || IC > (1 << 24) || OC > INT32_MAX || B > 65535 * 4) return MXQ_E_SHAPE;
-  const char* impl = getenv("MXQ_GEMV_IMPL");
-  const bool ring_only = impl && impl[0] == 'r';
-  // the IMMA kernel needs 256-column quad-blocks and a CTA share that fits beside its activation image
-  if (ring_only || IC % 256 != 0 || IC > 32768) return gemv_ring_grouped(x, w, y, n, B, IC, OC, flags, stream);
+  const char* impl = getenv("MXQ_GEMV_IMPL");                 // "ring" / "mma": force one kernel (profiling)
+  const bool ring_only = impl && impl[0] == 'r', mma_only = impl && impl[0] == 'm';
+  // The IMMA kernel needs 256-column quad-blocks.  Its 8-warp CTA builds the activation image in
+  // ceil(IC / 4096) rounds; measured on B200 (profiles/r2_gemv_chain.txt) it wins up to IC = 8192
+  // (4096^2: 3.9 vs 4.2 us, 11008 x 4096: 8.3 vs 8.7 us) and loses at IC = 11008 (9.3 vs 8.6 us),
+  // where the 14-warp ring kernel stages the activations faster.
+  if (ring_only || IC % 256 != 0 || IC > 32768 || (!mma_only && IC > 8192))
+    return gemv_ring_grouped(x, w, y, n, B, IC, OC, flags, stream);
   cudaStream_t st = as_stream(stream);
   const __half* xh = (const __half*)x;
   const bool pdl = !(flags & MXQ_GEMV_NO_PDL);
@@ -562,6 +591,10 @@ extern "C" int mxq_gemv_grouped(const void* x, const mxq_packed_t* w, void* cons
 // profiling aid, not part of the documented surface
 extern "C" __attribute__((visibility("default"))) int mxq_debug_gemv2_trace(unsigned long long* host_out) {
   return (int)cudaMemcpyFromSymbol(host_out, g2::g_trace, sizeof(unsigned long long) * 6 * 160);
+}
+
+extern "C" __attribute__((visibility("default"))) int mxq_debug_gemv2_itrace(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g2::g_itrace, sizeof(long long) * 8 * 16 * 6);
 }
 
 extern "C" int mxq_gemv_ex(const void* x, mxq_packed_t w, void* y, int64_t B, int64_t IC, int64_t OC,

@@ -76,26 +76,34 @@ class ColumnShardedMXQLinear:
 
     # -- fused path: the GEMM epilogue writes its tile into every peer's output over NVLink ------
     def _symm_out(self, M: int, device):
-        if self._symm is not None and self._symm[0].shape[0] == M:
+        """TWO symmetric [M, OC_total] buffers used by alternate calls.  Call k+1 stores into the
+        other buffer, so a fast rank cannot overwrite a result a slower peer is still reading; by
+        the time call k+2 reuses call k's buffer every rank has passed the barrier that ends call
+        k+1, which on each rank's stream comes after its reads of call k's result."""
+        if self._symm is not None and self._symm[0][0].shape[0] == M:
             return self._symm
         import torch.distributed._symmetric_memory as symm_mem
-        t = symm_mem.empty((M, self.OC_total), dtype=torch.float16, device=device)
         grp = self.group if self.group is not None else dist.group.WORLD
-        try:
-            hdl = symm_mem.rendezvous(t, grp)
-        except TypeError:
-            hdl = symm_mem.rendezvous(t, grp.group_name)
-        self._symm = (t, hdl)
+        bufs = []
+        for _ in range(2):
+            t = symm_mem.empty((M, self.OC_total), dtype=torch.float16, device=device)
+            try:
+                hdl = symm_mem.rendezvous(t, grp)
+            except TypeError:
+                hdl = symm_mem.rendezvous(t, grp.group_name)
+            bufs.append((t, hdl))
+        self._symm = bufs
         return self._symm
 
     def _fused_state(self, M: int, device):
         if self._fused is not None and self._fused["M"] == M:
             return self._fused
         import ctypes as C
-        out, hdl = self._symm_out(M, device)
-        self._fused = dict(M=M, out=out, hdl=hdl, pstruct=self.ops.L.packed_struct(self.p),
-                           ptrs=(C.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs]),
-                           mc=int(getattr(hdl, "multicast_ptr", 0) or 0))
+        bufs = self._symm_out(M, device)
+        self._fused = dict(M=M, pstruct=self.ops.L.packed_struct(self.p), parity=0,
+                           out=[t for t, _ in bufs], hdl=[h for _, h in bufs],
+                           ptrs=[(C.c_void_p * self.world)(*[int(p) for p in h.buffer_ptrs]) for _, h in bufs],
+                           mc=[int(getattr(h, "multicast_ptr", 0) or 0) for _, h in bufs])
         return self._fused
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -111,21 +119,24 @@ class ColumnShardedMXQLinear:
             # Python call path must not be the longer one
             st = self._fused_state(M, x.device)
             L = ops.L
-            if x.dtype != torch.float16 or not x.is_contiguous() or x.shape[1] != self.IC:
-                raise ValueError(f"x must be contiguous fp16 [M, {self.IC}]")
+            if not x.is_cuda or x.dtype != torch.float16 or not x.is_contiguous() or x.dim() != 2 or x.shape[1] != self.IC:
+                raise ValueError(f"x must be a contiguous CUDA fp16 [M, {self.IC}] tensor")
             col0 = self.rank * self.OC_local
-            if self.mode == "mc":
-                if not st["mc"]:
-                    raise RuntimeError("symmetric memory has no multicast mapping on this system (mode='mc')")
-                rc = L.lib().mxq_gemm_multicast(x.data_ptr(), st["pstruct"], st["mc"], M, self.IC, self.OC_local,
-                                                self.OC_total, col0, self._ws.data_ptr(), self._ws.numel(), L.stream())
-            else:
-                rc = L.lib().mxq_gemm_scatter(x.data_ptr(), st["pstruct"], st["ptrs"], self.world, M, self.IC,
-                                              self.OC_local, self.OC_total, col0, self._ws.data_ptr(),
-                                              self._ws.numel(), L.stream())
+            b = st["parity"]
+            st["parity"] = b ^ 1
+            with L.on(x) as stream:
+                if self.mode == "mc":
+                    if not st["mc"][b]:
+                        raise RuntimeError("symmetric memory has no multicast mapping on this system (mode='mc')")
+                    rc = L.lib().mxq_gemm_multicast(x.data_ptr(), st["pstruct"], st["mc"][b], M, self.IC, self.OC_local,
+                                                    self.OC_total, col0, self._ws.data_ptr(), self._ws.numel(), stream)
+                else:
+                    rc = L.lib().mxq_gemm_scatter(x.data_ptr(), st["pstruct"], st["ptrs"][b], self.world, M, self.IC,
+                                                  self.OC_local, self.OC_total, col0, self._ws.data_ptr(),
+                                                  self._ws.numel(), stream)
             L.check(rc, "mxq_gemm_" + ("multicast" if self.mode == "mc" else "scatter"))
-            st["hdl"].barrier(channel=0)    # every rank's tiles have landed in every rank's buffer
-            return st["out"]
+            st["hdl"][b].barrier(channel=0)    # every rank's tiles have landed in every rank's buffer
+            return st["out"][b]
         y_local = ops.gemm(x, self.p, workspace=self._ws, validate=False)
         return gather_columns(y_local, self.group)
 

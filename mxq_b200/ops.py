@@ -36,8 +36,9 @@ def fakequant_fwd(x: torch.Tensor, num_bits: int = 2, group: int = 16, group_bit
         raise ValueError("in_features must be a multiple of 64 for the mixed 2/4-bit recipe")
     out = torch.empty_like(x)
     codes = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if return_codes else None
-    rc = L.lib().mxq_fakequant_fwd(L.ptr(x), L.ptr(out), L.ptr(codes), rows, cols, L.dtype_enum(x),
-                                   group, num_bits, L.ptr(group_bits), L.stream())
+    with L.on(x) as st:
+        rc = L.lib().mxq_fakequant_fwd(L.ptr(x), L.ptr(out), L.ptr(codes), rows, cols, L.dtype_enum(x),
+                                       group, num_bits, L.ptr(group_bits), st)
     L.check(rc, "mxq_fakequant_fwd")
     return (out, codes) if return_codes else out
 
@@ -50,8 +51,9 @@ def ste_bwd(grad_out: torch.Tensor, x: torch.Tensor, lo: float, hi: float) -> to
     g = grad_out.contiguous()
     xc = x.contiguous()
     gi = torch.empty_like(g)
-    rc = L.lib().mxq_ste_bwd(L.ptr(g), L.ptr(xc), L.ptr(gi), g.numel(), L.dtype_enum(g),
-                             float(lo), float(hi), L.stream())
+    with L.on(grad_out) as st:
+        rc = L.lib().mxq_ste_bwd(L.ptr(g), L.ptr(xc), L.ptr(gi), g.numel(), L.dtype_enum(g),
+                                 float(lo), float(hi), st)
     L.check(rc, "mxq_ste_bwd")
     return gi
 
@@ -96,9 +98,10 @@ def segquant_fwd(x: torch.Tensor, mode: str, bits: int, nseg: int, seglen: int, 
     need = L.lib().mxq_segquant_workspace_bytes(nseg, seglen, L.dtype_enum(x))
     if workspace is None or workspace.numel() < need:
         workspace = _ws(need, x.device)
-    rc = L.lib().mxq_segquant_fwd(L.ptr(x), L.ptr(out), nseg, seglen, L.dtype_enum(x),
-                                  0 if mode == "sym" else 1, int(bits), int(period), int(valid),
-                                  L.ptr(workspace), workspace.numel(), L.stream())
+    with L.on(x) as st:
+        rc = L.lib().mxq_segquant_fwd(L.ptr(x), L.ptr(out), nseg, seglen, L.dtype_enum(x),
+                                      0 if mode == "sym" else 1, int(bits), int(period), int(valid),
+                                      L.ptr(workspace), workspace.numel(), st)
     L.check(rc, "mxq_segquant_fwd")
     return out
 
@@ -115,10 +118,11 @@ def colsumsq(X: torch.Tensor, out: torch.Tensor | None = None, prev_scale: float
     need = L.lib().mxq_colsumsq_workspace_bytes(tokens, cols)
     if workspace is None or workspace.numel() * workspace.element_size() < need:
         workspace = _ws(need, X.device)
-    rc = L.lib().mxq_colsumsq(L.ptr(X2), tokens, cols, L.dtype_enum(X2), L.ptr(out),
-                              float(prev_scale), float(add_scale), int(accumulate),
-                              L.ptr(workspace), workspace.numel() * workspace.element_size(),
-                              L.stream())
+    with L.on(X) as st:
+        rc = L.lib().mxq_colsumsq(L.ptr(X2), tokens, cols, L.dtype_enum(X2), L.ptr(out),
+                                  float(prev_scale), float(add_scale), int(accumulate),
+                                  L.ptr(workspace), workspace.numel() * workspace.element_size(),
+                                  st)
     L.check(rc, "mxq_colsumsq")
     return out
 
@@ -128,8 +132,9 @@ def wanda_metric(W: torch.Tensor, scaler_row: torch.Tensor) -> torch.Tensor:
     L.require_cuda(W, scaler_row)
     W = W.contiguous()
     out = torch.empty(W.shape, dtype=torch.float32, device=W.device)
-    rc = L.lib().mxq_wanda_metric(L.ptr(W), L.ptr(scaler_row.contiguous().float()), L.ptr(out),
-                                  W.shape[0], W.shape[1], L.dtype_enum(W), L.stream())
+    with L.on(W) as st:
+        rc = L.lib().mxq_wanda_metric(L.ptr(W), L.ptr(scaler_row.contiguous().float()), L.ptr(out),
+                                      W.shape[0], W.shape[1], L.dtype_enum(W), st)
     L.check(rc, "mxq_wanda_metric")
     return out
 
@@ -150,8 +155,9 @@ def allocate_group_bits(W: torch.Tensor, scaler_row: torch.Tensor | None = None,
     gb = torch.empty(cols // group, dtype=torch.uint8, device=W.device)
     imp = torch.empty(cols // group, dtype=torch.float64, device=W.device) if return_importance else None
     ws = _ws(L.lib().mxq_allocate_bits_workspace_bytes(cols), W.device)
-    rc = L.lib().mxq_allocate_bits(L.ptr(W), L.ptr(sr), rows, cols, group, low_bits, L.ptr(gb), L.ptr(imp),
-                                   L.ptr(ws), ws.numel(), L.stream())
+    with L.on(W) as st:
+        rc = L.lib().mxq_allocate_bits(L.ptr(W), L.ptr(sr), rows, cols, group, low_bits, L.ptr(gb), L.ptr(imp),
+                                       L.ptr(ws), ws.numel(), st)
     L.check(rc, "mxq_allocate_bits")
     return (gb, imp) if return_importance else gb
 
@@ -170,9 +176,10 @@ def ptq_quant(W: torch.Tensor, colstat: torch.Tensor | None = None, low_bits: in
     need = L.lib().mxq_ptq_workspace_bytes(rows, cols)
     if workspace is None or workspace.numel() < need:
         workspace = _ws(need, W.device)
-    rc = L.lib().mxq_ptq_quant(L.ptr(W), L.ptr(Wq), L.ptr(codes), L.ptr(colstat), rows, cols, group,
-                               low_bits, L.ptr(group_bits), L.ptr(workspace), workspace.numel(),
-                               L.stream())
+    with L.on(W) as st:
+        rc = L.lib().mxq_ptq_quant(L.ptr(W), L.ptr(Wq), L.ptr(codes), L.ptr(colstat), rows, cols, group,
+                                   low_bits, L.ptr(group_bits), L.ptr(workspace), workspace.numel(),
+                                   st)
     L.check(rc, "mxq_ptq_quant")
     return (Wq, codes) if return_codes else Wq
 
@@ -187,8 +194,9 @@ def rowquant(x: torch.Tensor, bits: int, qq_scale_bits: int | None = 4):
     codes = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
     scale = torch.empty(rows, dtype=torch.float32, device=x.device)
     zero = torch.empty(rows, dtype=torch.float32, device=x.device)
-    rc = L.lib().mxq_rowquant(L.ptr(x), L.ptr(y), L.ptr(codes), L.ptr(scale), L.ptr(zero), rows,
-                              cols, bits, qq_scale_bits or 0, L.stream())
+    with L.on(x) as st:
+        rc = L.lib().mxq_rowquant(L.ptr(x), L.ptr(y), L.ptr(codes), L.ptr(scale), L.ptr(zero), rows,
+                                  cols, bits, qq_scale_bits or 0, st)
     L.check(rc, "mxq_rowquant")
     return y, codes, scale, zero
 
@@ -222,8 +230,9 @@ def pack(W: torch.Tensor, colstat: torch.Tensor | None = None, out: dict | None 
     need = L.lib().mxq_pack_workspace_bytes(OC, IC)
     if workspace is None or workspace.numel() < need:
         workspace = _ws(need, W.device)
-    rc = L.lib().mxq_pack(L.ptr(W), L.ptr(colstat), OC, IC, L.packed_struct(out), L.ptr(workspace),
-                          workspace.numel(), L.stream())
+    with L.on(W) as st:
+        rc = L.lib().mxq_pack(L.ptr(W), L.ptr(colstat), OC, IC, L.packed_struct(out), L.ptr(workspace),
+                              workspace.numel(), st)
     L.check(rc, "mxq_pack")
     return out
 
@@ -243,9 +252,10 @@ def ptq_quant_pack(W: torch.Tensor, colstat: torch.Tensor | None = None, out=Non
     need = L.lib().mxq_ptq_workspace_bytes(rows, cols)
     if workspace is None or workspace.numel() < need:
         workspace = _ws(need, W.device)
-    rc = L.lib().mxq_ptq_quant_pack(L.ptr(W), L.ptr(Wq), L.ptr(codes), L.ptr(colstat), rows, cols,
-                                    L.packed_struct(packed), L.ptr(workspace), workspace.numel(),
-                                    L.stream())
+    with L.on(W) as st:
+        rc = L.lib().mxq_ptq_quant_pack(L.ptr(W), L.ptr(Wq), L.ptr(codes), L.ptr(colstat), rows, cols,
+                                        L.packed_struct(packed), L.ptr(workspace), workspace.numel(),
+                                        st)
     L.check(rc, "mxq_ptq_quant_pack")
     return (Wq, packed, codes) if return_codes else (Wq, packed)
 
@@ -270,15 +280,18 @@ def _check_packed(p: dict):
 def unpack(p: dict, dtype=torch.float32) -> torch.Tensor:
     OC, IC = _check_packed(p)
     out = torch.empty((OC, IC), dtype=dtype, device=p["weight"].device)
-    rc = L.lib().mxq_unpack(L.packed_struct(p), OC, IC, L.ptr(out), L.dtype_enum(out), L.stream())
+    with L.on(out) as st:
+        rc = L.lib().mxq_unpack(L.packed_struct(p), OC, IC, L.ptr(out), L.dtype_enum(out), st)
     L.check(rc, "mxq_unpack")
     return out
 
 
 def gemv(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, validate: bool = True,
-         pdl: bool = True):
-    """y[B, OC] = x[B, IC] @ dequant(W)^T, fp16.  pdl: programmatic dependent launch (the kernel may
-    prefetch its weights into L2 while the previous kernel of the stream is still running)."""
+         pdl: bool = False):
+    """y[B, OC] = x[B, IC] @ dequant(W)^T, fp16.  pdl=True: programmatic dependent launch -- the
+    kernel copies its packed weights into shared memory while the previous kernel of the stream is
+    still running, which is only correct if that kernel does not write them (a decode chain over
+    resident weights); x and y are touched after the dependency wait in either mode."""
     OC, IC = _check_packed(p) if validate else _packed_dims(p)
     L.require_cuda(x)
     if x.dtype != torch.float16 or x.dim() != 2 or x.shape[1] != IC:
@@ -287,13 +300,14 @@ def gemv(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, validate: bo
     B = x.shape[0]
     if out is None:
         out = torch.empty((B, OC), dtype=torch.float16, device=x.device)
-    rc = L.lib().mxq_gemv_ex(L.ptr(x), L.packed_struct(p), L.ptr(out), B, IC, OC,
-                             0 if pdl else 1, L.stream())
+    with L.on(x) as st:
+        rc = L.lib().mxq_gemv_ex(L.ptr(x), L.packed_struct(p), L.ptr(out), B, IC, OC,
+                                 0 if pdl else 1, st)
     L.check(rc, "mxq_gemv")
     return out
 
 
-def gemv_grouped(x: torch.Tensor, ps: list, outs: list | None = None, pdl: bool = True, validate: bool = True):
+def gemv_grouped(x: torch.Tensor, ps: list, outs: list | None = None, pdl: bool = False, validate: bool = True):
     """Decode GEMV of up to 4 packed linears of one shape sharing the activation x (q/k/v, gate/up)
     in ONE launch.  Returns the list of fp16 [B, OC] outputs."""
     import ctypes as C
@@ -312,7 +326,8 @@ def gemv_grouped(x: torch.Tensor, ps: list, outs: list | None = None, pdl: bool 
         outs = [torch.empty((B, OC), dtype=torch.float16, device=x.device) for _ in ps]
     warr = (L.PackedC * len(ps))(*[L.packed_struct(p) for p in ps])
     yarr = (C.c_void_p * len(ps))(*[o.data_ptr() for o in outs])
-    rc = L.lib().mxq_gemv_grouped(L.ptr(x), warr, yarr, len(ps), B, IC, OC, 0 if pdl else 1, L.stream())
+    with L.on(x) as st:
+        rc = L.lib().mxq_gemv_grouped(L.ptr(x), warr, yarr, len(ps), B, IC, OC, 0 if pdl else 1, st)
     L.check(rc, "mxq_gemv_grouped")
     return outs
 
@@ -347,7 +362,8 @@ def gemm(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, workspace=No
         wptr, wbytes = L.ptr(workspace), workspace.numel()
     else:
         wptr, wbytes = None, 0
-    rc = L.lib().mxq_gemm(L.ptr(x), L.packed_struct(p), L.ptr(out), M, IC, OC, wptr, wbytes, L.stream())
+    with L.on(x) as st:
+        rc = L.lib().mxq_gemm(L.ptr(x), L.packed_struct(p), L.ptr(out), M, IC, OC, wptr, wbytes, st)
     L.check(rc, "mxq_gemm")
     return out
 
@@ -360,9 +376,10 @@ def gemm_scatter(x: torch.Tensor, p: dict, peer_ptrs: list, ldy: int, col0: int,
     L.require_cuda(x)
     x = x.contiguous()
     arr = (C.c_void_p * len(peer_ptrs))(*[int(a) for a in peer_ptrs])
-    rc = L.lib().mxq_gemm_scatter(L.ptr(x), L.packed_struct(p), arr, len(peer_ptrs), x.shape[0], IC, OC,
-                                  ldy, col0, L.ptr(workspace), 0 if workspace is None else workspace.numel(),
-                                  L.stream())
+    with L.on(x) as st:
+        rc = L.lib().mxq_gemm_scatter(L.ptr(x), L.packed_struct(p), arr, len(peer_ptrs), x.shape[0], IC, OC,
+                                      ldy, col0, L.ptr(workspace), 0 if workspace is None else workspace.numel(),
+                                      st)
     L.check(rc, "mxq_gemm_scatter")
 
 
@@ -375,9 +392,10 @@ def gemm_multicast(x: torch.Tensor, p: dict, multicast_ptr: int, ldy: int, col0:
     if not multicast_ptr:
         raise RuntimeError("gemm_multicast needs a multicast mapping (symmetric memory without NVSwitch multicast support)")
     x = x.contiguous()
-    rc = L.lib().mxq_gemm_multicast(L.ptr(x), L.packed_struct(p), int(multicast_ptr), x.shape[0], IC, OC,
-                                    ldy, col0, L.ptr(workspace), 0 if workspace is None else workspace.numel(),
-                                    L.stream())
+    with L.on(x) as st:
+        rc = L.lib().mxq_gemm_multicast(L.ptr(x), L.packed_struct(p), int(multicast_ptr), x.shape[0], IC, OC,
+                                        ldy, col0, L.ptr(workspace), 0 if workspace is None else workspace.numel(),
+                                        st)
     L.check(rc, "mxq_gemm_multicast")
 
 
@@ -388,7 +406,8 @@ def gemm_dense(x: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
     M, IC = x.shape
     OC = W.shape[0]
     out = torch.empty((M, OC), dtype=torch.float16, device=x.device)
-    rc = L.lib().mxq_gemm_dense(L.ptr(x), L.ptr(W), L.ptr(out), M, IC, OC, L.stream())
+    with L.on(x) as st:
+        rc = L.lib().mxq_gemm_dense(L.ptr(x), L.ptr(W), L.ptr(out), M, IC, OC, st)
     L.check(rc, "mxq_gemm_dense")
     return out
 
@@ -401,8 +420,9 @@ def awq_gemv(x: torch.Tensor, kernel: torch.Tensor, scales: torch.Tensor, zeros:
     B, IC = x.shape
     OC = kernel.shape[0]
     out = torch.empty((B, OC), dtype=torch.float16, device=x.device)
-    rc = L.lib().mxq_awq_gemv(L.ptr(x), L.ptr(kernel.contiguous()), L.ptr(scales.contiguous()),
-                              L.ptr(zeros.contiguous()), L.ptr(out), B, IC, OC, group_size,
-                              L.stream())
+    with L.on(x) as st:
+        rc = L.lib().mxq_awq_gemv(L.ptr(x), L.ptr(kernel.contiguous()), L.ptr(scales.contiguous()),
+                                  L.ptr(zeros.contiguous()), L.ptr(out), B, IC, OC, group_size,
+                                  st)
     L.check(rc, "mxq_awq_gemv")
     return out

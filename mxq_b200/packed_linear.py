@@ -35,6 +35,21 @@ class MXQLinear(nn.Module):
         for k, (shape, dt) in ops.packed_shapes(out_features, in_features).items():
             self.register_buffer(k, torch.zeros(shape, dtype=dt, device=device))
         self._ws = None
+        self._checked = False
+        # programmatic dependent launch lets the GEMV fetch its packed weights while the previous
+        # kernel of the stream still runs: only legal when that kernel does not write them, so it is
+        # opt-in (a decode loop over resident weights sets `module.pdl = True`)
+        self.pdl = False
+
+    def _apply(self, fn, recurse=True):
+        """nn.Module.to(dtype) / .half() / .bfloat16() / .float() cast floating buffers; the packed
+        fp16 scale tensors are part of a bit-exact storage format, so only their DEVICE follows."""
+        def keep_dtype(t):
+            r = fn(t)
+            return r if r.dtype == t.dtype else t.to(device=r.device)
+        self._ws = None
+        self._checked = False
+        return super()._apply(keep_dtype, recurse)
 
     @property
     def packed(self) -> dict:
@@ -49,6 +64,8 @@ class MXQLinear(nn.Module):
         return m
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """The kernels compute in fp16 (fp32 accumulation) like the reference binding
+        (gemv_mxq_cuda.cu:242-256); other input dtypes are cast in and the result is cast back."""
         if not x.is_cuda:
             raise RuntimeError("MXQLinear needs CUDA tensors (no CPU fallback)")
         lead = x.shape[:-1]
@@ -56,15 +73,19 @@ class MXQLinear(nn.Module):
         if x2.dtype != torch.float16:
             x2 = x2.half()
         if x2.shape[0] == 0:
-            return x.new_zeros((*lead, self.out_features), dtype=torch.float16)
+            return x.new_zeros((*lead, self.out_features))
+        if not self._checked:
+            ops._check_packed(self.packed)          # once per (re)materialisation of the buffers
+            self._checked = True
         if x2.shape[0] <= self.GEMV_MAX_TOKENS:
-            y = ops.gemv(x2, self.packed, validate=False)
+            y = ops.gemv(x2, self.packed, validate=False, pdl=self.pdl)
         else:
             need = ops.gemm_workspace_bytes(x2.shape[0], self.in_features, self.out_features)
             if self._ws is None or self._ws.device != x2.device or self._ws.numel() < need:
                 self._ws = torch.empty(need, dtype=torch.uint8, device=x2.device)
             y = ops.gemm(x2, self.packed, workspace=self._ws, validate=False)
-        return y.reshape(*lead, self.out_features)
+        y = y.reshape(*lead, self.out_features)
+        return y if x.dtype == torch.float16 else y.to(x.dtype)
 
     def dequantize(self, dtype=torch.float16) -> torch.Tensor:
         return ops.unpack(self.packed, dtype)

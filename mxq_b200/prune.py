@@ -30,12 +30,10 @@ def nas_quant(args, model, tokenizer, dev, dataloader=None):
     network access (prune.py:329)."""
     print('Starting ...')
     if dataloader is None:
-        try:
-            from lib.data import get_loaders  # the reference's own loader, if importable
-        except Exception as e:  # pragma: no cover - offline
-            raise RuntimeError("nas_quant needs a calibration dataloader (pass dataloader=...)") from e
-        dataloader, _ = get_loaders(dataset, nsamples=args.nsamples, seed=args.seed, seqlen=2048,
-                                    tokenizer=tokenizer)
+        # the reference downloads wikitext2 here (prune.py:329, lib/data.py: needs the `datasets`
+        # package and network access); data loading is outside this package's scope
+        raise RuntimeError("nas_quant needs a calibration dataloader: pass dataloader=<iterable of "
+                           "(input_ids[1, seqlen], ...) batches>")
     use_cache = model.config.use_cache
     model.config.use_cache = False
     layers = model.model.layers
@@ -162,9 +160,10 @@ class LlamaLayerPTQ:
             X2 = X.reshape(-1, X.shape[-1])
             if on_stat is not None:
                 on_stat(key, X2, True)
-            rc = ops.L.lib().mxq_colsumsq_ex(ops.L.ptr(X2), X2.shape[0], X2.shape[1], ops.L.dtype_enum(X2),
-                                             ops.L.ptr(stats[key]), 0.0, 2.0 / nsamples, 0, ctas_per_sm,
-                                             ops.L.ptr(self.stat_ws), self.stat_ws.numel(), ops.L.stream())
+            with ops.L.on(X2) as st:
+                rc = ops.L.lib().mxq_colsumsq_ex(ops.L.ptr(X2), X2.shape[0], X2.shape[1], ops.L.dtype_enum(X2),
+                                                 ops.L.ptr(stats[key]), 0.0, 2.0 / nsamples, 0, ctas_per_sm,
+                                                 ops.L.ptr(self.stat_ws), self.stat_ws.numel(), st)
             ops.L.check(rc, "mxq_colsumsq")
             if on_stat is not None:
                 on_stat(key, X2, False)

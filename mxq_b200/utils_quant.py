@@ -12,7 +12,18 @@ import torch.nn as nn
 from . import ops
 
 
+# QuantizeLinear passes the constant [-2, 2] (utils_quant.py:636,719) on every forward: one shared
+# CPU tensor and its per-dtype bounds are cached instead of being rebuilt 672 times per QAT step
+_CLIP = torch.tensor([-2.0, 2.0])
+_CLIP_CACHE: dict = {}
+
+
 def _clip_bounds(clip_val, dtype):
+    if clip_val is _CLIP:
+        hit = _CLIP_CACHE.get(dtype)
+        if hit is None:
+            hit = _CLIP_CACHE[dtype] = _clip_bounds(_CLIP.clone(), dtype)
+        return hit
     lo, hi = (float(v) for v in clip_val.detach().to("cpu", torch.float32).tolist())
     if dtype != torch.float32:
         # input.ge(clip_val[1]) compares in the tensor dtype: the 0-dim clip value is cast
@@ -118,14 +129,14 @@ class QuantizeLinear(nn.Linear):
         if self.w_bits >= 32:
             weight = self.weight
         elif self.w_bits >= 2:
-            weight_clip_val = torch.tensor([-2.0, 2.0])          # utils_quant.py:636
+            weight_clip_val = _CLIP                              # utils_quant.py:636
             weight = MXAsymQuantizer.apply(real_weights, weight_clip_val, self.w_bits,
                                            self.weight_layerwise)
         else:
             # w_bits == 1 sign quantizer / BiT-style branch (:649-715): outside the MXQ path.
             raise NotImplementedError("w_bits < 2 is not part of the MXQ hot path")
         if self.a_bits < 32 and self.a_bits > 2:                  # utils_quant.py:717-721
-            act_clip_val = torch.tensor([-2.0, 2.0])
+            act_clip_val = _CLIP
             input_ = self.act_quantizer.apply(input_, act_clip_val, self.a_bits, self.act_layerwise)
         out = nn.functional.linear(input_, weight)
         if self.bias is not None:

@@ -129,6 +129,31 @@ def gen_fasterquant(mxqgpt_mod, layerwrapper):
     print("fasterquant.npz", len(out), "arrays")
 
 
+def gen_fasterquant_blocksize(mxqgpt_mod):
+    """fasterquant with the signature's default blocksize=128 (one 48-wide 2-bit group per block,
+    mxqgpt.py:388,413-415) and with 32 (groups of 32 + 16)."""
+    torch.cuda.synchronize = lambda *a, **k: None
+    out = {}
+    g = torch.Generator().manual_seed(12)
+    w = torch.randn(64, 512, generator=g) * 0.02
+    w[3, :48] = 0.125          # constant 48-wide group
+    w[16:32, 64:112] = 0.01    # 16 rows sharing one scale
+    for bs in (128, 48, 32):
+        layer = torch.nn.Linear(512, 64, bias=False)
+        layer.weight.data = w.to(torch.float16)
+        gpt = mxqgpt_mod.MXQGPT(layer)
+        X = torch.randn(2, 24, 512, generator=g).to(torch.float16)
+        X[:, :, [9, 300]] = 0
+        for j in range(2):
+            gpt.add_batch(X[j], None)
+        gpt.fasterquant(blocksize=bs)
+        out[f"bs{bs}/W"] = w.to(torch.float16).numpy()
+        out[f"bs{bs}/X"] = X.numpy()
+        out[f"bs{bs}/Wq"] = layer.weight.data.numpy()
+    np.savez_compressed(os.path.join(OUT, "fasterquant_blocksize.npz"), **out)
+    print("fasterquant_blocksize.npz", len(out), "arrays")
+
+
 def gen_quantizer(quantizer):
     """Quantizer used directly (a-7): bits 2/4, perchannel, asym, qq_scale_bits=4."""
     out = {}
@@ -210,11 +235,13 @@ def gen_actquant(utils_quant):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    only = sys.argv[1:]
     torch.manual_seed(0)
     torch.set_num_threads(4)
     utils_quant, mxqgpt_mod, layerwrapper, quantizer = _import_reference()
     gen_fakequant(utils_quant)
     gen_fasterquant(mxqgpt_mod, layerwrapper)
+    gen_fasterquant_blocksize(mxqgpt_mod)
     gen_quantizer(quantizer)
     gen_actquant(utils_quant)
 

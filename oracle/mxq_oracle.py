@@ -412,6 +412,35 @@ def fasterquant(W16, dead=None, group: int = 16, low_bits: int = 2,
     return W_out
 
 
+def fasterquant_blocksize(W16, dead=None, blocksize: int = 128):
+    """MXQGPT.fasterquant with a `blocksize` other than 16 (the signature's default is 128,
+    mxqgpt.py:388): inside every 64-column block the 2-bit columns [0, 48) are cut into groups
+    `range(0, 48, blocksize)` (:413-415: 128 -> one 48-wide group, 32 -> 32 + 16), the last 16
+    columns of all blocks are pooled per row as before (:431-436)."""
+    W = np.asarray(W16, dtype=np.float16).astype(F32).copy()
+    N, K = W.shape
+    if K % 64:
+        raise ValueError("columns must be a multiple of 64")
+    if dead is not None:
+        W[:, np.asarray(dead, dtype=bool)] = 0
+    out = W.copy()
+    xb = W.reshape(N, K // 64, 64)
+    ob = out.reshape(N, K // 64, 64)
+    for j0 in range(0, 48, blocksize):
+        j1 = min(j0 + blocksize, 48)
+        seg = xb[:, :, j0:j1]
+        scale, zero = _find_params(seg.min(axis=2), seg.max(axis=2), 3)
+        scale_q = _qq_scale(scale)[0]
+        ob[:, :, j0:j1] = _quant_dequant(seg, scale_q[:, :, None], zero[:, :, None], 3)[0]
+    pool = xb[:, :, 48:]
+    flat = pool.reshape(N, -1)
+    scale, zero = _find_params(flat.min(axis=1), flat.max(axis=1), 15)
+    scale_q = _qq_scale(scale)[0]
+    ob[:, :, 48:] = _quant_dequant(pool, scale_q[:, None, None], zero[:, None, None], 15)[0]
+    with np.errstate(over="ignore"):
+        return out.astype(np.float16)
+
+
 # --------------------------------------------------------------------------------------
 # (a-9) packed mixed 2/4-bit layout   cuda_kernel/csrc/quantization/gemv_mxq_cuda.cu:39-208
 # --------------------------------------------------------------------------------------

@@ -48,6 +48,30 @@ def graph_time(fn, reps=5):
 
 def main():
     which = sys.argv[1:] or ["shapes", "chain", "ref"]
+    if "early" in which:
+        shapes = [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)]
+        nl = 8
+        packs = [[rand_packed(oc, ic) for oc, ic in shapes] for _ in range(nl)]
+        xin = {4096: torch.randn(1, 4096, device=dev).half(), 11008: torch.randn(1, 11008, device=dev).half()}
+        yout = {4096: torch.empty(1, 4096, device=dev, dtype=torch.float16),
+                11008: torch.empty(1, 11008, device=dev, dtype=torch.float16)}
+        gbytes = nl * sum(packed_nbytes(oc, ic) + 2 * (oc + ic) for oc, ic in shapes)
+        os.environ["MXQ_GEMV_IMPL"] = "mma"
+        for early in (0, 1):
+            os.environ["MXQ_GEMV_EARLY"] = str(early)
+            for oc, ic in ((4096, 4096), (11008, 4096), (4096, 11008)):
+                ps = [layer[{(4096, 4096): 0, (11008, 4096): 4, (4096, 11008): 6}[(oc, ic)]] for layer in packs] * 3
+                us = graph_time(lambda: [ops.gemv(xin[ic], p, out=yout[oc], validate=False, pdl=True) for p in ps]) / len(ps)
+                nb = packed_nbytes(oc, ic) + 2 * (oc + ic)
+                print(f"{oc}x{ic} early={early}: {us:.2f} us/gemv = {nb / us / 1e3:.0f} GB/s ({nb / us / 1e3 / HBM:.2f})", flush=True)
+
+            def plain():
+                for layer in packs:
+                    for (oc, ic), p in zip(shapes, layer):
+                        ops.gemv(xin[ic], p, out=yout[oc], validate=False, pdl=True)
+            us = graph_time(plain)
+            print(f"chain 56 launches early={early}: {us:.1f} us = {gbytes / us / 1e3:.0f} GB/s ({gbytes / us / 1e3 / HBM:.2f} of HBM)", flush=True)
+        os.environ.pop("MXQ_GEMV_EARLY")
     if "dbg" in which:
         # profiling modes of the IMMA kernel on same-shape chains: MXQ_GEMV_DBG bit 0 = no arithmetic,
         # bit 2 = no copies, bits 8-10 = units issued before the dependency wait

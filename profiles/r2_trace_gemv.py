@@ -53,3 +53,13 @@ for oc, ic in ((4096, 4096), (4096, 11008)):
         print(f"{oc}x{ic} pdl={int(pdl)} kernel {MID} of the chain, {len(t)} CTAs, ns rel. to first CTA start:")
         for i, name in enumerate(NAMES):
             print(f"   {name:8s} min {t[:, i].min():6d}  mean {t[:, i].mean():8.0f}  max {t[:, i].max():6d}")
+        if int(DBG) & 64:
+            ib = (C.c_longlong * (8 * 16 * 6))()
+            L.lib().mxq_debug_gemv2_itrace(ib)
+            it = np.array(ib, dtype=np.int64).reshape(8, 16, 6)
+            for w in (0, 3, 7):
+                base = it[w, 0, 0]
+                print(f"   warp {w} per-iteration cycles (top, waited, loaded, computed, issued, end) rel. to its first iteration:")
+                for k in range(5):
+                    if it[w, k, 0] > 0 and it[w, k, 0] >= base:
+                        print("      ", [int(v - base) for v in it[w, k]])
