@@ -53,18 +53,24 @@ class MXQGPT:
         """mxqgpt.py:387-448.  ``percdamp`` is unused by the reference too.  ``pack=True`` (an
         extension) additionally packs the ORIGINAL weights into the mixed 2/4-bit layout
         (``self.packed``) before they are replaced by their fake-quantized values."""
-        if blocksize != 16:
-            # nas_quant always passes 16 (prune.py:409).  The default 128 would make one 48-wide
-            # 2-bit group per 64-column block (mxqgpt.py:413-415), a recipe nothing uses.
-            raise NotImplementedError("fasterquant is implemented for blocksize=16 (prune.py:409)")
+        # mxqgpt.py:413-415: the 48 two-bit columns of every 64-column block are cut into groups
+        # range(0, 48, blocksize): 16 (what nas_quant passes, prune.py:409), 32 -> 32 + 16, and
+        # anything >= 48 (the signature's default 128) -> one 48-wide group.
+        width = min(int(blocksize), 48)
+        if width not in (16, 32, 48):
+            raise NotImplementedError("fasterquant: blocksize must be 16, 32 or >= 48")
+        if pack and width != 16:
+            raise ValueError("the packed layout has 16-column groups (gemv_mxq_cuda.cu:131-136): pack=True needs blocksize=16")
         W = self.layer.weight.data
         if W.dtype != torch.float16:
             raise TypeError("MXQGPT.fasterquant expects an fp16 layer (main.py loads the model in fp16)")
-        colstat = self.diagH if self.nsamples > 0 else None
+        # nsamples == 0: H is all zero, so every column is "dead" and W becomes 0 (mxqgpt.py:399-403);
+        # the zero-initialised diagonal reproduces that
+        colstat = self.diagH
         if pack:
             Wq, self.packed = ops.ptq_quant_pack(W, colstat)
         else:
-            Wq = ops.ptq_quant(W, colstat, low_bits=2, group=16)
+            Wq = ops.ptq_quant(W, colstat, low_bits=2, group=width)
         self.layer.weight.data = Wq.reshape(self.layer.weight.shape).to(self.layer.weight.data.dtype)
 
     def free(self):

@@ -165,7 +165,9 @@ def allocate_group_bits(W: torch.Tensor, scaler_row: torch.Tensor | None = None,
 def ptq_quant(W: torch.Tensor, colstat: torch.Tensor | None = None, low_bits: int = 2,
               group: int = 16, group_bits=None, return_codes: bool = False, out=None,
               workspace=None):
-    """MXQGPT.fasterquant(blocksize=16) (mxq_quant/lib/mxqgpt.py:387-448): fp16 in, fp16 out."""
+    """MXQGPT.fasterquant (mxq_quant/lib/mxqgpt.py:387-448): fp16 in, fp16 out.  `group` = width of
+    the 2-bit groups: 16 (blocksize=16, prune.py:409), or 32 / 48 for the reference recipe
+    (blocksize 32 / >= 48: groups inside the 48 low columns of every 64-column block)."""
     L.require_cuda(W, colstat, group_bits)
     if W.dtype != torch.float16:
         raise TypeError("ptq_quant expects fp16 weights (the reference casts back to the weight dtype)")

@@ -108,7 +108,7 @@ def test_group128_row_resident_kernel(cuda, dtype):
     """BASELINE's "group 128" recipe without a mask runs the row-resident kernel (rows >= 148): same bits
     as the mask-driven kernel, degenerate groups included (a constant group and an all-zero row give
     alpha = 0, i.e. NaN in fp16 where the epsilon rounds to zero -- compared as bit patterns).  The
-    mask-driven kernel is the one pinned to the oracle for this recipe (test_explicit_mask_paths)."""
+    both kernels are pinned to the oracle for this recipe (here and in test_explicit_mask_paths)."""
     from mxq_b200 import ops
     g = torch.Generator().manual_seed(11)
     x = (torch.randn(300, 1536, generator=g) * 0.02).to(TD[dtype])
@@ -121,6 +121,9 @@ def test_group128_row_resident_kernel(cuda, dtype):
     got = ops.fakequant_fwd(xd, group=128)
     it = torch.int32 if dtype == "fp32" else torch.int16
     assert torch.equal(got.view(it), want.view(it))
+    # ... and the row-resident kernel itself against the oracle (the bench times THIS kernel)
+    ref = O.fakequant_fwd(x.float().numpy(), dtype, 2, group=128, group_bits=O.reference_group_bits(1536, 128, 2))
+    assert bits_equal(to_np(got), ref)
 
 
 @pytest.mark.parametrize("dtype,shape", [("fp32", (4096, 4096)), ("bf16", (4096, 11008)),

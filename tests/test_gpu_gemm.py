@@ -106,3 +106,49 @@ def test_split_k_mlp_shape_vs_unpack_matmul(cuda):
     y = ops.gemm(x, p).float()
     ref = x.float() @ ops.unpack(p).T
     assert float((y - ref).abs().max() / ref.abs().max()) <= TOL
+
+
+def _outlier_x(M, IC, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((M, IC))
+    ch = rng.choice(IC, 8, replace=False)
+    x[:, ch] *= rng.uniform(20, 100, 8)
+    return x.astype(np.float16)
+
+
+@pytest.mark.parametrize("M,OC,IC", [(512, 512, 4096), (300, 264, 1024), (64, 512, 8192)])
+def test_packed_outlier_activations_per_element(cuda, M, OC, IC):
+    """north_star's tolerance per element, |y - y_ref| <= 1e-3 * sum_k |w_k x_k| (+ the fp16 store),
+    with LLM-like outlier channels.  The GEMM dequantizes the weights to fp16 operands (one rounding
+    of s * (q - z), 2^-11 relative) and accumulates in fp32 on the tensor cores."""
+    from mxq_b200 import ops
+    p = O.random_packed(OC, IC, seed=M + OC + IC)
+    x = _outlier_x(M, IC, seed=IC)
+    ref = O.gemm_mxq_f32(x, p)
+    Wd = np.abs(O.decode_mxq(p).astype(np.float64))
+    bound = 1e-3 * (np.abs(x.astype(np.float64)) @ Wd.T) + np.abs(ref) * 2.0 ** -11
+    y = ops.gemm(torch.from_numpy(x).to(cuda), packed_to_dev(p, cuda)).cpu().numpy().astype(np.float64)
+    err = np.abs(y - ref)
+    assert (err <= bound).all(), f"worst err/bound {float((err / bound).max()):.3f}"
+
+
+@pytest.mark.parametrize("OC,IC", [(4096, 11008), (3584, 8192), (1024, 28672)])
+def test_full_size_more_shapes(cuda, OC, IC):
+    """down_proj (4096 x 11008) and two Llama-2-70B shards at 8 ranks (gate/up 28672/8 x 8192, down_proj
+    8192/8 x 28672) at M = 2048: GEMM == fp32 matmul on the unpacked weights, per element."""
+    from mxq_b200 import ops
+    torch.manual_seed(OC + IC)
+    p = {}
+    for k, (s, d) in ops.packed_shapes(OC, IC).items():
+        if d == torch.float16:
+            p[k] = (torch.rand(s, device=cuda) * 0.009 + 0.001).half()
+        else:
+            p[k] = torch.randint(-2 ** 31, 2 ** 31 - 1, s, device=cuda, dtype=torch.int64).to(torch.int32)
+    x = torch.randn(2048, IC, device=cuda).half()
+    x[:, 100:108] *= 20
+    y = ops.gemm(x, p).float()
+    Wd = ops.unpack(p)                                   # fp32 decode (bit-exact vs the oracle: test_gpu_packed)
+    ref = x.float() @ Wd.T
+    bound = 1e-3 * (x.float().abs() @ Wd.abs().T) + ref.abs() * 2.0 ** -11
+    # the fp32 reference itself carries ~K * 2^-24 relative summation noise: well inside the bound
+    assert bool(((y - ref).abs() <= bound).all()), float(((y - ref).abs() / bound).max())

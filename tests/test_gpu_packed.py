@@ -198,3 +198,94 @@ def test_gemv_grouped_shared_activation(cuda, OC, IC, n, B):
         assert float((y.float() - single).abs().max()) <= 2e-3 * float(np.abs(ref).max())
     with pytest.raises(ValueError):
         ops.gemv_grouped(xd, pd + [packed_to_dev(O.random_packed(OC + 8, IC, seed=1), cuda)][:1] if n < 4 else pd * 2)
+
+
+# ---------------------------------------------------------------------------------------------
+# LLM-like activations: a few channels 20-100x larger than the rest (what bench.py's calibration
+# plants, and what real decoder inputs look like).  north_star states the tolerance per element:
+# |y - y_ref| <= 1e-3 * sum_k |w_k x_k| (+ half an fp16 ulp of the result, which is stored in fp16).
+# The GEMV converts x to block floating point per 16 columns (csrc/gemv_mma.cu); its share of the
+# error is measured separately against the same oracle evaluated on the block-floating x.
+# ---------------------------------------------------------------------------------------------
+def _outlier_x(B, IC, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, IC))
+    ch = rng.choice(IC, 8, replace=False)
+    x[:, ch] *= rng.uniform(20, 100, 8)
+    x[:, ch[0] ^ 1] *= 1e-3          # a tiny neighbour inside an outlier's 16-column group
+    return x.astype(np.float16)
+
+
+def _per_element_bound(x16, p):
+    Wd = np.abs(O.decode_mxq(p).astype(np.float64))
+    return np.abs(x16.astype(np.float64)) @ Wd.T
+
+
+def _block_float(x16):
+    """x as the GEMV sees it: int16 mantissas per 16-column group, scale 2^(E-14), E = exponent of
+    1.0078 * max|x| of the group (csrc/gemv_mma.cu stage_group)."""
+    x = x16.astype(np.float64).reshape(x16.shape[0], -1, 16)
+    gmax = np.minimum(np.abs(x).max(axis=2, keepdims=True), 65504.0) * 1.0078125
+    with np.errstate(divide="ignore"):
+        e = np.floor(np.log2(np.where(gmax > 0, gmax, 1.0)))
+    sc = np.where(gmax > 0, 2.0 ** (e - 14), 0.0)
+    X = np.rint(np.divide(x, sc, out=np.zeros_like(x), where=sc > 0))
+    return (X * sc).reshape(x16.shape)
+
+
+@pytest.mark.parametrize("OC,IC,B", [(4096, 4096, 1), (512, 11008, 2), (256, 8192, 4), (1024, 4096, 3)])
+def test_gemv_outlier_activations_per_element(cuda, OC, IC, B):
+    from mxq_b200 import ops
+    p = O.random_packed(OC, IC, seed=OC ^ IC)
+    x = _outlier_x(B, IC, seed=B + IC)
+    ref = O.gemm_mxq_f32(x, p)
+    bound = 1e-3 * _per_element_bound(x, p) + np.abs(ref) * 2.0 ** -11
+    y = ops.gemv(torch.from_numpy(x).to(cuda), packed_to_dev(p, cuda)).cpu().numpy().astype(np.float64)
+    err = np.abs(y - ref)
+    assert (err <= bound).all(), f"worst err/bound {float((err / bound).max()):.3f}"
+    # share of the block-floating conversion: the exact product of the converted activations
+    xbf = _block_float(x)
+    ref_bf = xbf @ O.decode_mxq(p).astype(np.float64).T
+    conv = np.abs(ref_bf - ref)
+    assert (conv <= 0.05 * bound).all(), f"block-floating share {float((conv / bound).max()):.4f} of the bound"
+    assert (np.abs(y - ref_bf) <= np.abs(ref_bf) * 2.0 ** -11 + 1e-6 * _per_element_bound(x, p)).all(), \
+        "kernel == exact integer arithmetic on the converted activations (up to the fp16 store)"
+
+
+def test_awq_gemv_g32(cuda):
+    """G = 32 (gemv_cuda.cu:45-99): zeros row width rounded up to 4 words (:56), group g = col / 32
+    uses nibble g % 8 of zeros word g / 8 and scale g."""
+    from mxq_b200 import engine
+    rng = np.random.default_rng(32)
+    OC, IC, B, G = 96, 4096, 2, 32
+    ng = IC // G
+    zw = -(-(-(-ng // 8)) // 4) * 4
+    kernel = rng.integers(0, 2 ** 32, (OC, IC // 8), dtype=np.uint64).astype(np.uint32)
+    zeros = rng.integers(0, 2 ** 32, (OC, zw), dtype=np.uint64).astype(np.uint32)
+    scales = rng.uniform(0.001, 0.01, (OC, zw * 8)).astype(np.float16)
+    x = rng.standard_normal((B, IC)).astype(np.float16)
+    q = ((kernel[:, :, None] >> (4 * np.arange(8, dtype=np.uint32))) & 0xF).reshape(OC, IC).astype(np.float64)
+    g = np.arange(IC) // G
+    z = ((zeros[:, g // 8] >> (4 * (g % 8)).astype(np.uint32)) & 0xF).astype(np.float64)
+    Wd = scales.astype(np.float64)[:, g] * (q - z)
+    ref = x.astype(np.float64) @ Wd.T
+    y = engine.gemv_forward_cuda(torch.from_numpy(x).to(cuda), torch.from_numpy(kernel.view(np.int32)).to(cuda),
+                                 torch.from_numpy(scales).to(cuda), torch.from_numpy(zeros.view(np.int32)).to(cuda), G)
+    bound = 1e-3 * (np.abs(x.astype(np.float64)) @ np.abs(Wd).T) + np.abs(ref) * 2.0 ** -11
+    assert (np.abs(y.cpu().numpy().astype(np.float64) - ref) <= bound).all()
+
+
+def test_gemv_generic_and_imma_kernels_agree(cuda, monkeypatch):
+    """IC % 256 == 0 shapes can run either kernel (MXQ_GEMV_IMPL): both meet the oracle, and both
+    compute exact integer group sums, so they differ only in the fp32 summation order."""
+    from mxq_b200 import ops
+    OC, IC = 1024, 4096
+    p = O.random_packed(OC, IC, seed=99)
+    x = _outlier_x(1, IC, seed=3)
+    pd, xd = packed_to_dev(p, cuda), torch.from_numpy(x).to(cuda)
+    ref = O.gemm_mxq_f32(x, p)
+    bound = 1e-3 * _per_element_bound(x, p) + np.abs(ref) * 2.0 ** -11
+    for impl in ("mma", "ring"):
+        monkeypatch.setenv("MXQ_GEMV_IMPL", impl)
+        y = ops.gemv(xd, pd).cpu().numpy().astype(np.float64)
+        assert (np.abs(y - ref) <= bound).all(), impl

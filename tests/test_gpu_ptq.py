@@ -222,3 +222,38 @@ def test_colsumsq_ring_kernel(cuda):
         got = out.cpu().numpy()
         assert np.abs(got - ref).max() <= 1e-5 * ref.max(), (dt, shape)
         assert got[7] == 0.0 and np.array_equal(got == 0, O.dead_columns(X.float().numpy()))
+
+
+@pytest.mark.parametrize("bs", [128, 48, 32])
+def test_fasterquant_default_and_other_blocksizes(cuda, golden_dir, bs):
+    """MXQGPT.fasterquant with the signature's default blocksize=128 (mxqgpt.py:388: one 48-wide 2-bit
+    group per 64-column block, :413-415) and 48 / 32, bit-exact vs the unmodified reference's output."""
+    import os
+    from mxq_b200 import MXQGPT
+    d = np.load(os.path.join(golden_dir, "fasterquant_blocksize.npz"))
+    W, X, Wq = d[f"bs{bs}/W"], d[f"bs{bs}/X"], d[f"bs{bs}/Wq"]
+    layer = torch.nn.Linear(W.shape[1], W.shape[0], bias=False).to(cuda).half()
+    layer.weight.data = torch.from_numpy(W).to(cuda)
+    gpt = MXQGPT(layer)
+    for j in range(X.shape[0]):
+        gpt.add_batch(torch.from_numpy(X[j]).to(cuda), None)
+    if bs == 128:
+        gpt.fasterquant()                                  # the default
+    else:
+        gpt.fasterquant(blocksize=bs)
+    got = layer.weight.data.cpu().numpy()
+    assert np.array_equal(got.view(np.uint16), Wq.view(np.uint16))
+    with pytest.raises(NotImplementedError):
+        MXQGPT(layer).fasterquant(blocksize=8)
+
+
+def test_fasterquant_without_samples_zeroes_the_weight(cuda):
+    """nsamples == 0: H == 0, every column is dead, W[:, dead] = 0 (mxqgpt.py:399-403)."""
+    from mxq_b200 import MXQGPT
+    torch.manual_seed(3)
+    layer = torch.nn.Linear(256, 64, bias=False).to(cuda).half()
+    W0 = layer.weight.data.cpu().numpy().copy()
+    gpt = MXQGPT(layer)
+    gpt.fasterquant(blocksize=16)
+    want = O.fasterquant(W0, np.ones(256, bool))
+    assert np.array_equal(layer.weight.data.cpu().numpy().view(np.uint16), want.view(np.uint16))

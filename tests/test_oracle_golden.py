@@ -113,3 +113,15 @@ def test_actquant_bit_exact(golden_dir):
             assert np.array_equal(gi.view(np.uint32), A[k[:-2] + "/gi"].view(np.uint32)), k
         n += 1
     assert n >= 45
+
+
+def test_fasterquant_blocksize_bit_exact(golden_dir):
+    """fasterquant(blocksize=128 / 48 / 32) of the unmodified reference (oracle/gen_golden.py)."""
+    d = np.load(os.path.join(golden_dir, "fasterquant_blocksize.npz"))
+    for bs in (128, 48, 32):
+        W, X, Wq = d[f"bs{bs}/W"], d[f"bs{bs}/X"], d[f"bs{bs}/Wq"]
+        out = O.fasterquant_blocksize(W, O.dead_columns(X), bs)
+        assert np.array_equal(out.view(np.uint16), Wq.view(np.uint16)), bs
+    W, X = d["bs128/W"], d["bs128/X"]
+    dead = O.dead_columns(X)
+    assert np.array_equal(O.fasterquant_blocksize(W, dead, 16).view(np.uint16), O.fasterquant(W, dead).view(np.uint16))
