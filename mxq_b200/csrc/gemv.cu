@@ -746,10 +746,20 @@ int launch_gemv(const __half* x, const mxq_packed_t* ws, void* const* ys, int n,
   if (getenv("MXQ_GEMV_VERBOSE"))
     fprintf(stderr, "mxq_gemv %dx%d B=%d: warps %d wpr %d rpr %d rounds %d stages %d smem %zu grid %u\n",
             OC, IC, B, W, plan.wpr, plan.rpr, plan.rounds, plan.nstages, smem, gx);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(gemv_mxq_kernel<NB>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+  // Same shared-memory configuration as the IMMA kernel (gemv_mma.cu): opt-in limit raised once, carve-out
+  // pinned to "max shared", so a decode chain that alternates between the two kernels (and between
+  // shapes) never makes an SM re-partition L1 / shared memory between consecutive launches.
+  {
+    static bool configured = false;                  // benign race: idempotent attribute writes
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(gemv_mxq_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(kSmemPerSM - kSmemCtaReserve));
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(gemv_mxq_kernel<NB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               (int)cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return (int)e;
+      configured = true;
+    }
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(gx, gy);

@@ -45,8 +45,6 @@ int gemv_ring_grouped(const void* x, const mxq_packed_t* w, void* const* y, int 
 
 namespace g2 {
 
-constexpr int kWarps = 8;
-constexpr int kThreads = kWarps * 32;
 constexpr int kRing = 4;         // ring slots per warp (57 KB per CTA; the probe streams at full rate with 4)
 constexpr int kMaxGroup = 4;
 // one unit = 16 rows (4 second-order groups) x 4 blocks (256 columns); slot layout in bytes
@@ -69,7 +67,7 @@ struct Plan {
 
 // Profiling only: {start, copies issued, waited, staged, loop done, done} per CTA.
 __device__ unsigned long long g_trace[6 * 160];
-__device__ long long g_itrace[8 * 16 * 6];     // [warp][iteration][stamp] clock64 of CTA 1 (MXQ_GEMV_DBG & 64)
+__device__ long long g_itrace[16 * 16 * 6];     // [warp][iteration][stamp] clock64 of CTA 1 (MXQ_GEMV_DBG & 64)
 __device__ __forceinline__ unsigned long long gtimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -208,11 +206,12 @@ __device__ __forceinline__ void stage_group(const __half* __restrict__ xg, bool 
 // groups pad the prologue and the tail so that "at most kRing - 1 groups pending" always means
 // "the unit about to be consumed has landed").
 // ---------------------------------------------------------------------------------------------
-template <int NB, bool kDbg>
-__global__ void __launch_bounds__(kThreads, 2) gemv_mma_kernel(const __half* __restrict__ x,
+template <int NB, bool kDbg, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 2) gemv_mma_kernel(const __half* __restrict__ x,
                                                                const __grid_constant__ Group G,
                                                                int B, int IC, int OC, const Plan plan) {
   extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int kThreads = kWarps * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int li = blockIdx.x / plan.gxl;
@@ -481,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, 2) gemv_mma_kernel(const __half* __r
 
 constexpr size_t kSmemPerSM = 227 * 1024, kSmemCtaReserve = 1024;
 
-template <int NB, bool kDbg>
+template <int NB, bool kDbg, int kWarps>
 int launch_k(const __half* x, const Group& G, int n, int B, int IC, int OC, bool pdl, const Plan& plan, size_t smem,
              cudaStream_t st) {
   // One shared-memory configuration for every shape: the opt-in limit is raised once to half an SM
@@ -489,17 +488,17 @@ int launch_k(const __half* x, const Group& G, int n, int B, int IC, int OC, bool
   // the SM re-partition L1 / shared memory (which would serialise them under PDL).
   static bool configured = false;                    // benign race: idempotent attribute writes
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemv_mma_kernel<NB, kDbg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemv_mma_kernel<NB, kDbg, kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(kSmemPerSM - kSmemCtaReserve));
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(gemv_mma_kernel<NB, kDbg>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(gemv_mma_kernel<NB, kDbg, kWarps>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              (int)cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n * plan.gxl), (unsigned)ceil_div(B, NB));
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(kWarps * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -507,7 +506,7 @@ int launch_k(const __half* x, const Group& G, int n, int B, int IC, int OC, bool
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemv_mma_kernel<NB, kDbg>, x, G, B, IC, OC, plan);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemv_mma_kernel<NB, kDbg, kWarps>, x, G, B, IC, OC, plan);
   return e == cudaSuccess ? MXQ_OK : (int)e;
 }
 
@@ -529,16 +528,23 @@ int launch(const __half* x, const mxq_packed_t* ws, void* const* ys, int n, int 
   if (const char* e = getenv("MXQ_GEMV_EARLY")) plan.early = atoi(e);
   const int rows_cta = plan.q * 4;
   const size_t rowtab = (size_t)((rows_cta * 2 + (rows_cta / 8 + 2) * 4 + 15) & ~15);
-  const size_t smem = (size_t)kWarps * kRing * kUnitBytes + rowtab + (size_t)NB * plan.ximg +
-                      (size_t)kWarps * NB * rows_cta * sizeof(float);
+  // 8 warps (110 registers) or 12 warps (78 registers): two CTAs -- this launch and, under PDL, the
+  // next one -- fit on an SM either way.  12 warps build the activation image of a long row in fewer
+  // rounds and split the units 12 ways; with only a few units per warp 8 is better balanced.
+  int warps = ((int64_t)plan.T * plan.nqb >= 64 && NB == 1) ? 12 : 8;
+  if (const char* e = getenv("MXQ_GEMV_WARPS2")) { const int v = atoi(e); if (v == 8 || v == 12) warps = v; }
+  const size_t smem = (size_t)warps * kRing * kUnitBytes + rowtab + (size_t)NB * plan.ximg +
+                      (size_t)warps * NB * rows_cta * sizeof(float);
   if (smem + kSmemCtaReserve > kSmemPerSM) return MXQ_E_SHAPE;
   Group G{};
   for (int i = 0; i < n; ++i) { G.w[i] = ws[i]; G.y[i] = (__half*)ys[i]; }
   if (getenv("MXQ_GEMV_VERBOSE"))
     fprintf(stderr, "mxq_gemv(mma) %dx%d B=%d n=%d: q %d T %d nqb %d units/warp %d smem %zu grid %d\n", OC, IC, B, n,
-            plan.q, plan.T, plan.nqb, (int)ceil_div((int64_t)plan.T * plan.nqb, kWarps), smem, n * plan.gxl);
-  if (plan.dbg) return launch_k<NB, true>(x, G, n, B, IC, OC, pdl, plan, smem, st);
-  return launch_k<NB, false>(x, G, n, B, IC, OC, pdl, plan, smem, st);
+            plan.q, plan.T, plan.nqb, (int)ceil_div((int64_t)plan.T * plan.nqb, warps), smem, n * plan.gxl);
+  if (plan.dbg) return warps == 12 ? launch_k<NB, true, 12>(x, G, n, B, IC, OC, pdl, plan, smem, st)
+                                   : launch_k<NB, true, 8>(x, G, n, B, IC, OC, pdl, plan, smem, st);
+  return warps == 12 ? launch_k<NB, false, 12>(x, G, n, B, IC, OC, pdl, plan, smem, st)
+                     : launch_k<NB, false, 8>(x, G, n, B, IC, OC, pdl, plan, smem, st);
 }
 
 }  // namespace g2
@@ -569,14 +575,15 @@ extern "C" int mxq_gemv_grouped(const void* x, const mxq_packed_t* w, void* cons
     if (rc) return rc;
   }
   if (IC % 64 || OC % 8 || IC == 0 || IC > (1 << 24) || OC > INT32_MAX || B > 65535 * 4) return MXQ_E_SHAPE;
-  const char* impl = getenv("MXQ_GEMV_IMPL");                 // "ring" / "mma": force one kernel (profiling)
-  const bool ring_only = impl && impl[0] == 'r', mma_only = impl && impl[0] == 'm';
-  // The IMMA kernel needs 256-column quad-blocks.  Its 8-warp CTA builds the activation image in
-  // ceil(IC / 4096) rounds; measured on B200 (profiles/r2_gemv_chain.txt) it wins up to IC = 8192
-  // (4096^2: 3.9 vs 4.2 us, 11008 x 4096: 8.3 vs 8.7 us) and loses at IC = 11008 (9.3 vs 8.6 us),
-  // where the 14-warp ring kernel stages the activations faster.
-  if (ring_only || IC % 256 != 0 || IC > 32768 || (!mma_only && IC > 8192))
-    return gemv_ring_grouped(x, w, y, n, B, IC, OC, flags, stream);
+  // Kernel choice.  Measured on B200 (profiles/r2_gemv_chain.txt, CUDA graph over > L2 of weights, PDL):
+  //   same-shape chains   4096^2: IMMA 3.9 us, ring 4.2 us;  11008x4096: 8.4 vs 8.7;  4096x11008: 9.3 vs 8.6
+  //   bench.py's mixed 56-linear chain: ring 336 us, IMMA 350 us, alternating between the two 383 us
+  //   (two different kernels cannot be co-resident -- 59 K + 28 K registers -- so the PDL overlap is lost)
+  // A decode step is a chain of mixed shapes, so ONE kernel serves a whole process: the ring kernel by
+  // default, the IMMA kernel with MXQ_GEMV_IMPL=mma (it needs IC % 256 == 0; other shapes fall back).
+  const char* impl = getenv("MXQ_GEMV_IMPL");
+  const bool use_mma = impl && impl[0] == 'm' && IC % 256 == 0 && IC <= 32768;
+  if (!use_mma) return gemv_ring_grouped(x, w, y, n, B, IC, OC, flags, stream);
   cudaStream_t st = as_stream(stream);
   const __half* xh = (const __half*)x;
   const bool pdl = !(flags & MXQ_GEMV_NO_PDL);
@@ -594,7 +601,7 @@ extern "C" __attribute__((visibility("default"))) int mxq_debug_gemv2_trace(unsi
 }
 
 extern "C" __attribute__((visibility("default"))) int mxq_debug_gemv2_itrace(long long* host_out) {
-  return (int)cudaMemcpyFromSymbol(host_out, g2::g_itrace, sizeof(long long) * 8 * 16 * 6);
+  return (int)cudaMemcpyFromSymbol(host_out, g2::g_itrace, sizeof(long long) * 16 * 16 * 6);
 }
 
 extern "C" int mxq_gemv_ex(const void* x, mxq_packed_t w, void* y, int64_t B, int64_t IC, int64_t OC,

@@ -24,10 +24,17 @@ def find_layers(module, layers=(nn.Linear,), name=''):
 
 
 @torch.no_grad()
-def nas_quant(args, model, tokenizer, dev, dataloader=None):
-    """prune.py:326-425.  ``dataloader`` (extension): iterable of (input_ids, ...) batches; when
-    omitted the reference's wikitext2 loader is needed, which requires the `datasets` package and
-    network access (prune.py:329)."""
+def nas_quant(args, model, tokenizer, dev, dataloader=None, batch_size: int = 1, timers: dict | None = None):
+    """prune.py:326-425: calibration capture (Catcher), per layer: MXQGPT per linear, forward hooks
+    feeding add_batch during the layer forwards over all samples, fasterquant (blocksize 16), a
+    second forward with the quantized weights, in/out swap.
+
+    Extensions: ``dataloader`` -- iterable of (input_ids[1, seqlen], ...) batches (the reference
+    downloads wikitext2 here, prune.py:329); ``batch_size`` -- samples per layer forward (the
+    reference runs one at a time, :400-402,416-417; statistics and outputs are identical, the dense
+    forwards just stop being launch-bound); ``timers`` -- dict that receives the device time of the
+    layer forwards (incl. the statistics hooks) and of fasterquant(+pack) in ms; ``args.pack`` --
+    also attach the packed 2/4-bit tensors of every linear as ``module.mxq_packed``."""
     print('Starting ...')
     if dataloader is None:
         # the reference downloads wikitext2 here (prune.py:329, lib/data.py: needs the `datasets`
@@ -66,12 +73,31 @@ def nas_quant(args, model, tokenizer, dev, dataloader=None):
     outs = torch.zeros_like(inps)
     kwargs = {k: v for k, v in cache['kwargs'].items() if k in ("attention_mask", "position_ids", "position_embeddings")}
     print('Ready.')
+    bs = max(1, int(batch_size))
+    marks = []                      # (phase, start event, end event)
+
+    def timed(phase):
+        if timers is None:
+            return None
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks.append((phase, a, b))
+        a.record()
+        return b
+
+    def forward_all(layer):
+        end = timed("forward")
+        for j in range(0, args.nsamples, bs):
+            out = layer(inps[j:j + bs], **kwargs)
+            outs[j:j + bs] = out[0] if isinstance(out, tuple) else out
+        if end is not None:
+            end.record()
 
     for i in range(len(layers)):
         layer = layers[i]
         if f"model.layers.{i}" in device_map:
             dev = device_map[f"model.layers.{i}"]
-            kwargs = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in kwargs.items()}
+            kwargs = {k: (tuple(t.to(dev) for t in v) if isinstance(v, tuple) else v.to(dev) if torch.is_tensor(v) else v)
+                      for k, v in kwargs.items()}
             inps, outs = inps.to(dev), outs.to(dev)
         subset = find_layers(layer)
         gpts = {name: MXQGPT(subset[name]) for name in subset}
@@ -82,10 +108,10 @@ def nas_quant(args, model, tokenizer, dev, dataloader=None):
             return tmp
 
         handles = [subset[name].register_forward_hook(add_batch(name)) for name in gpts]
-        for j in range(args.nsamples):
-            outs[j] = layer(inps[j].unsqueeze(0), **kwargs)[0]
+        forward_all(layer)
         for h in handles:
             h.remove()
+        end = timed("quant")
         for name in gpts:
             print(i, name)
             print('Pruning ...')
@@ -94,14 +120,18 @@ def nas_quant(args, model, tokenizer, dev, dataloader=None):
             if getattr(args, "pack", False):
                 subset[name].mxq_packed = gpts[name].packed
             gpts[name].free()
-        for j in range(args.nsamples):
-            outs[j] = layer(inps[j].unsqueeze(0), **kwargs)[0]
+        if end is not None:
+            end.record()
+        forward_all(layer)
         layers[i] = layer
-        torch.cuda.empty_cache()
         inps, outs = outs, inps
 
     model.config.use_cache = use_cache
     torch.cuda.empty_cache()
+    if timers is not None:
+        torch.cuda.synchronize()
+        for phase, a, b in marks:
+            timers[phase + "_ms"] = timers.get(phase + "_ms", 0.0) + a.elapsed_time(b)
 
 
 class LinearQuantJob:
@@ -136,10 +166,10 @@ def llama_linears(hidden: int, inter: int, kv_hidden: int | None = None):
 class LlamaLayerPTQ:
     """The mxq work of one decoder layer given its captured linear inputs: 4 activation statistics
     (what the 7 MXQGPT.add_batch hooks compute, prune.py:389-402) + fasterquant + pack of the 7
-    linears (prune.py:404-414).  Kernels launched per layer: 4 x 2 (statistics) + 7 x 3 (dead
-    mask, pool pre-pass, fused quantize+pack tile kernel)."""
+    linears (prune.py:404-414).  Kernels launched per layer: 4 x 2 (statistics: partial sums +
+    finalize) + 7 x 1 (the fused 16-row-tile fasterquant + pack kernel)."""
 
-    LAUNCHES_PER_LAYER = 4 * 2 + 7 * 3
+    LAUNCHES_PER_LAYER = 4 * 2 + 7
 
     def __init__(self, hidden: int, inter: int, device, max_tokens: int, kv_hidden=None):
         self.linears = llama_linears(hidden, inter, kv_hidden)

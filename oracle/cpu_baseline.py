@@ -99,3 +99,28 @@ def fakequant_sample(rows: int, cols: int, dtype: str, threads: int | None = Non
     dt = time.perf_counter() - t0
     esz = 4 if dtype == "fp32" else 2
     return dt, rows * cols * esz * 5, f"{rows}x{cols} {dtype} fwd+bwd, numpy oracle port on {threads} threads"
+
+
+def dequant_matmul_sample(rows: int, cols: int, M: int, threads: int | None = None, what: str = "bytes", seed: int = 0):
+    """CPU leg of the packed dequant-GEMV / GEMM (the reference ships no CPU path for the packed
+    format): restated decode of gemv_mxq_cuda.cu:131-136,152-153,178-179 on `rows` output rows
+    (threaded over row slabs) followed by an fp32 matmul with an [M, cols] activation block.
+    Returns (seconds, work, description); work = packed bytes (+x, y) or 2*M*rows*cols FLOP."""
+    threads = threads or os.cpu_count() or 1
+    p = O.random_packed(rows, cols, seed=seed)
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((M, cols), dtype=np.float32).astype(np.float16)
+    slabs = _slabs(rows, 64)
+
+    def sub(s):
+        r0, r1 = s
+        q = dict(weight=p["weight"][r0:r1], weight_last=p["weight_last"][r0:r1], zeros_and_scales=p["zeros_and_scales"][r0:r1],
+                 zeros_2nd=p["zeros_2nd"][r0 // 4:r1 // 4], scales_2nd=p["scales_2nd"][r0 // 4:r1 // 4],
+                 scales_4b=p["scales_4b"][r0:r1], zeros_4b=p["zeros_4b"][r0 // 8:r1 // 8])
+        return x.astype(np.float32) @ O.decode_mxq(q).astype(np.float32).T
+    t0 = time.perf_counter()
+    _pmap(sub, slabs, threads)
+    dt = time.perf_counter() - t0
+    nbytes = sum(v.nbytes for v in p.values()) + 2 * M * (rows + cols)
+    work = nbytes if what == "bytes" else 2.0 * M * rows * cols
+    return dt, work, (f"decode + fp32 matmul of a packed {rows}x{cols} linear, M = {M}, numpy oracle port on {threads} threads")

@@ -113,8 +113,11 @@ def main():
         yq = [torch.empty(1, 4096, device=dev, dtype=torch.float16) for _ in range(3)]
         yg = [torch.empty(1, 11008, device=dev, dtype=torch.float16) for _ in range(2)]
         gbytes = nl * sum(packed_nbytes(oc, ic) + 2 * (oc + ic) for oc, ic in shapes)
-        for impl in ("mma", "ring"):
-            os.environ["MXQ_GEMV_IMPL"] = impl
+        for impl in ("auto", "mma", "ring"):
+            if impl == "auto":
+                os.environ.pop("MXQ_GEMV_IMPL", None)          # the library's per-shape choice
+            else:
+                os.environ["MXQ_GEMV_IMPL"] = impl
             for pdl in (True, False):
                 def plain():
                     for layer in packs:

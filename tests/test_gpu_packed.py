@@ -289,3 +289,33 @@ def test_gemv_generic_and_imma_kernels_agree(cuda, monkeypatch):
         monkeypatch.setenv("MXQ_GEMV_IMPL", impl)
         y = ops.gemv(xd, pd).cpu().numpy().astype(np.float64)
         assert (np.abs(y - ref) <= bound).all(), impl
+
+
+@pytest.mark.parametrize("OC,IC,B", [(256, 4096, 1), (4096, 4096, 1), (4096, 4096, 8), (512, 8192, 2), (128, 11008, 3),
+                                     (11008, 256, 4), (4104, 256, 2), (64, 28672, 1), (4096, 11008, 1), (11008, 4096, 2)])
+def test_gemv_imma_kernel(cuda, monkeypatch, OC, IC, B):
+    """The opt-in IMMA kernel (MXQ_GEMV_IMPL=mma, csrc/gemv_mma.cu): same oracle, same bound, incl. row
+    counts that leave partial 16-row tiles / short last CTAs, ragged quad-block counts (11008 = 43 x 256)
+    and every batch tiling."""
+    from mxq_b200 import ops
+    monkeypatch.setenv("MXQ_GEMV_IMPL", "mma")
+    p = O.random_packed(OC, IC, seed=OC + IC + B)
+    x = _outlier_x(B, IC, seed=B)
+    ref = O.gemm_mxq_f32(x, p)
+    bound = 1e-3 * _per_element_bound(x, p) + np.abs(ref) * 2.0 ** -11
+    y = ops.gemv(torch.from_numpy(x).to(cuda), packed_to_dev(p, cuda)).cpu().numpy().astype(np.float64)
+    assert y.shape == (B, OC)
+    assert (np.abs(y - ref) <= bound).all()
+
+
+def test_gemv_imma_grouped(cuda, monkeypatch):
+    from mxq_b200 import ops
+    monkeypatch.setenv("MXQ_GEMV_IMPL", "mma")
+    OC, IC, n = 4096, 4096, 3
+    ps = [O.random_packed(OC, IC, seed=31 * i + 1) for i in range(n)]
+    x = _outlier_x(1, IC, seed=9)
+    ys = ops.gemv_grouped(torch.from_numpy(x).to(cuda), [packed_to_dev(p, cuda) for p in ps])
+    for p, y in zip(ps, ys):
+        ref = O.gemm_mxq_f32(x, p)
+        bound = 1e-3 * _per_element_bound(x, p) + np.abs(ref) * 2.0 ** -11
+        assert (np.abs(y.cpu().numpy().astype(np.float64) - ref) <= bound).all()
