@@ -191,12 +191,38 @@ MXQ_API int mxq_gemv_ex(const void* x, mxq_packed_t w, void* y, int64_t B, int64
 MXQ_API int mxq_gemv_grouped(const void* x, const mxq_packed_t* w, void* const* y, int n, int64_t B,
                              int64_t IC, int64_t OC, unsigned flags, void* stream);
 
+/* ---- (f-3) importance-driven allocation folded into the packed path ----------------------------------
+ * The packed layout is positional (the last 16 of every 64 columns are the 4-bit ones,
+ * utils_quant.py:349-353, mxqgpt.py:404-419).  A data-driven choice of the 4-bit group (mxq_allocate_bits,
+ * Wanda metric prune.py:177; act-order permutation weight_permutation.py:27-93) is expressed as a
+ * permutation of 16-column groups: packed group g holds original group group_perm[g].  The weights are
+ * gathered once before packing (mxq_gather_groups), the prefill GEMM gathers its activations the same way,
+ * and the decode GEMV applies the permutation while it stages x in shared memory (no extra pass). */
+MXQ_API int mxq_gather_groups(const void* in, const int32_t* group_perm, void* out, int64_t rows, int64_t cols,
+                              void* stream);   /* fp16 [rows, cols], cols % 16 == 0, out != in */
+MXQ_API int mxq_gemv_grouped_perm(const void* x, const mxq_packed_t* w, void* const* y, int n, int64_t B,
+                                  int64_t IC, int64_t OC, const int32_t* group_perm /* int32[IC/16] or NULL */,
+                                  unsigned flags, void* stream);
+
 /* ---- (a-10) gemv_forward_cuda (AWQ uniform 4-bit)   gemv_cuda.cu:346-399, gemv_cuda.h:4-9 ------
  * kernel int32[OC, IC/8] (nibble j of word i = column 8i+j), zeros int32[OC, zw] (nibble g%8 of
  * word g/8, g = col/G), scales fp16[OC, zw*8]; zw = ceil(IC/G/8) rounded up to 1/2/4 words for
  * G = 128/64/32 (gemv_cuda.cu:200,129,56). */
 MXQ_API int mxq_awq_gemv(const void* x, const int32_t* kernel, const void* scales, const int32_t* zeros,
                  void* y, int64_t B, int64_t IC, int64_t OC, int group_size, void* stream);
+
+/* ---- AWQ uniform 4-bit prefill GEMM   gemm_cuda_gen.cu:424-478 (declared in gemm_cuda.h, never built by
+ * the reference's setup.py:37-41) ------------------------------------------------------------------
+ * y[m, n] = sum_k x[m, k] * W[k][n],  W[k][n] = fp16(scales[k/G][n] * (q - z)).  x fp16 [M, IC];
+ * kernel int32 [IC, OC/8], zeros int32 [IC/G, OC/8]: output channel 8j + c = nibble
+ * {0,4,1,5,2,6,3,7}[c] of word j (dequantize.cuh:15-77); scales fp16 [IC/G, OC]; y fp16 [M, OC].
+ * G % 32 == 0, OC % 64 == 0, OC % G == 0 (the reference's own checks, :447-454), IC % 64 == 0.
+ * fp32 accumulation over all of K (the reference's `split_k_iters` fp16 partial sums do not exist).
+ * workspace: mxq_awq_gemm_workspace_bytes(IC, OC) (the dequantized fp16 operand). */
+MXQ_API size_t mxq_awq_gemm_workspace_bytes(int64_t IC, int64_t OC);
+MXQ_API int mxq_awq_gemm(const void* x, const int32_t* kernel, const void* scales, const int32_t* zeros, void* y,
+                         int64_t M, int64_t IC, int64_t OC, int group_size, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 /* ---- prefill: packed dequant-GEMM on tcgen05/TMEM (no reference kernel exists for the mixed
  * layout; gemm_cuda_gen.cu:424-478 is the un-built AWQ 4-bit analogue) --------------------------

@@ -25,7 +25,7 @@ SYMBOLS = [
     "mxq_colsumsq_workspace_bytes", "mxq_colsumsq", "mxq_colsumsq_ex", "mxq_wanda_metric",
     "mxq_allocate_bits_workspace_bytes", "mxq_allocate_bits",
     "mxq_ptq_workspace_bytes", "mxq_ptq_quant", "mxq_rowquant",
-    "mxq_pack_workspace_bytes", "mxq_pack", "mxq_ptq_quant_pack", "mxq_unpack", "mxq_gemv", "mxq_gemv_ex", "mxq_gemv_grouped", "mxq_awq_gemv",
+    "mxq_pack_workspace_bytes", "mxq_pack", "mxq_ptq_quant_pack", "mxq_unpack", "mxq_gemv", "mxq_gemv_ex", "mxq_gemv_grouped", "mxq_gemv_grouped_perm", "mxq_gather_groups", "mxq_awq_gemv", "mxq_awq_gemm_workspace_bytes", "mxq_awq_gemm",
     "mxq_gemm_workspace_bytes", "mxq_gemm", "mxq_gemm_plan", "mxq_gemm_scatter", "mxq_gemm_multicast", "mxq_gemm_dense",
 ]
 
@@ -78,7 +78,12 @@ def lib() -> C.CDLL:
     L.mxq_gemv.argtypes = [vp, PackedC, vp, i64, i64, i64, vp]
     L.mxq_gemv_ex.argtypes = [vp, PackedC, vp, i64, i64, i64, C.c_uint, vp]
     L.mxq_gemv_grouped.argtypes = [vp, C.POINTER(PackedC), C.POINTER(vp), i32, i64, i64, i64, C.c_uint, vp]
+    L.mxq_gemv_grouped_perm.argtypes = [vp, C.POINTER(PackedC), C.POINTER(vp), i32, i64, i64, i64, vp, C.c_uint, vp]
+    L.mxq_gather_groups.argtypes = [vp, vp, vp, i64, i64, vp]
     L.mxq_awq_gemv.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i32, vp]
+    L.mxq_awq_gemm_workspace_bytes.restype = sz
+    L.mxq_awq_gemm_workspace_bytes.argtypes = [i64, i64]
+    L.mxq_awq_gemm.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i32, vp, sz, vp]
     L.mxq_gemm_workspace_bytes.restype = sz
     L.mxq_gemm_workspace_bytes.argtypes = [i64, i64, i64]
     L.mxq_gemm.argtypes = [vp, PackedC, vp, i64, i64, i64, vp, sz, vp]

@@ -29,6 +29,7 @@ SOURCES = {
     "gemv.cu": [],
     "gemv_mma.cu": [],
     "gemm_tcgen05.cu": [],
+    "awq_gemm.cu": ["-fmad=false"],
 }
 
 COMMON = [

@@ -383,6 +383,7 @@ struct GemvGroup {
   __half* y[kGemvMaxGroup];
   int n;       // linears in the launch
   int gxl;     // CTAs per linear (gridDim.x = n * gxl)
+  const int32_t* gperm;   // optional: 16-column group g of the packed weight reads activation group gperm[g]
 };
 
 // Profiling only (MXQ_GEMV_DBG & 8): per-CTA %globaltimer stamps {start, waited, staged, done}.
@@ -453,7 +454,8 @@ __global__ void __launch_bounds__(NB == 1 ? 512 : 256, 1) gemv_mxq_kernel(
     for (int i = threadIdx.x; i < NB * ngrp; i += blockDim.x) {
       const int b = NB == 1 ? 0 : i / ngrp, g = i - b * ngrp;
       const int bb = min(b0 + b, B - 1);
-      const uint4* xp = reinterpret_cast<const uint4*>(x + (size_t)bb * IC + (size_t)g * 16);
+      const int gsrc = G.gperm ? __ldg(G.gperm + g) : g;      // importance-driven column order (per 16-column group)
+      const uint4* xp = reinterpret_cast<const uint4*>(x + (size_t)bb * IC + (size_t)gsrc * 16);
       const uint4 v0 = __ldg(xp), v1 = __ldg(xp + 1);
       const int xblk = g >> 2, k = g & 3;
       unsigned char* xb = xsm + (size_t)b * xb_stride;
@@ -688,7 +690,7 @@ constexpr size_t kSmemPerSM = 227 * 1024, kSmemCtaReserve = 4096;   // static sm
 
 template <int NB>
 int launch_gemv(const __half* x, const mxq_packed_t* ws, void* const* ys, int n, int B, int IC, int OC,
-                bool pdl, cudaStream_t st) {
+                const int32_t* gperm, bool pdl, cudaStream_t st) {
   constexpr int kMaxWarps = NB == 1 ? kGemvMaxWarps : 8;
   const int nblk = IC / 64, ngrp = OC / 4, nchunk = (nblk + 63) / 64;
   const size_t ximg = (size_t)NB * nblk * (kXBlkBytes + 32);
@@ -738,6 +740,7 @@ int launch_gemv(const __half* x, const mxq_packed_t* ws, void* const* ys, int n,
   plan.spw = (int)ceil_div(plan.ksl, plan.wpr);
   GemvGroup G{};
   G.n = n;
+  G.gperm = gperm;
   G.gxl = (int)ceil_div(ngrp, plan.q);
   for (int i = 0; i < n; ++i) { G.w[i] = ws[i]; G.y[i] = (__half*)ys[i]; }
   const unsigned gx = (unsigned)(n * G.gxl);
@@ -788,7 +791,7 @@ static int gemv_check_packed(const mxq_packed_t& w) {
 // Generic-shape path (any IC % 64 == 0) behind mxq_gemv_grouped (gemv_mma.cu dispatches).
 namespace mxq {
 int gemv_ring_grouped(const void* x, const mxq_packed_t* w, void* const* y, int n, int64_t B, int64_t IC,
-                      int64_t OC, unsigned flags, void* stream) {
+                      int64_t OC, const int32_t* gperm, unsigned flags, void* stream) {
   if (B < 0 || IC < 0 || OC < 0 || n < 0 || n > kGemvMaxGroup) return MXQ_E_SHAPE;
   if (B == 0 || OC == 0 || n == 0) return MXQ_OK;
   MXQ_CHECK_PTR(x);
@@ -803,9 +806,9 @@ int gemv_ring_grouped(const void* x, const mxq_packed_t* w, void* const* y, int 
   cudaStream_t st = as_stream(stream);
   const __half* xh = (const __half*)x;
   const bool pdl = !(flags & MXQ_GEMV_NO_PDL);
-  if (B == 1) return launch_gemv<1>(xh, w, y, n, (int)B, (int)IC, (int)OC, pdl, st);
-  if (B == 2) return launch_gemv<2>(xh, w, y, n, (int)B, (int)IC, (int)OC, pdl, st);
-  return launch_gemv<4>(xh, w, y, n, (int)B, (int)IC, (int)OC, pdl, st);
+  if (B == 1) return launch_gemv<1>(xh, w, y, n, (int)B, (int)IC, (int)OC, gperm, pdl, st);
+  if (B == 2) return launch_gemv<2>(xh, w, y, n, (int)B, (int)IC, (int)OC, gperm, pdl, st);
+  return launch_gemv<4>(xh, w, y, n, (int)B, (int)IC, (int)OC, gperm, pdl, st);
 }
 }  // namespace mxq
 

@@ -41,7 +41,7 @@ namespace mxq {
 
 // generic-shape kernel (gemv.cu)
 int gemv_ring_grouped(const void* x, const mxq_packed_t* w, void* const* y, int n, int64_t B, int64_t IC,
-                      int64_t OC, unsigned flags, void* stream);
+                      int64_t OC, const int32_t* gperm, unsigned flags, void* stream);
 
 namespace g2 {
 
@@ -77,6 +77,7 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 struct Group {
   mxq_packed_t w[kMaxGroup];
   __half* y[kMaxGroup];
+  const int32_t* gperm;   // optional: 16-column group g of the packed weight reads activation group gperm[g]
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -321,7 +322,9 @@ __global__ void __launch_bounds__(kWarps * 32, 2) gemv_mma_kernel(const __half* 
       const int b = NB == 1 ? 0 : i / ng, gi = i - b * ng;
       const int bb = min(b0g + b, B - 1);
       unsigned char* xb = ximg + (size_t)b * plan.ximg;
-      stage_group(x + (size_t)bb * IC + (size_t)gi * 16, gi * 16 < IC, gi & 3, xb + 16 + (size_t)gi * 32,
+      const bool live = gi * 16 < IC;
+      const int gsrc = (live && G.gperm) ? __ldg(G.gperm + gi) : gi;
+      stage_group(x + (size_t)bb * IC + (size_t)gsrc * 16, live, gi & 3, xb + 16 + (size_t)gi * 32,
                   reinterpret_cast<int*>(xb + 16 + (size_t)ng * 32) + gi,
                   reinterpret_cast<float*>(xb + 16 + (size_t)ng * 36) + gi);
     }
@@ -511,8 +514,8 @@ int launch_k(const __half* x, const Group& G, int n, int B, int IC, int OC, bool
 }
 
 template <int NB>
-int launch(const __half* x, const mxq_packed_t* ws, void* const* ys, int n, int B, int IC, int OC, bool pdl,
-           cudaStream_t st) {
+int launch(const __half* x, const mxq_packed_t* ws, void* const* ys, int n, int B, int IC, int OC,
+           const int32_t* gperm, bool pdl, cudaStream_t st) {
   const int nblk = IC / 64, ngrp = OC / 4;
   Plan plan;
   const int cpl = kNumSMs / n;
@@ -537,6 +540,7 @@ int launch(const __half* x, const mxq_packed_t* ws, void* const* ys, int n, int 
                       (size_t)warps * NB * rows_cta * sizeof(float);
   if (smem + kSmemCtaReserve > kSmemPerSM) return MXQ_E_SHAPE;
   Group G{};
+  G.gperm = gperm;
   for (int i = 0; i < n; ++i) { G.w[i] = ws[i]; G.y[i] = (__half*)ys[i]; }
   if (getenv("MXQ_GEMV_VERBOSE"))
     fprintf(stderr, "mxq_gemv(mma) %dx%d B=%d n=%d: q %d T %d nqb %d units/warp %d smem %zu grid %d\n", OC, IC, B, n,
@@ -563,8 +567,8 @@ static int gemv_check_packed(const mxq_packed_t& w) {
   return MXQ_OK;
 }
 
-extern "C" int mxq_gemv_grouped(const void* x, const mxq_packed_t* w, void* const* y, int n, int64_t B,
-                                int64_t IC, int64_t OC, unsigned flags, void* stream) {
+extern "C" int mxq_gemv_grouped_perm(const void* x, const mxq_packed_t* w, void* const* y, int n, int64_t B,
+                                     int64_t IC, int64_t OC, const int32_t* group_perm, unsigned flags, void* stream) {
   if (B < 0 || IC < 0 || OC < 0 || n < 0 || n > g2::kMaxGroup) return MXQ_E_SHAPE;
   if (B == 0 || OC == 0 || n == 0) return MXQ_OK;
   MXQ_CHECK_PTR(x);
@@ -583,16 +587,21 @@ extern "C" int mxq_gemv_grouped(const void* x, const mxq_packed_t* w, void* cons
   // default, the IMMA kernel with MXQ_GEMV_IMPL=mma (it needs IC % 256 == 0; other shapes fall back).
   const char* impl = getenv("MXQ_GEMV_IMPL");
   const bool use_mma = impl && impl[0] == 'm' && IC % 256 == 0 && IC <= 32768;
-  if (!use_mma) return gemv_ring_grouped(x, w, y, n, B, IC, OC, flags, stream);
+  if (!use_mma) return gemv_ring_grouped(x, w, y, n, B, IC, OC, group_perm, flags, stream);
   cudaStream_t st = as_stream(stream);
   const __half* xh = (const __half*)x;
   const bool pdl = !(flags & MXQ_GEMV_NO_PDL);
   int rc;
-  if (B == 1) rc = g2::launch<1>(xh, w, y, n, (int)B, (int)IC, (int)OC, pdl, st);
-  else if (B == 2) rc = g2::launch<2>(xh, w, y, n, (int)B, (int)IC, (int)OC, pdl, st);
-  else rc = g2::launch<4>(xh, w, y, n, (int)B, (int)IC, (int)OC, pdl, st);
-  if (rc == MXQ_E_SHAPE) return gemv_ring_grouped(x, w, y, n, B, IC, OC, flags, stream);
+  if (B == 1) rc = g2::launch<1>(xh, w, y, n, (int)B, (int)IC, (int)OC, group_perm, pdl, st);
+  else if (B == 2) rc = g2::launch<2>(xh, w, y, n, (int)B, (int)IC, (int)OC, group_perm, pdl, st);
+  else rc = g2::launch<4>(xh, w, y, n, (int)B, (int)IC, (int)OC, group_perm, pdl, st);
+  if (rc == MXQ_E_SHAPE) return gemv_ring_grouped(x, w, y, n, B, IC, OC, group_perm, flags, stream);
   return rc;
+}
+
+extern "C" int mxq_gemv_grouped(const void* x, const mxq_packed_t* w, void* const* y, int n, int64_t B,
+                                int64_t IC, int64_t OC, unsigned flags, void* stream) {
+  return mxq_gemv_grouped_perm(x, w, y, n, B, IC, OC, nullptr, flags, stream);
 }
 
 // profiling aid, not part of the documented surface

@@ -76,3 +76,35 @@ extern "C" int mxq_unpack(mxq_packed_t in, int64_t OC, int64_t IC, void* out, in
     return MXQ_E_DTYPE;
   MXQ_LAUNCH_RESULT();
 }
+
+// out[m, 16 g .. 16 g + 15] = in[m, 16 perm[g] ..]: the importance-driven column order applied to
+// fp16 rows -- the weights before packing, the activations before the prefill GEMM (the decode GEMV
+// applies it while it stages x).  One 32-byte group per thread pair.
+namespace mxq {
+__global__ void __launch_bounds__(256) gather_groups_kernel(const uint4* __restrict__ in, const int32_t* __restrict__ perm,
+                                                            uint4* __restrict__ out, int64_t rows, int ngroups) {
+  const int64_t total = rows * ngroups * 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (ngroups * 2);
+    const int c = (int)(i - r * ngroups * 2);
+    const int g = c >> 1;
+    out[i] = in[r * ngroups * 2 + (int64_t)__ldg(perm + g) * 2 + (c & 1)];
+  }
+}
+}  // namespace mxq
+
+extern "C" int mxq_gather_groups(const void* in, const int32_t* group_perm, void* out, int64_t rows, int64_t cols,
+                                 void* stream) {
+  if (rows < 0 || cols < 0 || cols % 16) return MXQ_E_SHAPE;
+  if (rows == 0 || cols == 0) return MXQ_OK;
+  MXQ_CHECK_PTR(in);
+  MXQ_CHECK_PTR(out);
+  if (!group_perm) return MXQ_E_NULL;
+  if (in == out) return MXQ_E_UNSUPPORTED;
+  const int64_t total = rows * (cols / 16) * 2;
+  int64_t grid = mxq::ceil_div(total, 256);
+  if (grid > mxq::kNumSMs * 16) grid = mxq::kNumSMs * 16;
+  mxq::gather_groups_kernel<<<(unsigned)grid, 256, 0, mxq::as_stream(stream)>>>((const uint4*)in, group_perm, (uint4*)out, rows,
+                                                                               (int)(cols / 16));
+  MXQ_LAUNCH_RESULT();
+}

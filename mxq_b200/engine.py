@@ -36,3 +36,10 @@ def gemm_mxq_forward_cuda(in_feats, kernel, kernel_last, zeros_and_scales, scale
 def gemv_forward_cuda(in_feats, kernel, scaling_factors, zeros, group_size):
     """AWQ uniform 4-bit GEMV (gemv_cuda.cu:346-399)."""
     return ops.awq_gemv(in_feats, kernel, scaling_factors, zeros, group_size)
+
+
+def gemm_forward_cuda(in_feats, kernel, scaling_factors, zeros, split_k_iters=1):
+    """AWQ uniform 4-bit prefill GEMM (gemm_cuda_gen.cu:424-478, gemm_cuda.h; present in the reference's
+    sources but absent from its build, setup.py:37-41).  `split_k_iters` is accepted and ignored: the
+    tcgen05 kernel accumulates all of K in fp32 (the reference adds fp16 split-K partials, :477)."""
+    return ops.awq_gemm(in_feats, kernel, scaling_factors, zeros)

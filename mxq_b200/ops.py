@@ -162,6 +162,38 @@ def allocate_group_bits(W: torch.Tensor, scaler_row: torch.Tensor | None = None,
     return (gb, imp) if return_importance else gb
 
 
+def importance_permutation(group_bits: torch.Tensor) -> torch.Tensor:
+    """Group permutation that moves the pooled (4-bit) group of every 4 consecutive groups -- as
+    chosen by `allocate_group_bits` -- to the last slot, where the positional packed layout keeps its
+    4-bit columns; the other three keep their order.  Returns int32[ngroups] with
+    packed group g = original group perm[g] (host-side integer bookkeeping, on the mask's device)."""
+    gb = group_bits.detach().to("cpu").view(-1, 4)
+    pooled = (gb & POOL) != 0
+    if not bool((pooled.sum(dim=1) == 1).all()):
+        raise ValueError("exactly one pooled group per 4 consecutive groups is required")
+    j = pooled.int().argmax(dim=1)                                  # pooled slot of every block
+    slots = torch.arange(4).expand(gb.shape[0], 4)
+    rest = slots[slots != j[:, None]].view(-1, 3)
+    order = torch.cat([rest, j[:, None]], dim=1)                     # [nblk, 4]
+    perm = (order + 4 * torch.arange(gb.shape[0])[:, None]).reshape(-1).to(torch.int32)
+    return perm.to(group_bits.device)
+
+
+def gather_groups(t: torch.Tensor, group_perm: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """out[..., 16 g : 16 g + 16] = t[..., 16 perm[g] : ...] for fp16 rows (mxq_gather_groups)."""
+    L.require_cuda(t, group_perm, out)
+    if t.dtype != torch.float16 or t.shape[-1] % 16 or group_perm.dtype != torch.int32 or \
+            group_perm.numel() != t.shape[-1] // 16:
+        raise ValueError("gather_groups: fp16 [..., cols] with cols % 16 == 0 and int32 perm[cols / 16]")
+    t2 = t.reshape(-1, t.shape[-1]).contiguous()
+    if out is None:
+        out = torch.empty_like(t2)
+    with L.on(t2) as st:
+        rc = L.lib().mxq_gather_groups(L.ptr(t2), L.ptr(group_perm.contiguous()), L.ptr(out), t2.shape[0], t2.shape[1], st)
+    L.check(rc, "mxq_gather_groups")
+    return out.reshape(t.shape)
+
+
 def ptq_quant(W: torch.Tensor, colstat: torch.Tensor | None = None, low_bits: int = 2,
               group: int = 16, group_bits=None, return_codes: bool = False, out=None,
               workspace=None):
@@ -220,12 +252,18 @@ def alloc_packed(OC: int, IC: int, device) -> dict:
 
 
 def pack(W: torch.Tensor, colstat: torch.Tensor | None = None, out: dict | None = None,
-         workspace=None) -> dict:
-    """fp16 W[OC, IC] -> packed mixed 2/4-bit tensors (layout of gemv_mxq_cuda.cu:39-208)."""
-    L.require_cuda(W, colstat)
+         workspace=None, group_perm: torch.Tensor | None = None) -> dict:
+    """fp16 W[OC, IC] -> packed mixed 2/4-bit tensors (layout of gemv_mxq_cuda.cu:39-208).
+    group_perm (int32[IC/16], e.g. from importance_permutation): the column order the weights are
+    packed in; the consumer must be given the same permutation (gemv(..., group_perm=...), MXQLinear)."""
+    L.require_cuda(W, colstat, group_perm)
     if W.dtype != torch.float16:
         raise TypeError("pack expects fp16 weights")
     W = W.contiguous()
+    if group_perm is not None:
+        W = gather_groups(W, group_perm)
+        if colstat is not None:
+            colstat = colstat.float().view(-1, 16)[group_perm.long()].reshape(-1).contiguous()
     OC, IC = W.shape
     if out is None:
         out = alloc_packed(OC, IC, W.device)
@@ -275,7 +313,7 @@ def _check_packed(p: dict):
         if tuple(t.shape) != tuple(shape) or t.dtype != dt or not t.is_contiguous():
             raise ValueError(f"packed tensor '{k}' must be contiguous {dt} {tuple(shape)}, got "
                              f"{t.dtype} {tuple(t.shape)}")
-        L.require_cuda(t)
+    L.require_cuda(*p.values())
     return OC, IC
 
 
@@ -289,19 +327,30 @@ def unpack(p: dict, dtype=torch.float32) -> torch.Tensor:
 
 
 def gemv(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, validate: bool = True,
-         pdl: bool = False):
+         pdl: bool = False, group_perm: torch.Tensor | None = None):
     """y[B, OC] = x[B, IC] @ dequant(W)^T, fp16.  pdl=True: programmatic dependent launch -- the
     kernel copies its packed weights into shared memory while the previous kernel of the stream is
     still running, which is only correct if that kernel does not write them (a decode chain over
     resident weights); x and y are touched after the dependency wait in either mode."""
     OC, IC = _check_packed(p) if validate else _packed_dims(p)
-    L.require_cuda(x)
+    L.require_cuda(x, p["weight"], out)
     if x.dtype != torch.float16 or x.dim() != 2 or x.shape[1] != IC:
         raise ValueError(f"x must be fp16 [B, {IC}]")
     x = x.contiguous()
     B = x.shape[0]
     if out is None:
         out = torch.empty((B, OC), dtype=torch.float16, device=x.device)
+    if group_perm is not None:
+        import ctypes as C
+        if group_perm.dtype != torch.int32 or group_perm.numel() != IC // 16 or group_perm.device != x.device:
+            raise ValueError(f"group_perm must be int32[{IC // 16}] on the activations' device")
+        warr = (L.PackedC * 1)(L.packed_struct(p))
+        yarr = (C.c_void_p * 1)(out.data_ptr())
+        with L.on(x) as st:
+            rc = L.lib().mxq_gemv_grouped_perm(L.ptr(x), warr, yarr, 1, B, IC, OC, L.ptr(group_perm.contiguous()),
+                                               0 if pdl else 1, st)
+        L.check(rc, "mxq_gemv_grouped_perm")
+        return out
     with L.on(x) as st:
         rc = L.lib().mxq_gemv_ex(L.ptr(x), L.packed_struct(p), L.ptr(out), B, IC, OC,
                                  0 if pdl else 1, st)
@@ -319,7 +368,7 @@ def gemv_grouped(x: torch.Tensor, ps: list, outs: list | None = None, pdl: bool 
     if len(set(dims)) != 1:
         raise ValueError("all linears of a group must have the same [OC, IC]")
     OC, IC = dims[0]
-    L.require_cuda(x)
+    L.require_cuda(x, *[q["weight"] for q in ps])
     if x.dtype != torch.float16 or x.dim() != 2 or x.shape[1] != IC:
         raise ValueError(f"x must be fp16 [B, {IC}]")
     x = x.contiguous()
@@ -350,7 +399,7 @@ def gemm(x: torch.Tensor, p: dict, out: torch.Tensor | None = None, workspace=No
     split_k=False passes no workspace: whole tiles only, i.e. every output element is one
     K-ordered fp32 accumulation (bit-identical to the sharded / fused-exchange paths)."""
     OC, IC = _check_packed(p) if validate else _packed_dims(p)
-    L.require_cuda(x)
+    L.require_cuda(x, p["weight"], out)
     if x.dtype != torch.float16 or x.dim() != 2 or x.shape[1] != IC:
         raise ValueError(f"x must be fp16 [M, {IC}]")
     x = x.contiguous()
@@ -375,7 +424,9 @@ def gemm_scatter(x: torch.Tensor, p: dict, peer_ptrs: list, ldy: int, col0: int,
     [M, ldy] fp16 buffer in `peer_ptrs` (device addresses; peers mapped over NVLink)."""
     import ctypes as C
     OC, IC = _packed_dims(p)
-    L.require_cuda(x)
+    L.require_cuda(x, p["weight"])
+    if x.dtype != torch.float16 or x.dim() != 2 or x.shape[1] != IC:
+        raise ValueError(f"x must be fp16 [M, {IC}]")
     x = x.contiguous()
     arr = (C.c_void_p * len(peer_ptrs))(*[int(a) for a in peer_ptrs])
     with L.on(x) as st:
@@ -390,7 +441,9 @@ def gemm_multicast(x: torch.Tensor, p: dict, multicast_ptr: int, ldy: int, col0:
     symmetric [M, ldy] fp16 buffer behind the NVSwitch multicast address `multicast_ptr`: one
     multimem.st per 16 bytes lands in every rank's copy."""
     OC, IC = _packed_dims(p)
-    L.require_cuda(x)
+    L.require_cuda(x, p["weight"])
+    if x.dtype != torch.float16 or x.dim() != 2 or x.shape[1] != IC:
+        raise ValueError(f"x must be fp16 [M, {IC}]")
     if not multicast_ptr:
         raise RuntimeError("gemm_multicast needs a multicast mapping (symmetric memory without NVSwitch multicast support)")
     x = x.contiguous()
@@ -427,4 +480,29 @@ def awq_gemv(x: torch.Tensor, kernel: torch.Tensor, scales: torch.Tensor, zeros:
                                   L.ptr(zeros.contiguous()), L.ptr(out), B, IC, OC, group_size,
                                   st)
     L.check(rc, "mxq_awq_gemv")
+    return out
+
+
+def awq_gemm(x: torch.Tensor, kernel: torch.Tensor, scales: torch.Tensor, zeros: torch.Tensor,
+             workspace: torch.Tensor | None = None) -> torch.Tensor:
+    """AWQ uniform 4-bit prefill GEMM (gemm_cuda_gen.cu:424-478): x fp16 [M, IC], kernel int32
+    [IC, OC/8], scales fp16 [IC/G, OC], zeros int32 [IC/G, OC/8] -> fp16 [M, OC]."""
+    L.require_cuda(x, kernel, scales, zeros)
+    if x.dtype != torch.float16 or x.dim() != 2 or kernel.dim() != 2 or kernel.shape[0] != x.shape[1]:
+        raise ValueError("x must be fp16 [M, IC] and kernel int32 [IC, OC/8]")
+    x = x.contiguous()
+    M, IC = x.shape
+    OC = kernel.shape[1] * 8
+    if scales.dim() != 2 or scales.shape[1] != OC or IC % scales.shape[0]:
+        raise ValueError("scales must be fp16 [IC/G, OC]")
+    G = IC // scales.shape[0]
+    out = torch.empty((M, OC), dtype=torch.float16, device=x.device)
+    need = L.lib().mxq_awq_gemm_workspace_bytes(IC, OC)
+    if workspace is None or workspace.numel() < need:
+        workspace = _ws(need, x.device)
+    with L.on(x) as st:
+        rc = L.lib().mxq_awq_gemm(L.ptr(x), L.ptr(kernel.contiguous()), L.ptr(scales.contiguous()),
+                                  L.ptr(zeros.contiguous()), L.ptr(out), M, IC, OC, G, L.ptr(workspace),
+                                  workspace.numel(), st)
+    L.check(rc, "mxq_awq_gemm")
     return out

@@ -29,11 +29,14 @@ class MXQLinear(nn.Module):
 
     GEMV_MAX_TOKENS = 8        # up to here the weight-streaming GEMV wins over a 256-token MMA tile
 
-    def __init__(self, in_features: int, out_features: int, device=None):
+    def __init__(self, in_features: int, out_features: int, device=None, group_perm: torch.Tensor | None = None):
         super().__init__()
         self.in_features, self.out_features = in_features, out_features
         for k, (shape, dt) in ops.packed_shapes(out_features, in_features).items():
             self.register_buffer(k, torch.zeros(shape, dtype=dt, device=device))
+        # importance-driven column order: packed 16-column group g = original group perm[g];
+        # None = the reference's positional recipe
+        self.register_buffer("group_perm", None if group_perm is None else group_perm.to(device=device, dtype=torch.int32))
         self._ws = None
         self._checked = False
         # programmatic dependent launch lets the GEMV fetch its packed weights while the previous
@@ -56,9 +59,9 @@ class MXQLinear(nn.Module):
         return {k: getattr(self, k) for k in PACKED_KEYS}
 
     @classmethod
-    def from_packed(cls, packed: dict) -> "MXQLinear":
+    def from_packed(cls, packed: dict, group_perm: torch.Tensor | None = None) -> "MXQLinear":
         OC, IC = packed["weight"].shape[0], packed["weight"].shape[1] * 16
-        m = cls(IC, OC, device=packed["weight"].device)
+        m = cls(IC, OC, device=packed["weight"].device, group_perm=group_perm)
         for k in PACKED_KEYS:
             getattr(m, k).copy_(packed[k])
         return m
@@ -78,8 +81,10 @@ class MXQLinear(nn.Module):
             ops._check_packed(self.packed)          # once per (re)materialisation of the buffers
             self._checked = True
         if x2.shape[0] <= self.GEMV_MAX_TOKENS:
-            y = ops.gemv(x2, self.packed, validate=False, pdl=self.pdl)
+            y = ops.gemv(x2, self.packed, validate=False, pdl=self.pdl, group_perm=self.group_perm)
         else:
+            if self.group_perm is not None:
+                x2 = ops.gather_groups(x2, self.group_perm)
             need = ops.gemm_workspace_bytes(x2.shape[0], self.in_features, self.out_features)
             if self._ws is None or self._ws.device != x2.device or self._ws.numel() < need:
                 self._ws = torch.empty(need, dtype=torch.uint8, device=x2.device)
@@ -88,22 +93,32 @@ class MXQLinear(nn.Module):
         return y if x.dtype == torch.float16 else y.to(x.dtype)
 
     def dequantize(self, dtype=torch.float16) -> torch.Tensor:
-        return ops.unpack(self.packed, dtype)
+        """The dequantized weight in the ORIGINAL column order."""
+        W = ops.unpack(self.packed, dtype)
+        if self.group_perm is None:
+            return W
+        inv = torch.empty_like(self.group_perm)
+        inv[self.group_perm.long()] = torch.arange(self.group_perm.numel(), dtype=torch.int32, device=inv.device)
+        return W.view(W.shape[0], -1, 16)[:, inv.long()].reshape(W.shape)
 
     def extra_repr(self) -> str:
         return f"in_features={self.in_features}, out_features={self.out_features}, bits=3.0 (2/4 mixed)"
 
 
 @torch.no_grad()
-def pack_linear(linear: nn.Linear, colstat: torch.Tensor | None = None) -> MXQLinear:
+def pack_linear(linear: nn.Linear, colstat: torch.Tensor | None = None, importance: bool = False) -> MXQLinear:
     """Quantize an fp16 nn.Linear into the packed layout (encode policy: DESIGN.md section 2).
-    `colstat`: calibration column statistic, zero = dead column (mxqgpt.py:401-403)."""
+    `colstat`: calibration column statistic (diag(H) of MXQGPT / scaler_row of WrappedGPT), zero = dead
+    column (mxqgpt.py:401-403).  importance=True: of every 4 groups the one with the largest Wanda
+    metric |W| * sqrt(colstat) (prune.py:177) gets the 4 bits instead of the positionally last one."""
     if linear.bias is not None:
         raise ValueError("the MXQ path has no bias (utils_quant.py:613)")
     W = linear.weight.data
     if not W.is_cuda:
         raise RuntimeError("pack_linear needs CUDA weights (no CPU fallback)")
-    return MXQLinear.from_packed(ops.pack(W.half(), colstat))
+    W = W.half()
+    perm = ops.importance_permutation(ops.allocate_group_bits(W, colstat)) if importance else None
+    return MXQLinear.from_packed(ops.pack(W, colstat, group_perm=perm), group_perm=perm)
 
 
 def convert_model(model: nn.Module) -> nn.Module:
@@ -118,7 +133,8 @@ def convert_model(model: nn.Module) -> nn.Module:
 
 def save_packed(model: nn.Module, path: str) -> None:
     """{"format", "linears": {module name: {packed key: tensor}}} of every MXQLinear in `model`."""
-    linears = {n: {k: v.detach().cpu() for k, v in m.packed.items()}
+    linears = {n: dict({k: v.detach().cpu() for k, v in m.packed.items()},
+                       **({"group_perm": m.group_perm.detach().cpu()} if m.group_perm is not None else {}))
                for n, m in model.named_modules() if isinstance(m, MXQLinear)}
     torch.save({"format": FORMAT, "linears": linears}, path)
 
@@ -140,5 +156,7 @@ def load_packed(model: nn.Module, path: str, device=None) -> nn.Module:
             if t is None:
                 t = next(iter(old.buffers()))
             dev = t.device
-        setattr(parent, leaf, MXQLinear.from_packed({k: v.to(dev) for k, v in packed.items()}))
+        perm = packed.get("group_perm")
+        setattr(parent, leaf, MXQLinear.from_packed({k: packed[k].to(dev) for k in PACKED_KEYS},
+                                                    group_perm=None if perm is None else perm.to(dev)))
     return model

@@ -24,9 +24,12 @@ def main(force: bool = False) -> str | None:
     if not os.path.isdir(SRC):
         print("reference sources not present; skipping oracle/_ref build")
         return None
-    if os.path.exists(SO) and not force:
-        return SO
     from torch.utils import cpp_extension as ce
+    if os.path.exists(SO) and not force:
+        if not os.path.exists(os.path.join(OUT, "awq_gemm_ref.so")):
+            inc = [f"-I{p}" for p in ce.include_paths(device_type="cuda")] + [f"-I{sysconfig.get_paths()['include']}"]
+            build_awq_gemm(ce, inc, [f"-L{p}" for p in ce.library_paths(device_type="cuda")])
+        return SO
     os.makedirs(OUT, exist_ok=True)
     inc = [f"-I{p}" for p in ce.include_paths(device_type="cuda")] + [f"-I{sysconfig.get_paths()['include']}"]
     common = ["-O3", "-std=c++17", "-DTORCH_EXTENSION_NAME=mxq_inference_engine", "-DTORCH_API_INCLUDE_EXTENSION_H",
@@ -54,7 +57,30 @@ def main(force: bool = False) -> str | None:
     for o in objs:
         os.remove(o)
     print(SO)
+    build_awq_gemm(ce, inc, libs)
     return SO
+
+
+def build_awq_gemm(ce, inc, libs):
+    """Second module: the reference's AWQ 4-bit GEMM (gemm_cuda_gen.cu) behind oracle/awq_gemm_ref_binding.cpp."""
+    so = os.path.join(OUT, "awq_gemm_ref.so")
+    common = ["-O3", "-std=c++17", "-DTORCH_EXTENSION_NAME=awq_gemm_ref", "-DTORCH_API_INCLUDE_EXTENSION_H",
+              "-D_GLIBCXX_USE_CXX11_ABI=1", "-DENABLE_BF16", f"-I{SRC}"]
+    o1, o2 = os.path.join(OUT, "gemm_cuda_gen.o"), os.path.join(OUT, "awq_binding.o")
+    a = subprocess.Popen(["nvcc", *common, *inc, "-gencode", "arch=compute_100a,code=sm_100a", "--use_fast_math",
+                          "-U__CUDA_NO_HALF_OPERATORS__", "-U__CUDA_NO_HALF_CONVERSIONS__", "--expt-relaxed-constexpr",
+                          "-Xcompiler", "-fPIC", "-c", os.path.join(SRC, "quantization", "gemm_cuda_gen.cu"), "-o", o1])
+    b = subprocess.Popen(["g++", *common, *inc, "-fPIC", "-c", os.path.join(HERE, "awq_gemm_ref_binding.cpp"), "-o", o2])
+    if a.wait() != 0 or b.wait() != 0:
+        print("reference AWQ GEMM failed to compile (tests that need it skip)")
+        return None
+    subprocess.check_call(["g++", "-shared", "-o", so, o1, o2, *libs, "-lc10", "-ltorch", "-ltorch_cpu",
+                           "-ltorch_python", "-lc10_cuda", "-ltorch_cuda", "-lcudart",
+                           "-Wl,-rpath," + ce.library_paths(device_type="cuda")[0]])
+    os.remove(o1)
+    os.remove(o2)
+    print(so)
+    return so
 
 
 if __name__ == "__main__":

@@ -44,8 +44,9 @@ def test_argument_errors_without_gpu():
     assert L.mxq_ste_bwd(None, p16, p16, 16, 0, -2.0, 2.0, None) == -1
     assert L.mxq_ste_bwd(p16, p16, p16, 16, 9, -2.0, 2.0, None) == -3
     assert L.mxq_ptq_quant(p16, p16, None, None, 8, 64, 16, 2, None, p16, 4096, None) == -2   # rows % 16
-    assert L.mxq_ptq_quant(p16, p16, None, None, 16, 64, 32, 2, None, p16, 4096, None) == -5  # group != 16
-    assert L.mxq_ptq_quant(p16, p16, None, None, 16, 64, 16, 2, None, p16, 8, None) == -6     # workspace
+    assert L.mxq_ptq_quant(p16, p16, None, None, 16, 64, 24, 2, None, p16, 4096, None) == -5  # group not 16 / 32 / 48
+    # the mask-driven path needs its workspace (the reference recipe runs one fused kernel without any)
+    assert L.mxq_ptq_quant(p16, p16, None, None, 16, 64, 16, 2, p16, p16, 8, None) == -6      # workspace
     assert L.mxq_rowquant(p16, None, None, None, None, 8, 16, 2, 4, None) == -2               # rows % 16 w/ qq
     pk = _lib.PackedC(p16, p16, p16, p16, p16, p16, p16)
     assert L.mxq_gemv(p16, pk, p16, 1, 100, 64, None) == -2

@@ -48,6 +48,37 @@ def _worker(rank, world, port, q):
                 res[mode] = bool(ok and torch.equal(y, ys.get("nccl", y)))
             except Exception as e:  # report, the parent decides
                 res[mode] = repr(e)[:300]
+        # write-after-read across ranks: back-to-back calls with DIFFERENT inputs while one rank is held
+        # back between the calls; the result of call k must survive until its reader is done even though
+        # the fast rank has already issued call k+1 (double-buffered symmetric output, dist.py)
+        for mode in ("p2p", "mc"):
+            if res.get(mode) is not True:
+                continue
+            lin = mdist.ColumnShardedMXQLinear(local, OC, mode=mode)
+            x2 = (x * 0.5).contiguous()
+            want1, want2 = ys["nccl"], None
+            y1 = lin(x)
+            if rank == 1:
+                torch.cuda._sleep(int(2e8))          # ~0.1 s: rank 1 reads y1 late
+            got1 = y1.clone()
+            y2 = lin(x2)
+            got2 = y2.clone()
+            torch.cuda.synchronize()
+            want2 = mdist.ColumnShardedMXQLinear(local, OC, mode="nccl")(x2)
+            torch.cuda.synchronize()
+            res[mode + "_war"] = bool(torch.equal(got1, want1) and torch.equal(got2, want2))
+        # device guard: the current device differs from the tensors' device
+        other = (rank + 1) % world
+        torch.cuda.set_device(other)
+        yg = ops.gemm(x, p, split_k=False)
+        torch.cuda.synchronize(dev)
+        res["device_guard"] = bool(torch.equal(yg, ref)) and torch.cuda.current_device() == other
+        try:
+            ops.gemv(x[:1].contiguous().to(torch.device("cuda", other)), p)
+            res["mixed_devices"] = "no error"
+        except RuntimeError as e:
+            res["mixed_devices"] = "different devices" in str(e)
+        torch.cuda.set_device(rank)
         dist.barrier()
         if rank == 0:
             q.put(res)
@@ -73,3 +104,6 @@ def test_world2_sharded_gemm(cuda):
     assert res["p2p"] is True, res
     # multicast needs an NVSwitch multicast mapping; where the system has none the mode reports it
     assert res["mc"] is True or "multicast" in str(res["mc"]), res
+    assert res.get("p2p_war") is True, res
+    assert res.get("mc_war", True) is True, res
+    assert res["device_guard"] is True and res["mixed_devices"] is True, res

@@ -152,3 +152,58 @@ def test_full_size_more_shapes(cuda, OC, IC):
     bound = 1e-3 * (x.float().abs() @ Wd.abs().T) + ref.abs() * 2.0 ** -11
     # the fp32 reference itself carries ~K * 2^-24 relative summation noise: well inside the bound
     assert bool(((y - ref).abs() <= bound).all()), float(((y - ref).abs() / bound).max())
+
+
+def _awq_case(M, IC, OC, G, seed):
+    rng = np.random.default_rng(seed)
+    kernel = rng.integers(0, 2 ** 32, (IC, OC // 8), dtype=np.uint64).astype(np.uint32)
+    zeros = rng.integers(0, 2 ** 32, (IC // G, OC // 8), dtype=np.uint64).astype(np.uint32)
+    scales = rng.uniform(0.001, 0.01, (IC // G, OC)).astype(np.float16)
+    x = rng.standard_normal((M, IC)).astype(np.float16)
+    nib = np.array([0, 4, 1, 5, 2, 6, 3, 7], dtype=np.uint32)           # channel c of a word <- nibble nib[c]
+    q = ((kernel[:, :, None] >> (4 * nib)) & 0xF).reshape(IC, OC).astype(np.float64)
+    z = ((zeros[:, :, None] >> (4 * nib)) & 0xF).reshape(IC // G, OC).astype(np.float64)
+    g = np.arange(IC) // G
+    W = scales.astype(np.float64)[g] * (q - z[g])                        # [IC, OC]
+    return x, kernel, scales, zeros, W
+
+
+@pytest.mark.parametrize("M,IC,OC,G", [(48, 512, 256, 128), (512, 4096, 1024, 128), (300, 1024, 192, 64), (2048, 4096, 4096, 128)])
+def test_awq_gemm_vs_oracle(cuda, M, IC, OC, G):
+    """AWQ uniform 4-bit prefill GEMM (gemm_cuda_gen.cu:424-478) against the restated decode + fp64 matmul."""
+    from mxq_b200 import engine
+    x, kernel, scales, zeros, W = _awq_case(M, IC, OC, G, seed=M + OC)
+    ref = x.astype(np.float64) @ W
+    y = engine.gemm_forward_cuda(torch.from_numpy(x).to(cuda), torch.from_numpy(kernel.view(np.int32)).to(cuda),
+                                 torch.from_numpy(scales).to(cuda), torch.from_numpy(zeros.view(np.int32)).to(cuda), 8)
+    bound = 1e-3 * (np.abs(x.astype(np.float64)) @ np.abs(W)) + np.abs(ref) * 2.0 ** -11
+    assert y.shape == (M, OC) and y.dtype == torch.float16
+    assert (np.abs(y.cpu().numpy().astype(np.float64) - ref) <= bound).all()
+
+
+def test_awq_gemm_matches_reference_kernel(cuda):
+    """The reference's own gemm_forward_cuda (compiled from its sources into oracle/_ref/awq_gemm_ref.so by
+    oracle/build_ref.py; the reference never builds it) on random bits: pins the nibble order of kernel and
+    zeros and the scale indexing against real reference code.  The reference sums fp16 split-K partials, so
+    the comparison is within fp16 accumulation noise of the fp64 oracle for both."""
+    import importlib.util
+    import os
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "awq_gemm_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/awq_gemm_ref.so not built (python oracle/build_ref.py)")
+    spec = importlib.util.spec_from_file_location("awq_gemm_ref", so)
+    refmod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(refmod)
+    from mxq_b200 import engine
+    M, IC, OC, G = 16, 1024, 256, 128
+    x, kernel, scales, zeros, W = _awq_case(M, IC, OC, G, seed=5)
+    args = (torch.from_numpy(x).to(cuda), torch.from_numpy(kernel.view(np.int32)).to(cuda),
+            torch.from_numpy(scales).to(cuda), torch.from_numpy(zeros.view(np.int32)).to(cuda))
+    y_ref = refmod.gemm_forward_cuda(*args, 1).float().cpu().numpy()
+    torch.cuda.synchronize()
+    y = engine.gemm_forward_cuda(*args, 1).float().cpu().numpy()
+    exact = x.astype(np.float64) @ W
+    scale = np.abs(exact).max()
+    assert np.abs(y_ref - exact).max() <= 4e-3 * scale, "the restated decode reproduces the reference kernel"
+    assert np.abs(y - exact).max() <= 1e-3 * scale
+    assert np.abs(y - y_ref).max() <= 4e-3 * scale
