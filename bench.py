@@ -685,7 +685,8 @@ def run_gemm70b(ctx, args, pk, iters=10):
     M = 2048
     shapes = {"q/o_proj": (8192, 8192), "k/v_proj": (1024, 8192), "gate/up_proj": (28672, 8192), "down_proj": (8192, 28672)}
     out = {}
-    tot_flops, tot_ms = 0.0, {"gemm": 0.0, "nccl": 0.0, "p2p": 0.0, "mc": 0.0}
+    MODES = ("nccl", "p2p", "mc", "p2p2", "mc2")
+    tot_flops, tot_ms = 0.0, dict.fromkeys(("gemm",) + MODES, 0.0)
     graph_note = {}
 
     def rand_packed(oc, ic):
@@ -738,7 +739,7 @@ def run_gemm70b(ctx, args, pk, iters=10):
         flops = 2.0 * M * oc * ic
         r = {"flops": flops, "tile_bytes_per_rank": M * ocl * 2}
         r["gemm_us"] = 1e3 * timed(lambda: ops.gemm(x, p, out=y, workspace=ws, validate=False), True, "gemm")
-        modes = ["nccl", "p2p", "mc"] if world > 1 else []
+        modes = list(MODES) if world > 1 else []
         for mode in modes:
             try:
                 lin = mdist.ColumnShardedMXQLinear(p, oc, mode=mode)
@@ -756,7 +757,7 @@ def run_gemm70b(ctx, args, pk, iters=10):
         out[name] = r
         del p, x, y
     clk = clocks.stop()
-    complete = [m for m in ("nccl", "p2p", "mc") if world > 1 and all((m + "_us") in r for r in out.values())]
+    complete = [m for m in MODES if world > 1 and all((m + "_us") in r for r in out.values())]
     best = min(complete, key=lambda m: tot_ms[m]) if complete else "gemm"
     tile_bytes = sum(r["tile_bytes_per_rank"] for r in out.values())
     res = {"workload": "Llama-2-70B-shape packed mixed 2/4-bit dequant-GEMM, M = 2048, output columns sharded over the ranks + gathered",
@@ -765,6 +766,11 @@ def run_gemm70b(ctx, args, pk, iters=10):
            "nccl_TFLOPs": tot_flops / tot_ms["nccl"] / 1e9 if "nccl" in complete else None,
            "p2p_TFLOPs": tot_flops / tot_ms["p2p"] / 1e9 if "p2p" in complete else None,
            "mc_TFLOPs": tot_flops / tot_ms["mc"] / 1e9 if "mc" in complete else None,
+           "p2p_phased_TFLOPs": tot_flops / tot_ms["p2p2"] / 1e9 if "p2p2" in complete else None,
+           "mc_phased_TFLOPs": tot_flops / tot_ms["mc2"] / 1e9 if "mc2" in complete else None,
+           "modes": "nccl = GEMM + NCCL all-gather; p2p / mc = exchange stores fused into the GEMM epilogue (peer stores / NVSwitch "
+                    "multicast); p2p2 / mc2 = phased: groups of tiles computed as K slices, each group's reduce + exchange pass on a "
+                    "side stream under the next group's tensor work (mxq_gemm_partials / mxq_gemm_reduce_store)",
            "per_shape": out,
            "nvlink_bytes_per_rank": {"egress_p2p": tile_bytes * (world - 1), "egress_mc": tile_bytes if world > 1 else 0,
                                      "ingress": tile_bytes * (world - 1)},

@@ -259,6 +259,20 @@ MXQ_API int mxq_gemm_multicast(const void* x, mxq_packed_t w, void* y_multicast,
                                int64_t OC, int64_t ldy, int64_t col0, void* workspace,
                                size_t workspace_bytes, void* stream);
 
+/* Phased exchange for shards that are a single partly filled wave (70B shapes at 8 ranks): per group of
+ * weight rows, (1) the GEMM with EVERY tile cut into `split` K slices -- fp32 partials into the
+ * workspace, no output written -- and (2) the second pass alone: slices added in slice order, fp16 rows
+ * stored into the peers' buffers (y_peers, npeers) or once into the multicast mapping (y_multicast, then
+ * y_peers may be NULL).  Run (2) of group g on another stream than (1) of group g+1 and the exchange
+ * overlaps the tensor work (mxq_b200/dist.py, modes "p2p2" / "mc2").  IC % 256 == 0,
+ * 1 <= split <= IC / 256.  workspace: mxq_gemm_partials_workspace_bytes(M, OC, split). */
+MXQ_API size_t mxq_gemm_partials_workspace_bytes(int64_t M, int64_t OC, int split);
+MXQ_API int mxq_gemm_partials(const void* x, mxq_packed_t w, int64_t M, int64_t IC, int64_t OC, int split,
+                              void* workspace, size_t workspace_bytes, void* stream);
+MXQ_API int mxq_gemm_reduce_store(const void* workspace, size_t workspace_bytes, void* const* y_peers, int npeers,
+                                  void* y_multicast, int64_t M, int64_t OC, int split, int64_t ldy, int64_t col0,
+                                  void* stream);
+
 /* Diagnostic: the same tcgen05/TMA pipeline with a dense fp16 B operand W[OC, IC] loaded by TMA
  * instead of dequantized in registers (y = x @ W^T).  Separates UMMA-descriptor errors from
  * dequant/swizzle errors in tests; not part of the reference surface. */

@@ -27,6 +27,7 @@ SYMBOLS = [
     "mxq_ptq_workspace_bytes", "mxq_ptq_quant", "mxq_rowquant",
     "mxq_pack_workspace_bytes", "mxq_pack", "mxq_ptq_quant_pack", "mxq_unpack", "mxq_gemv", "mxq_gemv_ex", "mxq_gemv_grouped", "mxq_gemv_grouped_perm", "mxq_gather_groups", "mxq_awq_gemv", "mxq_awq_gemm_workspace_bytes", "mxq_awq_gemm",
     "mxq_gemm_workspace_bytes", "mxq_gemm", "mxq_gemm_plan", "mxq_gemm_scatter", "mxq_gemm_multicast", "mxq_gemm_dense",
+    "mxq_gemm_partials_workspace_bytes", "mxq_gemm_partials", "mxq_gemm_reduce_store",
 ]
 
 
@@ -90,6 +91,10 @@ def lib() -> C.CDLL:
     L.mxq_gemm_dense.argtypes = [vp, vp, vp, i64, i64, i64, vp]
     L.mxq_gemm_scatter.argtypes = [vp, PackedC, C.POINTER(vp), i32, i64, i64, i64, i64, i64, vp, sz, vp]
     L.mxq_gemm_plan.argtypes = [i64, i64, i64, i32, C.POINTER(C.c_int32), C.POINTER(sz)]
+    L.mxq_gemm_partials_workspace_bytes.restype = sz
+    L.mxq_gemm_partials_workspace_bytes.argtypes = [i64, i64, i32]
+    L.mxq_gemm_partials.argtypes = [vp, PackedC, i64, i64, i64, i32, vp, sz, vp]
+    L.mxq_gemm_reduce_store.argtypes = [vp, sz, C.POINTER(vp), i32, vp, i64, i64, i32, i64, i64, vp]
     L.mxq_gemm_multicast.argtypes = [vp, PackedC, vp, i64, i64, i64, i64, i64, vp, sz, vp]
     _lib = L
     return L

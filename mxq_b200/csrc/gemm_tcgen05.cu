@@ -1097,9 +1097,22 @@ static size_t plan_workspace_bytes(const Plan& pl) {
 }
 
 // CTA-pair kernel: 1-D grid of clusters of 2 (see Plan); workspace (optional) enables the K split
+// force_split > 0: EVERY tile is cut into `force_split` K slices (phased exchange, see mxq_gemm_partials)
+// and only the pair kernel runs; the second pass is launched separately (mxq_gemm_reduce_store).
+static Plan make_plan_forced(int M, int OC, int split) {
+  Plan pl{};
+  pl.mt = ceil_div(M, 2 * pair::BM);
+  pl.nt = ceil_div(OC, pair::BN);
+  pl.tiles = pl.mt * pl.nt;
+  pl.full = 0;
+  pl.split = split;
+  pl.partial_bytes = (size_t)pl.tiles * split * 2 * kPartialSlotBytes;
+  return pl;
+}
+
 template <bool kDenseB>
 static int launch_pair(const void* x, const Params& p, cudaStream_t st, void* workspace = nullptr,
-                       size_t workspace_bytes = 0) {
+                       size_t workspace_bytes = 0, int force_split = 0) {
   CUtensorMap mx, mw;
   int rc = make_map(&mx, x, p.M, p.IC, pair::BM);
   if (rc) return rc;
@@ -1113,13 +1126,15 @@ static int launch_pair(const void* x, const Params& p, cudaStream_t st, void* wo
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::SMEM_BYTES);
   if (e != cudaSuccess) return (int)e;
   Params pp = p;
-  Plan pl = make_plan(p.M, p.IC, p.OC, workspace != nullptr);
-  if (pl.split > 1) {
+  Plan pl = force_split > 0 ? make_plan_forced(p.M, p.OC, force_split) : make_plan(p.M, p.IC, p.OC, workspace != nullptr);
+  if (pl.split > 1 || force_split > 0) {
     const uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
-    if (base + pl.partial_bytes > reinterpret_cast<uintptr_t>(workspace) + workspace_bytes)
+    if (base + pl.partial_bytes > reinterpret_cast<uintptr_t>(workspace) + workspace_bytes) {
+      if (force_split > 0) return MXQ_E_WORKSPACE;
       pl = make_plan(p.M, p.IC, p.OC, false);          // workspace too small: whole tiles only
-    else
+    } else {
       pp.partial = reinterpret_cast<float4*>(base);
+    }
   }
   pp.mt = pl.mt; pp.full = pl.full; pp.split = pl.split;
   const unsigned clusters = (unsigned)(pl.full + (pl.tiles - pl.full) * pl.split);
@@ -1129,7 +1144,7 @@ static int launch_pair(const void* x, const Params& p, cudaStream_t st, void* wo
   if (const char* e = getenv("MXQ_GEMM_DBG")) pp.dbg = atoi(e);
   if (const char* e = getenv("MXQ_GEMM_DBG_PTR")) pp.dbg_host = (unsigned long long*)strtoull(e, nullptr, 0);
   k<<<grid, THREADS, pair::SMEM_BYTES, st>>>(mx, mw, pp);
-  if (pl.split > 1) {
+  if (pl.split > 1 && force_split == 0) {
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     pair::OutPtrs out{};
@@ -1219,6 +1234,7 @@ extern "C" int mxq_gemm_scatter(const void* x, mxq_packed_t w, void* const* y_pe
     return MXQ_E_NULL;
   if (npeers < 1 || npeers > gemm::MAX_PEERS) return MXQ_E_SHAPE;
   if (IC % 64 || IC == 0 || OC % 8 || ldy % 8 || col0 % 8 || col0 + OC > ldy || ldy > INT32_MAX) return MXQ_E_SHAPE;
+  if (M > INT32_MAX || IC > (1 << 24)) return MXQ_E_SHAPE;
   gemm::Params p{};
   p.w = w;
   for (int i = 0; i < npeers; ++i) {
@@ -1247,6 +1263,64 @@ extern "C" int mxq_gemm_multicast(const void* x, mxq_packed_t w, void* y_multica
   p.M = (int)M; p.IC = (int)IC; p.OC = (int)OC;
   // the CTA-pair kernel carries the multicast epilogue; short M runs it too (rows beyond M are masked)
   return gemm::launch_pair<false>(x, p, as_stream(stream), workspace, workspace_bytes);
+}
+
+// ---- phased exchange (column-sharded GEMM whose shard is a single partly filled wave) ----------------
+// At 8 ranks a 70B shard has 16-56 tiles on 74 SM pairs: every tile finishes at the same time and the
+// exchange stores of the fused epilogue (114 us of NVLink ingress per rank for gate/up) follow 93 us of
+// tensor work instead of overlapping it.  The caller cuts the shard's weight rows into groups of N tiles
+// and runs, per group, (1) mxq_gemm_partials: the pair kernel with every tile cut into `split` K slices
+// so that the group alone fills the machine -- fp32 partials go to the workspace -- and (2)
+// mxq_gemm_reduce_store on a second stream: slices added in slice order, fp16 rows stored to the peers /
+// the multicast mapping.  Group g's exchange then runs under group g+1's tensor work.
+extern "C" size_t mxq_gemm_partials_workspace_bytes(int64_t M, int64_t OC, int split) {
+  if (M <= 0 || OC <= 0 || split < 1 || M > INT32_MAX || OC > INT32_MAX) return 256;
+  return 256 + gemm::make_plan_forced((int)M, (int)OC, split).partial_bytes;
+}
+
+extern "C" int mxq_gemm_partials(const void* x, mxq_packed_t w, int64_t M, int64_t IC, int64_t OC, int split,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (M < 0 || IC < 0 || OC < 0) return MXQ_E_SHAPE;
+  if (M == 0 || OC == 0) return MXQ_OK;
+  MXQ_CHECK_PTR(x);
+  MXQ_CHECK_PTR(w.weight);
+  MXQ_CHECK_PTR(workspace);
+  if (!w.weight_last || !w.zeros_and_scales || !w.zeros_2nd || !w.scales_2nd || !w.scales_4b || !w.zeros_4b)
+    return MXQ_E_NULL;
+  if (IC % (4 * gemm::BK) || IC == 0 || OC % 8 || M > INT32_MAX || OC > INT32_MAX || IC > (1 << 24)) return MXQ_E_SHAPE;
+  if (split < 1 || split > IC / (4 * gemm::BK)) return MXQ_E_SHAPE;
+  gemm::Params p{};
+  p.w = w; p.y[0] = nullptr; p.npeers = 1; p.ldy = (int)OC; p.col0 = 0;
+  p.M = (int)M; p.IC = (int)IC; p.OC = (int)OC;
+  return gemm::launch_pair<false>(x, p, as_stream(stream), workspace, workspace_bytes, split);
+}
+
+extern "C" int mxq_gemm_reduce_store(const void* workspace, size_t workspace_bytes, void* const* y_peers, int npeers,
+                                     void* y_multicast, int64_t M, int64_t OC, int split, int64_t ldy, int64_t col0,
+                                     void* stream) {
+  if (M < 0 || OC < 0) return MXQ_E_SHAPE;
+  if (M == 0 || OC == 0) return MXQ_OK;
+  MXQ_CHECK_PTR(workspace);
+  if (M > INT32_MAX || OC > INT32_MAX || OC % 8 || ldy % 8 || col0 % 8 || col0 + OC > ldy || ldy > INT32_MAX || split < 1)
+    return MXQ_E_SHAPE;
+  const gemm::Plan pl = gemm::make_plan_forced((int)M, (int)OC, split);
+  const uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
+  if (base + pl.partial_bytes > reinterpret_cast<uintptr_t>(workspace) + workspace_bytes) return MXQ_E_WORKSPACE;
+  gemm::pair::OutPtrs out{};
+  if (y_multicast) {
+    if (reinterpret_cast<uintptr_t>(y_multicast) & 15) return MXQ_E_ALIGN;
+    out.y[0] = (__half*)y_multicast; out.npeers = 1; out.mc = 1;
+  } else {
+    if (!y_peers || npeers < 1 || npeers > gemm::MAX_PEERS) return MXQ_E_SHAPE;
+    for (int i = 0; i < npeers; ++i) {
+      MXQ_CHECK_PTR(y_peers[i]);
+      out.y[i] = (__half*)y_peers[i];
+    }
+    out.npeers = npeers; out.mc = 0;
+  }
+  gemm::pair::gemm_split_reduce_kernel<<<(unsigned)pl.tiles * 16u, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(base), out, split, 0, pl.mt, (int)M, (int)OC, (int)ldy, (int)col0);
+  MXQ_LAUNCH_RESULT();
 }
 
 extern "C" int mxq_gemm_dense(const void* x, const void* W, void* y, int64_t M, int64_t IC, int64_t OC,

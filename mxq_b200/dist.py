@@ -8,6 +8,12 @@
                         every peer's output buffer over NVLink (symmetric memory, `mode="p2p"`),
                         or into all of them at once through the NVSwitch multicast mapping of
                         that buffer (`mode="mc"`: one multimem.st, egress = the tile once).
+                        `mode="p2p2"` / `"mc2"`: the same stores, but PHASED -- the shard's weight rows
+                        are cut into groups of N tiles, every group is computed as K slices that fill the
+                        machine (mxq_gemm_partials) and its reduce + exchange pass (mxq_gemm_reduce_store)
+                        runs on a side stream under the next group's tensor work.  At 8 ranks a 70B shard
+                        is a single partly filled wave, so without phasing the exchange can only start
+                        when all of the GEMM is done.
 * QAT                 : data parallel, NCCL gradient all-reduce (torch DDP around QuantizeLinear).
 """
 from __future__ import annotations
@@ -100,11 +106,90 @@ class ColumnShardedMXQLinear:
             return self._fused
         import ctypes as C
         bufs = self._symm_out(M, device)
-        self._fused = dict(M=M, pstruct=self.ops.L.packed_struct(self.p), parity=0,
+        self._fused = dict(M=M, pstruct=self.ops.L.packed_struct(self.p), parity=0, phased=None,
                            out=[t for t, _ in bufs], hdl=[h for _, h in bufs],
                            ptrs=[(C.c_void_p * self.world)(*[int(p) for p in h.buffer_ptrs]) for _, h in bufs],
                            mc=[int(getattr(h, "multicast_ptr", 0) or 0) for _, h in bufs])
         return self._fused
+
+    # -- phased exchange ---------------------------------------------------------------------------
+    def _phase_plan(self, M: int):
+        """(groups of (row0, rows), split) or None when the shard cannot be phased (rows not a multiple
+        of the 256-row tile, or K not a multiple of 256)."""
+        import os
+        BN, BM2, PAIRS = 256, 512, 74
+        if self.OC_local % BN or self.IC % 256 or self.OC_local < 2 * BN:
+            return None
+        nt, mt = self.OC_local // BN, -(-M // BM2)
+        G = int(os.environ.get("MXQ_DIST_PHASES", "0")) or (2 if nt < 8 else 4)
+        G = max(2, min(G, nt))
+        base, extra = divmod(nt, G)
+        groups, t0 = [], 0
+        for g in range(G):
+            n = base + (1 if g < extra else 0)
+            groups.append((t0 * BN, n * BN))
+            t0 += n
+        tiles = max(n // BN for _, n in groups) * mt
+        split = max(1, min(8, PAIRS // tiles, self.IC // 1024))     # a slice keeps >= 16 K blocks
+        return groups, split
+
+    def _phased_state(self, M: int, device):
+        st = self._fused_state(M, device)
+        if st.get("phased") is None:
+            plan = self._phase_plan(M)
+            if plan is None:
+                st["phased"] = False
+            else:
+                import ctypes as C
+                groups, split = plan
+                L = self.ops.L
+                need = max(L.lib().mxq_gemm_partials_workspace_bytes(M, rows, split) for _, rows in groups)
+                sliced = []
+                for row0, rows in groups:
+                    q = dict(weight=self.p["weight"][row0:row0 + rows], weight_last=self.p["weight_last"][row0:row0 + rows],
+                             zeros_and_scales=self.p["zeros_and_scales"][row0:row0 + rows],
+                             zeros_2nd=self.p["zeros_2nd"][row0 // 4:(row0 + rows) // 4],
+                             scales_2nd=self.p["scales_2nd"][row0 // 4:(row0 + rows) // 4],
+                             scales_4b=self.p["scales_4b"][row0:row0 + rows], zeros_4b=self.p["zeros_4b"][row0 // 8:(row0 + rows) // 8])
+                    sliced.append((L.packed_struct(q), row0, rows, q))   # row slices are contiguous views: no copies
+                st["phased"] = dict(split=split, groups=sliced,
+                                    ws=[torch.empty(int(need), dtype=torch.uint8, device=device) for _ in range(2)],
+                                    side=torch.cuda.Stream(device=device),
+                                    ev_part=[torch.cuda.Event() for _ in sliced], ev_red=[torch.cuda.Event() for _ in sliced],
+                                    null_peers=(C.c_void_p * 1)(None))
+        return st
+
+    def _forward_phased(self, x: torch.Tensor, multicast: bool) -> torch.Tensor:
+        L = self.ops.L
+        M = x.shape[0]
+        st = self._phased_state(M, x.device)
+        ph = st["phased"]
+        if not ph:
+            return None
+        b = st["parity"]
+        st["parity"] = b ^ 1
+        if multicast and not st["mc"][b]:
+            raise RuntimeError("symmetric memory has no multicast mapping on this system (mode='mc2')")
+        main = torch.cuda.current_stream(x.device)
+        side = ph["side"]
+        col_base = self.rank * self.OC_local
+        lib = L.lib()
+        with L.on(x):
+            for g, (pstruct, row0, rows, _keep) in enumerate(ph["groups"]):
+                ws = ph["ws"][g & 1]
+                if g >= 2:
+                    main.wait_event(ph["ev_red"][g - 2])          # the workspace of group g-2 has been reduced
+                L.check(lib.mxq_gemm_partials(x.data_ptr(), pstruct, M, self.IC, rows, ph["split"], ws.data_ptr(), ws.numel(),
+                                              main.cuda_stream), "mxq_gemm_partials")
+                ph["ev_part"][g].record(main)
+                side.wait_event(ph["ev_part"][g])
+                L.check(lib.mxq_gemm_reduce_store(ws.data_ptr(), ws.numel(), None if multicast else st["ptrs"][b], 0 if multicast else self.world,
+                                                  st["mc"][b] if multicast else None, M, rows, ph["split"], self.OC_total,
+                                                  col_base + row0, side.cuda_stream), "mxq_gemm_reduce_store")
+                ph["ev_red"][g].record(side)
+            main.wait_stream(side)
+        st["hdl"][b].barrier(channel=0)
+        return st["out"][b]
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         ops = self.ops
@@ -114,7 +199,14 @@ class ColumnShardedMXQLinear:
             self._ws_M = M
         if self.world == 1:
             return ops.gemm(x, self.p, workspace=self._ws, validate=False)
-        if self.mode in ("mc", "p2p"):
+        if self.mode in ("mc2", "p2p2") and self.world > 1:
+            if not x.is_cuda or x.dtype != torch.float16 or not x.is_contiguous() or x.dim() != 2 or x.shape[1] != self.IC:
+                raise ValueError(f"x must be a contiguous CUDA fp16 [M, {self.IC}] tensor")
+            y = self._forward_phased(x, self.mode == "mc2")
+            if y is not None:
+                return y
+            # shards that cannot be phased (fewer than two 256-row tiles) take the fused epilogue
+        if self.mode in ("mc", "p2p", "mc2", "p2p2"):
             # argument marshalling is cached per M: at 8 ranks a shard's GEMM is ~100 us and the
             # Python call path must not be the longer one
             st = self._fused_state(M, x.device)
@@ -125,7 +217,7 @@ class ColumnShardedMXQLinear:
             b = st["parity"]
             st["parity"] = b ^ 1
             with L.on(x) as stream:
-                if self.mode == "mc":
+                if self.mode in ("mc", "mc2"):
                     if not st["mc"][b]:
                         raise RuntimeError("symmetric memory has no multicast mapping on this system (mode='mc')")
                     rc = L.lib().mxq_gemm_multicast(x.data_ptr(), st["pstruct"], st["mc"][b], M, self.IC, self.OC_local,
@@ -134,7 +226,7 @@ class ColumnShardedMXQLinear:
                     rc = L.lib().mxq_gemm_scatter(x.data_ptr(), st["pstruct"], st["ptrs"][b], self.world, M, self.IC,
                                                   self.OC_local, self.OC_total, col0, self._ws.data_ptr(),
                                                   self._ws.numel(), stream)
-            L.check(rc, "mxq_gemm_" + ("multicast" if self.mode == "mc" else "scatter"))
+            L.check(rc, "mxq_gemm_" + ("multicast" if self.mode in ("mc", "mc2") else "scatter"))
             st["hdl"][b].barrier(channel=0)    # every rank's tiles have landed in every rank's buffer
             return st["out"][b]
         y_local = ops.gemm(x, self.p, workspace=self._ws, validate=False)

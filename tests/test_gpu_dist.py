@@ -48,6 +48,18 @@ def _worker(rank, world, port, q):
                 res[mode] = bool(ok and torch.equal(y, ys.get("nccl", y)))
             except Exception as e:  # report, the parent decides
                 res[mode] = repr(e)[:300]
+        # phased exchange (K-sliced groups + reduce/store pass on a side stream): slices are added in fp32 in
+        # slice order, so it matches the one-pass result within the GEMM tolerance, not bit for bit
+        for mode in ("p2p2", "mc2"):
+            try:
+                lin = mdist.ColumnShardedMXQLinear(local, OC, mode=mode)
+                assert lin._phase_plan(M) is not None
+                outs = [lin(x).clone() for _ in range(3)]          # both buffer parities
+                torch.cuda.synchronize()
+                ok = all(float((y.float() - ref.float()).abs().max() / ref.float().abs().max()) <= 1e-3 for y in outs)
+                res[mode] = bool(ok and torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]))
+            except Exception as e:
+                res[mode] = repr(e)[:300]
         # write-after-read across ranks: back-to-back calls with DIFFERENT inputs while one rank is held
         # back between the calls; the result of call k must survive until its reader is done even though
         # the fast rank has already issued call k+1 (double-buffered symmetric output, dist.py)
@@ -104,6 +116,8 @@ def test_world2_sharded_gemm(cuda):
     assert res["p2p"] is True, res
     # multicast needs an NVSwitch multicast mapping; where the system has none the mode reports it
     assert res["mc"] is True or "multicast" in str(res["mc"]), res
+    assert res["p2p2"] is True, res
+    assert res["mc2"] is True or "multicast" in str(res["mc2"]), res
     assert res.get("p2p_war") is True, res
     assert res.get("mc_war", True) is True, res
     assert res["device_guard"] is True and res["mixed_devices"] is True, res
