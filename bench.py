@@ -471,12 +471,22 @@ def run_components(ctx, pk, with_cpu=True):
                                         ops.L.dtype_enum(xs[k]), -2.0, 2.0, st()), "ste")
         mf, mb = graph_time(torch, fwd, 30), graph_time(torch, bwd, 30)
         m128 = graph_time(torch, lambda i: fwd(i, 128), 30)
+        # four weights per launch (QAT: q/k/v/o of a decoder layer through FakeQuantGroup) and the same
+        # weight under an importance mask (allocate_group_bits) on the row-resident kernel
+        m4 = graph_time(torch, lambda i: ops.fakequant_fwd_multi([xs[(i + j) % nset] for j in range(4)],
+                                                                 outs=[outs[(i + j) % nset] for j in range(4)]), 12) / 4
+        gb = ops.allocate_group_bits(xs[0].half(), torch.rand(4096, device=dev) + 0.1)
+        mmask = graph_time(torch, lambda i: ops.fakequant_fwd_multi([xs[i % nset]], pooled_mask=gb, outs=[outs[i % nset]]), 30)
         comp = {"workload": f"MXAsymQuantizer fwd + STE bwd, 4096x4096 {name} (Llama-2-7B q_proj), group 16 {{2,2,2 | pooled 4}}",
                 "fwd": {"ms": mf, "roofline": hbm_roof(2 * nb, mf, "fakequant_row_kernel", f"fq_{name}")},
                 "bwd": {"ms": mb, "roofline": hbm_roof(3 * nb, mb, "ste_bwd_kernel", f"ste_{name}")},
                 "fwd_group128": {"ms": m128, "roofline": hbm_roof(2 * nb, m128, "fakequant_row_kernel", f"fq128_{name}"),
                                  "note": "BASELINE configs[0] names 'group 128': the same recipe over 512-column blocks "
                                          "(no reference implementation; oracle-checked)"},
+                "fwd_4_weights_per_launch": {"ms_per_weight": m4, "GBps": 2 * nb / m4 / 1e6, "frac_hbm": 2 * nb / m4 / 1e6 / pk["hbm"],
+                                             "note": "mxq_fakequant_fwd_multi: q/k/v/o of a layer in one launch (FakeQuantGroup in the QAT step)"},
+                "fwd_importance_mask": {"ms": mmask, "GBps": 2 * nb / mmask / 1e6, "frac_hbm": 2 * nb / mmask / 1e6 / pk["hbm"],
+                                        "note": "allocate_group_bits mask (which group of every 4 is pooled) on the row-resident kernel"},
                 "GBps_fwd_plus_bwd": 5 * nb / (mf + mb) / 1e6, "frac_hbm_fwd_plus_bwd": 5 * nb / (mf + mb) / 1e6 / pk["hbm"]}
         # e2e: the autograd function with HOST tensors: W and the upstream gradient come from pinned
         # memory, the fake-quantized weight and the STE gradient go back

@@ -57,6 +57,17 @@ MXQ_API const char* mxq_error_string(int code);
 MXQ_API int mxq_fakequant_fwd(const void* x, void* out, uint8_t* codes, int64_t rows, int64_t cols,
                       int dtype, int group, int low_bits, const uint8_t* group_bits, void* stream);
 
+/* Row-resident variant for several weights at once and / or an importance mask:
+ *  - x / out / rows are HOST arrays of n entries; all tensors have `cols` columns and one dtype.  One
+ *    launch covers up to 8 tensors (QAT fake-quantizes the 4 + 2 same-width linears of a decoder layer
+ *    back to back; a 67 MB launch alone spends a fifth of its time in ramp and tail).
+ *  - pooled_mask (optional, uint8[cols / group]): only the POOL flag (0x80) is read -- WHICH groups share
+ *    the row's 4-bit statistic (mxq_allocate_bits); every other group is `low_bits` wide.  NULL = the
+ *    positional recipe.  Exactly the arithmetic of mxq_fakequant_fwd (bit-identical outputs).
+ *  group 16 or 128; rows of at most 3072 16-byte chunks; 16-bit dtypes with low_bits == 2. */
+MXQ_API int mxq_fakequant_fwd_multi(const void* const* x, void* const* out, const int64_t* rows, int n, int64_t cols,
+                                    int dtype, int group, int low_bits, const uint8_t* pooled_mask, void* stream);
+
 /* ---- (a-2) MXAsymQuantizer.backward   utils_quant.py:464-475 ---------------------------------
  * grad_in = grad_out; grad_in[x >= hi] = 0; grad_in[x <= lo] = 0.   n = number of elements. */
 MXQ_API int mxq_ste_bwd(const void* grad_out, const void* x, void* grad_in, int64_t n, int dtype,

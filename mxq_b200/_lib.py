@@ -20,7 +20,7 @@ _DTYPE = {torch.float32: MXQ_F32, torch.float16: MXQ_F16, torch.bfloat16: MXQ_BF
 
 # every symbol include/mxq_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    "mxq_version", "mxq_error_string", "mxq_fakequant_fwd", "mxq_ste_bwd",
+    "mxq_version", "mxq_error_string", "mxq_fakequant_fwd", "mxq_fakequant_fwd_multi", "mxq_ste_bwd",
     "mxq_segquant_workspace_bytes", "mxq_segquant_fwd",
     "mxq_colsumsq_workspace_bytes", "mxq_colsumsq", "mxq_colsumsq_ex", "mxq_wanda_metric",
     "mxq_allocate_bits_workspace_bytes", "mxq_allocate_bits",
@@ -55,6 +55,7 @@ def lib() -> C.CDLL:
     L.mxq_error_string.restype = C.c_char_p
     L.mxq_error_string.argtypes = [i32]
     L.mxq_fakequant_fwd.argtypes = [vp, vp, vp, i64, i64, i32, i32, i32, vp, vp]
+    L.mxq_fakequant_fwd_multi.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i32, i64, i32, i32, i32, vp, vp]
     L.mxq_ste_bwd.argtypes = [vp, vp, vp, i64, i32, f32, f32, vp]
     L.mxq_segquant_workspace_bytes.restype = sz
     L.mxq_segquant_workspace_bytes.argtypes = [i64, i64, i32]

@@ -314,9 +314,20 @@ __global__ void __launch_bounds__(kFQThreads) fakequant_fwd_kernel(const FQParam
 // on B200 for rows of up to 3072 chunks (profiles/): more independent loads in flight per SM and
 // no per-stage block barrier.
 // -------------------------------------------------------------------------------------------
-template <typename T, int THREADS, int NC, int G = 16>
-__global__ void __launch_bounds__(THREADS) fakequant_row_kernel(const uint4* __restrict__ x,
-                                                                uint4* __restrict__ out, int cpr,
+// Up to kFQMaxTensors weights of the same row length in ONE launch (QAT quantizes q/k/v/o, then gate/up,
+// of every decoder layer back to back: 672 launches of 15-25 us per step, each paying its own ramp and
+// tail; profiles/): grid = total rows, a CTA finds its tensor in the prefix table.
+constexpr int kFQMaxTensors = 8;
+struct FQRowTable {
+  const uint4* x[kFQMaxTensors];
+  uint4* out[kFQMaxTensors];
+  int row_end[kFQMaxTensors];     // exclusive prefix sums of the row counts
+  int n;
+  const uint8_t* pooled_mask;     // optional group_bits: only its POOL flag is read (which groups are pooled)
+};
+
+template <typename T, int THREADS, int NC, int G = 16, bool kMask = false>
+__global__ void __launch_bounds__(THREADS) fakequant_row_kernel(const __grid_constant__ FQRowTable tab, int cpr,
                                                                 int low_bits) {
   using D = DT<T>;
   constexpr bool k16 = sizeof(T) == 2;
@@ -327,9 +338,19 @@ __global__ void __launch_bounds__(THREADS) fakequant_row_kernel(const uint4* __r
   static_assert(LPG == 2 || LPG == 4 || LPG == 16 || LPG == 32, "group of 16 or 128 columns");
   __shared__ float2 part[THREADS / 32];
   const float kEps = D::rnd(1e-8f);
-  const uint4* xr = x + (size_t)blockIdx.x * cpr;
-  uint4* orow = out + (size_t)blockIdx.x * cpr;
+  int ti = 0, row = (int)blockIdx.x;
+#pragma unroll 1
+  while (ti + 1 < tab.n && row >= tab.row_end[ti]) ++ti;
+  if (ti > 0) row -= tab.row_end[ti - 1];
+  const uint4* xr = tab.x[ti] + (size_t)row * cpr;
+  uint4* orow = tab.out[ti] + (size_t)row * cpr;
   const int lane = threadIdx.x & 31;
+  // which groups share the row's pooled statistic: every fourth one (the reference's positional recipe,
+  // utils_quant.py:349-353) or the ones flagged in the mask (importance-driven allocation)
+  auto is_pooled = [&](int c) -> bool {
+    if (kMask) return (__ldg(tab.pooled_mask + (c >> LPG_SHIFT)) & MXQ_POOL_FLAG) != 0;
+    return ((c >> LPG_SHIFT) & 3) == 3;
+  };
 
   uint4 ch[NC];
 #pragma unroll
@@ -342,7 +363,7 @@ __global__ void __launch_bounds__(THREADS) fakequant_row_kernel(const uint4* __r
 #pragma unroll
   for (int i = 0; i < NC; ++i) {
     const int c = i * THREADS + threadIdx.x;
-    if (c < cpr && ((c >> LPG_SHIFT) & 3) == 3) {
+    if (c < cpr && is_pooled(c)) {
       float f[EPC];
       D::unpack(ch[i], f);
 #pragma unroll
@@ -366,7 +387,7 @@ __global__ void __launch_bounds__(THREADS) fakequant_row_kernel(const uint4* __r
   for (int i = 0; i < NC; ++i) {
     const int c = i * THREADS + threadIdx.x;
     const bool valid = c < cpr;          // cpr % LPG == 0 and THREADS % LPG == 0: groups never straddle
-    const bool pooled = ((c >> LPG_SHIFT) & 3) == 3;
+    const bool pooled = valid && is_pooled(c);
     if constexpr (k16) {
       uint32_t mn = P::vmin(P::vmin(ch[i].x, ch[i].y), P::vmin(ch[i].z, ch[i].w));
       uint32_t mx = P::vmax(P::vmax(ch[i].x, ch[i].y), P::vmax(ch[i].z, ch[i].w));
@@ -448,20 +469,38 @@ __global__ void __launch_bounds__(THREADS) fakequant_row_kernel(const uint4* __r
   }
 }
 
-template <typename T, int G = 16>
-static bool launch_fq_row(const FQParams& p, cudaStream_t st) {
-  const int c = p.cpr;
-  const uint4* x = (const uint4*)p.x;
-  uint4* o = (uint4*)p.out;
-  const unsigned g = (unsigned)p.rows;
-  if (c <= 256) fakequant_row_kernel<T, 128, 2, G><<<g, 128, 0, st>>>(x, o, c, p.low_bits);
-  else if (c <= 512) fakequant_row_kernel<T, 128, 4, G><<<g, 128, 0, st>>>(x, o, c, p.low_bits);
-  else if (c <= 1024) fakequant_row_kernel<T, 256, 4, G><<<g, 256, 0, st>>>(x, o, c, p.low_bits);
-  else if (c <= 1536) fakequant_row_kernel<T, 256, 6, G><<<g, 256, 0, st>>>(x, o, c, p.low_bits);
-  else if (c <= 2048) fakequant_row_kernel<T, 256, 8, G><<<g, 256, 0, st>>>(x, o, c, p.low_bits);
-  else if (c <= 3072) fakequant_row_kernel<T, 256, 12, G><<<g, 256, 0, st>>>(x, o, c, p.low_bits);
+template <typename T, int G, bool kMask>
+static bool launch_fq_row_tab(const FQRowTable& tab, int c, int low_bits, cudaStream_t st) {
+  const unsigned g = (unsigned)tab.row_end[tab.n - 1];
+  if (c <= 256) fakequant_row_kernel<T, 128, 2, G, kMask><<<g, 128, 0, st>>>(tab, c, low_bits);
+  else if (c <= 512) fakequant_row_kernel<T, 128, 4, G, kMask><<<g, 128, 0, st>>>(tab, c, low_bits);
+  else if (c <= 1024) fakequant_row_kernel<T, 256, 4, G, kMask><<<g, 256, 0, st>>>(tab, c, low_bits);
+  else if (c <= 1536) fakequant_row_kernel<T, 256, 6, G, kMask><<<g, 256, 0, st>>>(tab, c, low_bits);
+  else if (c <= 2048) fakequant_row_kernel<T, 256, 8, G, kMask><<<g, 256, 0, st>>>(tab, c, low_bits);
+  else if (c <= 3072) fakequant_row_kernel<T, 256, 12, G, kMask><<<g, 256, 0, st>>>(tab, c, low_bits);
   else return false;
   return true;
+}
+
+template <typename T, int G = 16>
+static bool launch_fq_row(const FQParams& p, cudaStream_t st) {
+  FQRowTable tab{};
+  tab.x[0] = (const uint4*)p.x; tab.out[0] = (uint4*)p.out; tab.row_end[0] = p.rows; tab.n = 1;
+  return launch_fq_row_tab<T, G, false>(tab, p.cpr, p.low_bits, st);
+}
+
+// dtype x {16, 128} x {positional, masked}
+static bool launch_fq_row_any(const FQRowTable& tab, int dtype, int group, int cpr, int low_bits, cudaStream_t st) {
+  const bool m = tab.pooled_mask != nullptr;
+#define MXQ_FQ_ROW(T)                                                                                       \
+  (group == 16 ? (m ? launch_fq_row_tab<T, 16, true>(tab, cpr, low_bits, st) : launch_fq_row_tab<T, 16, false>(tab, cpr, low_bits, st)) \
+               : (m ? launch_fq_row_tab<T, 128, true>(tab, cpr, low_bits, st) : launch_fq_row_tab<T, 128, false>(tab, cpr, low_bits, st)))
+  switch (dtype) {
+    case MXQ_F32: return MXQ_FQ_ROW(float);
+    case MXQ_F16: return MXQ_FQ_ROW(__half);
+    default: return MXQ_FQ_ROW(__nv_bfloat16);
+  }
+#undef MXQ_FQ_ROW
 }
 
 // -------------------------------------------------------------------------------------------
@@ -636,6 +675,43 @@ extern "C" int mxq_fakequant_fwd(const void* x, void* out, uint8_t* codes, int64
     case MXQ_F16: return launch_fq<__half>(p, ref, smem, grid, st);
     default: return launch_fq<__nv_bfloat16>(p, ref, smem, grid, st);
   }
+}
+
+// Several weights of one row length in one launch, and/or a mask that moves the pooled group
+// (importance-driven allocation): both run the row-resident kernel.
+extern "C" int mxq_fakequant_fwd_multi(const void* const* x, void* const* out, const int64_t* rows, int n,
+                                       int64_t cols, int dtype, int group, int low_bits,
+                                       const uint8_t* pooled_mask, void* stream) {
+  if (n < 0 || cols < 0) return MXQ_E_SHAPE;
+  if (n == 0 || cols == 0) return MXQ_OK;
+  if (!x || !out || !rows) return MXQ_E_NULL;
+  if (dtype != MXQ_F32 && dtype != MXQ_F16 && dtype != MXQ_BF16) return MXQ_E_DTYPE;
+  const int esize = dtype == MXQ_F32 ? 4 : 2;
+  if ((group != 16 && group != 128) || cols % (4 * group) || cols > (1 << 24)) return MXQ_E_SHAPE;
+  if (low_bits < 1 || low_bits > 8 || (esize == 2 && low_bits != 2)) return MXQ_E_UNSUPPORTED;
+  const int cpr = (int)(cols * esize / 16);
+  if (cpr > 3072) return MXQ_E_UNSUPPORTED;      // longer rows: mxq_fakequant_fwd (shared-memory ring)
+  cudaStream_t st = as_stream(stream);
+  for (int i0 = 0; i0 < n; i0 += kFQMaxTensors) {
+    FQRowTable tab{};
+    tab.pooled_mask = pooled_mask;
+    int64_t total = 0;
+    for (int i = i0; i < n && i < i0 + kFQMaxTensors; ++i) {
+      if (rows[i] < 0 || rows[i] > INT32_MAX) return MXQ_E_SHAPE;
+      if (rows[i] == 0) continue;
+      MXQ_CHECK_PTR(x[i]);
+      MXQ_CHECK_PTR(out[i]);
+      total += rows[i];
+      if (total > INT32_MAX) return MXQ_E_SHAPE;
+      tab.x[tab.n] = (const uint4*)x[i]; tab.out[tab.n] = (uint4*)out[i]; tab.row_end[tab.n] = (int)total;
+      ++tab.n;
+    }
+    if (tab.n == 0) continue;
+    if (!launch_fq_row_any(tab, dtype, group, cpr, low_bits, st)) return MXQ_E_UNSUPPORTED;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  return MXQ_OK;
 }
 
 extern "C" int mxq_ste_bwd(const void* grad_out, const void* x, void* grad_in, int64_t n,

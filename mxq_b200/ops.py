@@ -24,13 +24,19 @@ def _ws(nbytes: int, device) -> torch.Tensor:
 
 
 def fakequant_fwd(x: torch.Tensor, num_bits: int = 2, group: int = 16, group_bits=None,
-                  return_codes: bool = False):
-    """MXAsymQuantizer.forward (utils_quant.py:315-462) for a 2-D tensor."""
+                  return_codes: bool = False, uniform_low: bool = False):
+    """MXAsymQuantizer.forward (utils_quant.py:315-462) for a 2-D tensor.  uniform_low=True promises
+    that `group_bits` only MOVES the pooled 4-bit group (every other group is `num_bits` wide -- what
+    allocate_group_bits produces): the row-resident kernel then serves the mask instead of the
+    shared-memory ring kernel (same bits, 1.5-2x faster)."""
     if x.dim() != 2:
         raise ValueError("MXAsymQuantizer fake-quant is defined for 2-D weights (utils_quant.py:630)")
     L.require_cuda(x, group_bits)
     x = x.contiguous()
     rows, cols = x.shape
+    if uniform_low and group_bits is not None and not return_codes and group in (16, 128) and cols % (4 * group) == 0 \
+            and cols * x.element_size() <= 3072 * 16 and (x.element_size() == 4 or num_bits == 2):
+        return fakequant_fwd_multi([x], num_bits, group, pooled_mask=group_bits)[0]
     if cols % 64 and group_bits is None and group == 16:
         # the reference itself fails here: W_4b has K/64*16 columns (utils_quant.py:347,368)
         raise ValueError("in_features must be a multiple of 64 for the mixed 2/4-bit recipe")
@@ -41,6 +47,32 @@ def fakequant_fwd(x: torch.Tensor, num_bits: int = 2, group: int = 16, group_bit
                                        group, num_bits, L.ptr(group_bits), st)
     L.check(rc, "mxq_fakequant_fwd")
     return (out, codes) if return_codes else out
+
+
+def fakequant_fwd_multi(xs: list, num_bits: int = 2, group: int = 16, pooled_mask: torch.Tensor | None = None,
+                        outs: list | None = None) -> list:
+    """MXAsymQuantizer.forward for several 2-D weights of ONE width and dtype in a single launch (the
+    row-resident kernel; mxq_fakequant_fwd_multi).  pooled_mask: uint8[cols / group] from
+    allocate_group_bits -- which groups share the row's 4-bit statistic (None = the positional recipe)."""
+    import ctypes as C
+    if not xs:
+        return []
+    L.require_cuda(*xs, pooled_mask)
+    cols, dt = xs[0].shape[1], xs[0].dtype
+    if any(x.dim() != 2 or x.shape[1] != cols or x.dtype != dt for x in xs):
+        raise ValueError("fakequant_fwd_multi: 2-D tensors of one width and dtype")
+    xs = [x.contiguous() for x in xs]
+    if outs is None:
+        outs = [torch.empty_like(x) for x in xs]
+    n = len(xs)
+    xa = (C.c_void_p * n)(*[x.data_ptr() for x in xs])
+    oa = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+    ra = (C.c_int64 * n)(*[x.shape[0] for x in xs])
+    with L.on(xs[0]) as st:
+        rc = L.lib().mxq_fakequant_fwd_multi(xa, oa, ra, n, cols, L.dtype_enum(xs[0]), group, num_bits,
+                                             L.ptr(pooled_mask), st)
+    L.check(rc, "mxq_fakequant_fwd_multi")
+    return outs
 
 
 def ste_bwd(grad_out: torch.Tensor, x: torch.Tensor, lo: float, hi: float) -> torch.Tensor:

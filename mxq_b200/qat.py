@@ -15,20 +15,25 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .utils_quant import QuantizeLinear
+from .utils_quant import QuantizeLinear, group_quantize_linears
 
 
-def convert_linears(model: nn.Module, w_bits: int = 2, skip=("lm_head",)) -> int:
-    """Replace nn.Linear modules (except `skip`) by QuantizeLinear sharing the same weight."""
+def convert_linears(model: nn.Module, w_bits: int = 2, skip=("lm_head",), group: bool = True) -> int:
+    """Replace nn.Linear modules (except `skip`) by QuantizeLinear sharing the same weight.  group=True:
+    siblings of one width under one parent (q/k/v/o, gate/up) fake-quantize in one launch per forward."""
     n = 0
     for name, mod in list(model.named_modules()):
+        converted = []
         for cname, child in list(mod.named_children()):
             full = f"{name}.{cname}" if name else cname
             if type(child) is nn.Linear and not any(s in full for s in skip):
                 q = QuantizeLinear(child.in_features, child.out_features, w_bits=w_bits, a_bits=32)
                 q.weight = child.weight
                 setattr(mod, cname, q)
+                converted.append(q)
                 n += 1
+        if group and len(converted) > 1:
+            group_quantize_linears(converted)
     return n
 
 

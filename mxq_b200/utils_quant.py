@@ -107,6 +107,63 @@ class MXAsymQuantizer(torch.autograd.Function):
         return grad_input, None, None, None
 
 
+class MXAsymQuantizerMulti(torch.autograd.Function):
+    """MXAsymQuantizer over several weights of one width in ONE launch each way it matters: forward =
+    mxq_fakequant_fwd_multi, backward = the clipped straight-through estimator per tensor.  Numerically
+    identical to calling MXAsymQuantizer.apply on every weight."""
+
+    @staticmethod
+    def forward(ctx, clip_val, num_bits, *weights):
+        ctx.save_for_backward(clip_val, *weights)
+        return tuple(ops.fakequant_fwd_multi(list(weights), num_bits=int(num_bits), group=16))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        clip_val, *weights = ctx.saved_tensors
+        out = []
+        for g, w in zip(grads, weights):
+            if g is None:
+                out.append(None)
+            else:
+                lo, hi = _clip_bounds(clip_val, w.dtype)
+                out.append(ops.ste_bwd(g, w, lo, hi))
+        return (None, None, *out)
+
+
+class FakeQuantGroup:
+    """QuantizeLinear modules of one width that are evaluated together in every forward (q/k/v/o of an
+    attention block, gate/up of an MLP): the first member to run fake-quantizes ALL members' weights in
+    one launch, the others pick their result up.  A result is handed out once per forward; the group
+    falls back to per-module launches whenever its bookkeeping does not match (a member skipped, grad
+    mode changed, weights updated in between)."""
+
+    def __init__(self, members):
+        self.members = list(members)
+        for m in self.members:
+            m._fq_group = self
+        self._pending = {}
+        self._key = None
+
+    def weight_for(self, module):
+        ws = [m.weight for m in self.members]
+        key = (torch.is_grad_enabled(), tuple(w._version for w in ws), tuple(w.data_ptr() for w in ws))
+        if id(module) not in self._pending or key != self._key:
+            outs = MXAsymQuantizerMulti.apply(_CLIP, module.w_bits, *ws)
+            self._pending = {id(m): o for m, o in zip(self.members, outs)}
+            self._key = key
+        return self._pending.pop(id(module))
+
+
+def group_quantize_linears(modules) -> list:
+    """Form FakeQuantGroups from QuantizeLinear siblings of equal in_features / w_bits / dtype (same parent
+    module = evaluated in the same forward).  Returns the groups; un-groupable modules stay as they are."""
+    buckets = {}
+    for m in modules:
+        if isinstance(m, QuantizeLinear) and 2 <= m.w_bits < 32 and not m.weight_layerwise:
+            buckets.setdefault((m.in_features, m.w_bits, m.weight.dtype, m.weight.device), []).append(m)
+    return [FakeQuantGroup(ms) for ms in buckets.values() if len(ms) > 1]
+
+
 class QuantizeLinear(nn.Linear):
     """nn.Linear whose weight is fake-quantized on every forward (utils_quant.py:601-727).
     Constructor keywords and state-dict keys (``weight`` only; bias always off, :613) match."""
@@ -129,9 +186,13 @@ class QuantizeLinear(nn.Linear):
         if self.w_bits >= 32:
             weight = self.weight
         elif self.w_bits >= 2:
-            weight_clip_val = _CLIP                              # utils_quant.py:636
-            weight = MXAsymQuantizer.apply(real_weights, weight_clip_val, self.w_bits,
-                                           self.weight_layerwise)
+            grp = getattr(self, "_fq_group", None)
+            if grp is not None:
+                weight = grp.weight_for(self)                    # one launch for the whole sibling group
+            else:
+                weight_clip_val = _CLIP                          # utils_quant.py:636
+                weight = MXAsymQuantizer.apply(real_weights, weight_clip_val, self.w_bits,
+                                               self.weight_layerwise)
         else:
             # w_bits == 1 sign quantizer / BiT-style branch (:649-715): outside the MXQ path.
             raise NotImplementedError("w_bits < 2 is not part of the MXQ hot path")

@@ -199,3 +199,58 @@ def test_wide_dynamic_range_rows(cuda, dtype):
     assert np.array_equal(codes.cpu().numpy(), q.astype(np.uint8))
     assert bits_equal(to_np(out), want)
     assert bits_equal(to_np(ops.fakequant_fwd(x.to(cuda))), want)        # no-codes kernel variant
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_multi_tensor_launch_and_pooled_mask(cuda, dtype):
+    """One launch over several weights == one launch each; an importance mask (allocate_group_bits: only the
+    pooled group moves) on the row-resident kernel == the mask-driven ring kernel == the oracle."""
+    from mxq_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    xs = [(torch.randn(r, 1024, generator=g) * 0.02).to(TD[dtype]).to(cuda) for r in (300, 160, 16, 520, 1, 200, 64, 33, 700)]
+    outs = ops.fakequant_fwd_multi(xs)                       # 9 tensors: two launches of <= 8
+    for x, o in zip(xs, outs):
+        assert torch.equal(o, ops.fakequant_fwd(x)) or bits_equal(to_np(o), to_np(ops.fakequant_fwd(x)))
+        want = O.fakequant_fwd(x.float().cpu().numpy(), dtype, 2)
+        assert bits_equal(to_np(o), want)
+    # importance mask
+    W = xs[0]
+    stat = torch.rand(1024, device=cuda) + 0.1
+    stat[16 * 5:16 * 6] *= 300
+    gb = ops.allocate_group_bits(W.half(), stat)
+    assert int((gb[4:8] & 0x80).nonzero()[0]) == 1           # group 5 = slot 1 of block 1 became the pooled one
+    ring = ops.fakequant_fwd(W, group_bits=gb)
+    row = ops.fakequant_fwd(W, group_bits=gb, uniform_low=True)
+    assert bits_equal(to_np(row), to_np(ring))
+    want = O.fakequant_fwd(W.float().cpu().numpy(), dtype, 2, group=16, group_bits=gb.cpu().numpy())
+    assert bits_equal(to_np(row), want)
+
+
+def test_grouped_quantize_linears_match_ungrouped(cuda):
+    """FakeQuantGroup (q/k/v/o in one launch per forward) gives the same outputs and gradients as four
+    independent QuantizeLinear modules, across repeated forwards, no_grad forwards and weight updates."""
+    from mxq_b200.utils_quant import QuantizeLinear, group_quantize_linears
+    torch.manual_seed(4)
+    mods = [QuantizeLinear(256, o, w_bits=2).to(cuda) for o in (256, 64, 64, 256)]
+    refs = [QuantizeLinear(256, o, w_bits=2).to(cuda) for o in (256, 64, 64, 256)]
+    for m, r in zip(mods, refs):
+        r.weight.data.copy_(m.weight.data)
+    groups = group_quantize_linears(mods)
+    assert len(groups) == 1 and len(groups[0].members) == 4
+    for step in range(3):
+        x = torch.randn(8, 256, device=cuda)
+        with torch.no_grad():
+            for m, r in zip(mods[:2], refs[:2]):             # a partial, gradient-free forward in between
+                assert torch.equal(m(x), r(x))
+        la = sum((m(x) ** 2).sum() for m in mods)
+        lb = sum((r(x) ** 2).sum() for r in refs)
+        assert torch.equal(la, lb)
+        la.backward()
+        lb.backward()
+        for m, r in zip(mods, refs):
+            assert torch.equal(m.weight.grad, r.weight.grad)
+            with torch.no_grad():
+                m.weight -= 0.01 * m.weight.grad
+                r.weight -= 0.01 * r.weight.grad
+            m.weight.grad = None
+            r.weight.grad = None
