@@ -563,9 +563,9 @@ def run_components(ctx, pk, with_cpu=True):
     try:
         ms = graph_time(torch, gemv_all, 1, warm=1, reps=5)
         ach = gbytes / ms / 1e6
-        tr, src = ncu_traffic("gemv_mma_kernel", "gemv_4096x4096")
+        tr, src = ncu_traffic("gemv_mxq_kernel", "gemv_4096x4096")
         gemv["per_linear"] = {"ms_per_8_layers": ms, "launches": nl * len(shapes),
-                              "roofline": {"bound": "hbm", "kernel": "gemv_mma_kernel<1> (IC <= 8192) / gemv_mxq_kernel<1> (IC = 11008)",
+                              "roofline": {"bound": "hbm", "kernel": "gemv_mxq_kernel<1> (TMA-ring kernel; the IMMA kernel is opt-in, see imma_kernel below)",
                                            "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                                            "traffic": tr, "traffic_source": (src or "") + " (per 4096x4096 launch: 6,318,080 algorithmic bytes)",
                                            "algorithmic_bytes": gbytes}}
@@ -573,6 +573,16 @@ def run_components(ctx, pk, with_cpu=True):
         ach = gbytes / ms / 1e6
         gemv["grouped"] = {"ms_per_8_layers": ms, "launches": nl * 4, "GBps": ach, "frac_hbm": ach / pk["hbm"],
                            "note": "q/k/v and gate/up share their input: one grouped launch each (mxq_gemv_grouped)"}
+        # the integer-tensor-core kernel (csrc/gemv_mma.cu) on the same chains, for the record
+        os.environ["MXQ_GEMV_IMPL"] = "mma"
+        try:
+            m1 = graph_time(torch, gemv_all, 1, warm=1, reps=5)
+            m2 = graph_time(torch, gemv_grouped_all, 1, warm=1, reps=5)
+            gemv["imma_kernel"] = {"per_linear_GBps": gbytes / m1 / 1e6, "grouped_GBps": gbytes / m2 / 1e6,
+                                   "note": "MXQ_GEMV_IMPL=mma: IMMA m16n8k32 inner products + per-warp cp.async rings; faster on same-shape "
+                                           "chains of 4096-wide linears, slower on this mixed chain (DESIGN.md section 9)"}
+        finally:
+            os.environ.pop("MXQ_GEMV_IMPL", None)
     except Exception as e:
         gemv["error"] = repr(e)[:200]
     # same-box comparators on 4096x4096, batch 1 (outside the product path)

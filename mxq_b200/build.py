@@ -59,6 +59,9 @@ def _stale(target: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
+    common = list(COMMON)
+    if os.environ.get("MXQ_DEBUG") == "1":      # watchdog traps + pinned-host records in the GEMM barriers
+        common.append("-DMXQ_DEBUG")
     os.makedirs(OBJ, exist_ok=True)
     jobs = []
     objs = []
@@ -67,7 +70,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJ, name.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, _deps(src)):
-            cmd = [nvcc, *COMMON, *extra, "-c", src, "-o", obj]
+            cmd = [nvcc, *common, *extra, "-c", src, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)

@@ -554,12 +554,22 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
       : "memory");
   return ok != 0;
 }
+// Hang guard: a barrier that never completes is a programming error; after kHangCycles (~20 s at 2 GHz --
+// far beyond any time-slice, preemption or debugger pause a healthy launch can see; 0.5 s in MXQ_DEBUG
+// builds) the kernel traps instead of wedging the GPU.  (A guard-free `while (!try_wait) {}` was measured
+// too: the tighter polling of the 8 producer warps slows the MMA-issuing thread that shares their
+// schedulers -- 1262 -> 1049 TFLOP/s on 4096^2 -- so the counted loop stays.)
+#ifdef MXQ_DEBUG
+constexpr long long kHangCycles = 1000000000LL;
+#else
+constexpr long long kHangCycles = 40000000000LL;
+#endif
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait_cluster(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 4000000000LL) __trap();
+    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > kHangCycles) __trap();
   }
 }
 // debugging: waits that leave a record {site, kb, block, rank} in pinned host memory before trapping
@@ -573,12 +583,13 @@ __device__ __noinline__ void wd_record(unsigned long long* h, int site, int kb) 
     __threadfence_system();
   }
 }
+// The record in pinned host memory (`h`, MXQ_GEMM_DBG_PTR) exists in MXQ_DEBUG builds only.
 __device__ __forceinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, unsigned long long* h, int site, int kb,
                                               bool cluster) {
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!(cluster ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity))) {
-    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 1000000000LL) {
+    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > kHangCycles) {
       wd_record(h, site, kb);
       // let the other stuck threads record too before the context dies
       const long long t1 = clock64();
@@ -1142,7 +1153,9 @@ static int launch_pair(const void* x, const Params& p, cudaStream_t st, void* wo
   pp.dbg = 0;
   pp.dbg_host = nullptr;
   if (const char* e = getenv("MXQ_GEMM_DBG")) pp.dbg = atoi(e);
+#ifdef MXQ_DEBUG
   if (const char* e = getenv("MXQ_GEMM_DBG_PTR")) pp.dbg_host = (unsigned long long*)strtoull(e, nullptr, 0);
+#endif
   k<<<grid, THREADS, pair::SMEM_BYTES, st>>>(mx, mw, pp);
   if (pl.split > 1 && force_split == 0) {
     e = cudaGetLastError();
