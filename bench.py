@@ -760,15 +760,28 @@ def run_gemm70b(ctx, args, pk, iters=10):
         r = {"flops": flops, "tile_bytes_per_rank": M * ocl * 2}
         r["gemm_us"] = 1e3 * timed(lambda: ops.gemm(x, p, out=y, workspace=ws, validate=False), True, "gemm")
         modes = list(MODES) if world > 1 else []
+        y_check = {}
         for mode in modes:
             try:
                 lin = mdist.ColumnShardedMXQLinear(p, oc, mode=mode)
-                lin(x)
+                y_check[mode] = lin(x).clone()
                 # NCCL mode stays eager (the collective's own launch path is part of it); the fused modes are
                 # this repo's kernels + the symmetric-memory barrier kernel
                 r[mode + "_us"] = 1e3 * timed(lambda: lin(x), mode != "nccl", mode)
             except Exception as e:
                 r[mode + "_error"] = repr(e)[:200]
+        # correctness of the exchange on THIS run's data: every mode's gathered [M, N] result on every rank against
+        # the NCCL all-gather of the plain GEMM (fused modes are bit-identical to it, phased modes add K slices in fp32)
+        if "nccl" in y_check:
+            ref = y_check["nccl"].float()
+            scale = float(ref.abs().max())
+            worst = {}
+            for mode, yv in y_check.items():
+                if mode != "nccl":
+                    worst[mode] = ctx.max_over_ranks(float((yv.float() - ref).abs().max()) / max(scale, 1e-30))
+            r["max_rel_diff_vs_nccl"] = worst
+            r["verified"] = bool(all(v <= 1e-3 for v in worst.values()))
+        del y_check
         for mode in modes:
             if mode + "_us" in r:
                 tot_ms[mode] += r[mode + "_us"] * 1e-3
@@ -791,7 +804,7 @@ def run_gemm70b(ctx, args, pk, iters=10):
            "modes": "nccl = GEMM + NCCL all-gather; p2p / mc = exchange stores fused into the GEMM epilogue (peer stores / NVSwitch "
                     "multicast); p2p2 / mc2 = phased: groups of tiles computed as K slices, each group's reduce + exchange pass on a "
                     "side stream under the next group's tensor work (mxq_gemm_partials / mxq_gemm_reduce_store)",
-           "per_shape": out,
+           "per_shape": out, "verified": (all(r.get("verified", False) for r in out.values()) if world > 1 else None),
            "nvlink_bytes_per_rank": {"egress_p2p": tile_bytes * (world - 1), "egress_mc": tile_bytes if world > 1 else 0,
                                      "ingress": tile_bytes * (world - 1)},
            "roofline": {"bound": "tensor", "achieved": tot_flops / tot_ms["gemm"] / 1e9 / world, "peak": pk["tf_burst"], "unit": "TFLOP/s",
@@ -864,6 +877,12 @@ def run_qat(ctx, args, pk, steps=3, layers=LAYERS):
                             "backward pass.  allreduce_alone_ms = the same bytes in the same buckets with nothing to hide under; the exposed "
                             "part of it is ms_per_step at N GPUs minus ms_per_step at 1 GPU (both in the driver's SCALE record)"}
         del flat, chunks
+        # data-parallel correctness on this run: after the optimizer steps every rank must hold the same weights
+        chk = torch.stack([p.detach().float().sum() for p in list(student.parameters())[:16]]).double()
+        lo, hi = chk.clone(), chk.clone()
+        ctx.dist.all_reduce(lo, op=ctx.dist.ReduceOp.MIN)
+        ctx.dist.all_reduce(hi, op=ctx.dist.ReduceOp.MAX)
+        res_comm["replicas_in_sync"] = bool(torch.equal(lo, hi))
     # the fake-quant share: all quantized weights, 2 forwards (checkpoint recompute) + 1 STE backward
     ws = [m.weight.detach() for m in student.modules() if isinstance(m, qat.QuantizeLinear)]
     gs = {w.shape: torch.randn_like(w) for w in ws}
