@@ -202,6 +202,40 @@ MXQ_API int mxq_gemv_ex(const void* x, mxq_packed_t w, void* y, int64_t B, int64
 MXQ_API int mxq_gemv_grouped(const void* x, const mxq_packed_t* w, void* const* y, int n, int64_t B,
                              int64_t IC, int64_t OC, unsigned flags, void* stream);
 
+/* Decode-GEMV CHAIN (extension): a whole sequence of batch-1 gemv_mxq_forward_cuda calls
+ * (gemv_mxq_cuda.cu:225-273 launches one kernel per linear) as ONE persistent launch.  The packed
+ * weights of all jobs stream through shared memory back to back -- a linear boundary costs no launch,
+ * no fill and no drain -- which is what lets a 6 MB GEMV approach the HBM rate.
+ *   job j:  y_j[OC_j] = dequant(w_j) @ x_j[IC_j]      (fp16 in / out, fp32 accumulate, batch 1)
+ *   dep = -1: x_j is complete when the launch starts.  dep = i < j: x_j is (or depends on) y_i -- the
+ *   kernel orders the read of x_j after every store of y_i.  Jobs are otherwise UNORDERED: a job must
+ *   not write a buffer that an unordered job reads or writes.
+ * Requirements: IC % 256 == 0, IC <= 32768, OC % 32 == 0, n <= MXQ_GEMV_CHAIN_MAX_JOBS (split longer
+ * chains; stream order covers dependencies between launches); MXQ_E_UNSUPPORTED otherwise -- callers fall
+ * back to mxq_gemv per linear.
+ *   mxq_gemv_chain_plan   validates the HOST job array and writes a plan of mxq_gemv_chain_plan_bytes()
+ *                         bytes to HOST memory (64-byte aligned): the job table, which is passed to the
+ *                         kernel by value, and four TMA tensor maps per job.  The caller keeps the host
+ *                         plan and a DEVICE copy of it (64-byte aligned; the kernel reads the tensor maps
+ *                         from there).  Needs a current CUDA context (cuTensorMapEncodeTiled).
+ *   mxq_gemv_chain_run    launches the chain.  sync_ws: device int32[MXQ_GEMV_CHAIN_SYNC_WORDS], zeroed ONCE
+ *                         by the caller; the kernel re-arms it at exit (graph replays need no memset).
+ *                         Chains with dependencies are launched cooperatively (all CTAs co-resident). */
+#define MXQ_GEMV_CHAIN_MAX_JOBS 64
+#define MXQ_GEMV_CHAIN_SYNC_WORDS (MXQ_GEMV_CHAIN_MAX_JOBS + 1)
+typedef struct {
+  const void* x;      /* fp16 [IC] */
+  void* y;            /* fp16 [OC] */
+  mxq_packed_t w;
+  int64_t IC, OC;
+  int32_t dep;        /* -1, or the index of an earlier job whose y this job's x depends on */
+  int32_t reserved;
+} mxq_gemv_job_t;
+MXQ_API size_t mxq_gemv_chain_plan_bytes(void);
+MXQ_API int mxq_gemv_chain_plan(const mxq_gemv_job_t* jobs, int n, void* plan_host);
+MXQ_API int mxq_gemv_chain_run(const void* plan_host, const void* plan_dev, int32_t* sync_ws, unsigned flags,
+                               void* stream);
+
 /* ---- (f-3) importance-driven allocation folded into the packed path ----------------------------------
  * The packed layout is positional (the last 16 of every 64 columns are the 4-bit ones,
  * utils_quant.py:349-353, mxqgpt.py:404-419).  A data-driven choice of the 4-bit group (mxq_allocate_bits,

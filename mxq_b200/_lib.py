@@ -25,7 +25,7 @@ SYMBOLS = [
     "mxq_colsumsq_workspace_bytes", "mxq_colsumsq", "mxq_colsumsq_ex", "mxq_wanda_metric",
     "mxq_allocate_bits_workspace_bytes", "mxq_allocate_bits",
     "mxq_ptq_workspace_bytes", "mxq_ptq_quant", "mxq_rowquant",
-    "mxq_pack_workspace_bytes", "mxq_pack", "mxq_ptq_quant_pack", "mxq_unpack", "mxq_gemv", "mxq_gemv_ex", "mxq_gemv_grouped", "mxq_gemv_grouped_perm", "mxq_gather_groups", "mxq_awq_gemv", "mxq_awq_gemm_workspace_bytes", "mxq_awq_gemm",
+    "mxq_pack_workspace_bytes", "mxq_pack", "mxq_ptq_quant_pack", "mxq_unpack", "mxq_gemv", "mxq_gemv_ex", "mxq_gemv_grouped", "mxq_gemv_grouped_perm", "mxq_gemv_chain_plan_bytes", "mxq_gemv_chain_plan", "mxq_gemv_chain_run", "mxq_gather_groups", "mxq_awq_gemv", "mxq_awq_gemm_workspace_bytes", "mxq_awq_gemm",
     "mxq_gemm_workspace_bytes", "mxq_gemm", "mxq_gemm_plan", "mxq_gemm_scatter", "mxq_gemm_multicast", "mxq_gemm_dense",
     "mxq_gemm_partials_workspace_bytes", "mxq_gemm_partials", "mxq_gemm_reduce_store",
 ]
@@ -37,6 +37,15 @@ class PackedC(C.Structure):
                 ("zeros_and_scales", C.c_void_p), ("zeros_2nd", C.c_void_p),
                 ("scales_2nd", C.c_void_p), ("scales_4b", C.c_void_p), ("zeros_4b", C.c_void_p)]
 
+
+class GemvJobC(C.Structure):
+    """mxq_gemv_job_t"""
+    _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("w", PackedC), ("IC", C.c_int64), ("OC", C.c_int64),
+                ("dep", C.c_int32), ("reserved", C.c_int32)]
+
+
+GEMV_CHAIN_MAX_JOBS = 64
+GEMV_CHAIN_SYNC_WORDS = GEMV_CHAIN_MAX_JOBS + 1
 
 _lib = None
 
@@ -81,6 +90,10 @@ def lib() -> C.CDLL:
     L.mxq_gemv_ex.argtypes = [vp, PackedC, vp, i64, i64, i64, C.c_uint, vp]
     L.mxq_gemv_grouped.argtypes = [vp, C.POINTER(PackedC), C.POINTER(vp), i32, i64, i64, i64, C.c_uint, vp]
     L.mxq_gemv_grouped_perm.argtypes = [vp, C.POINTER(PackedC), C.POINTER(vp), i32, i64, i64, i64, vp, C.c_uint, vp]
+    L.mxq_gemv_chain_plan_bytes.restype = sz
+    L.mxq_gemv_chain_plan_bytes.argtypes = []
+    L.mxq_gemv_chain_plan.argtypes = [C.POINTER(GemvJobC), i32, vp]
+    L.mxq_gemv_chain_run.argtypes = [vp, vp, vp, C.c_uint, vp]
     L.mxq_gather_groups.argtypes = [vp, vp, vp, i64, i64, vp]
     L.mxq_awq_gemv.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i32, vp]
     L.mxq_awq_gemm_workspace_bytes.restype = sz

@@ -28,6 +28,7 @@ SOURCES = {
     "pack.cu": ["-fmad=false"],
     "gemv.cu": [],
     "gemv_mma.cu": [],
+    "gemv_chain.cu": [],
     "gemm_tcgen05.cu": [],
     "awq_gemm.cu": ["-fmad=false"],
 }

@@ -1,0 +1,785 @@
+// Persistent decode-GEMV chain for the packed mixed 2/4-bit layout (sm_100a).
+//
+// Replaces a SEQUENCE of gemv_mxq_forward_cuda calls
+// (mxq_quant/cuda_kernel/csrc/quantization/gemv_mxq_cuda.cu:39-273, one launch per linear) by ONE
+// launch that walks a job list (x_j, W_j, y_j).  Measured on B200: a 6.3 MB
+// 4096 x 4096 GEMV is 0.96 us of HBM time, but every dependent launch costs 2.7 us of skeleton
+// (griddepcontrol.wait return, activation image, fill, epilogue) even with no copies and no arithmetic,
+// so per-linear launches cannot exceed ~0.45 of the HBM rate.  Here the weight stream never stops at a
+// linear boundary:
+//
+//   * one CTA per SM, 16 warps: 8 compute warps, 2 producers, 1 reducer, 5 activation-image builders;
+//   * the producers stream the CTA's rows of ALL jobs back to back through a ring of shared-memory
+//     stages.  One stage = one 16-row tile x one K chunk of <= 4096 columns of every packed tensor
+//     (25 KB) and costs 7-10 TMA operations: weight / weight_last / zeros_and_scales / zeros_2nd arrive
+//     as 2-D tensor-map boxes (cp.async.bulk.tensor; rows beyond the tensor and columns beyond the row
+//     are zero-filled, so every box has the same byte count), scales_2nd / scales_4b / zeros_4b -- whose
+//     pieces are only 8-byte aligned in the reference layout -- as 1-D bulk copies of the enclosing
+//     16-byte aligned range (the consumer adds the skew).  An earlier version issued one bulk copy per
+//     row (52 per stage): a UBLKCP costs its warp 60-100 cycles, the stage took 2.9 us;
+//   * compute warp w = (set, q): the two sets alternate 16-row tiles, so the two compute warps of a
+//     scheduler are out of phase (one reduces / waits while the other multiplies); warp q of a set owns
+//     the four 256-column units 4q .. 4q+3 of every stage of its tiles.  Thread (g, t) of the warp
+//     multiplies two rows of one second-order row group with the four consecutive 64-column blocks of
+//     unit 4q + t: all its metadata for the visit comes from ONE 16-byte load per tensor and row.
+//     Inner products on mma.sync.m16n8k32 (IMMA.16832.U8.S8) as in csrc/gemv_mma.cu (the quad's thread
+//     t supplies its own block along k, the B columns separate the four blocks again, block-floating
+//     int16 activations split in signed high / low bytes), but the 2-bit codes are NOT shifted down:
+//     code c of a byte is masked in place at bits 7:6 after a multiply by 4^(3-c) (IMAD on the FMA pipe
+//     instead of SHF on the half-rate ALU pipe), i.e. all codes enter the mma as 64 * q, and the factor
+//     2^-6 (2^-4 for the 4-bit nibbles) is folded into the activation image's group scales;
+//   * the 4 K-partials of a tile go through a shared-memory exchange (4 tiles deep) to the reducer warp,
+//     which adds them in a fixed order (deterministic), stores y and, if a later job depends on this one,
+//     publishes the CTA's share with a release increment of the job's counter;
+//   * the builders convert x_j into the block-floating image of job j+1 while job j computes.  A job
+//     may name an earlier job `dep` whose y it reads as x (a real dependent chain): the builders then
+//     wait for the counter of `dep` (acquire) -- the weight stream of the waiting job is already in
+//     shared memory by then.  Launched cooperatively when a chain has dependencies (all CTAs co-resident).
+//
+// Shapes: IC % 256 == 0, OC % 32 == 0, batch 1.  Other calls stay on gemv.cu / gemv_mma.cu.
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace mxq {
+namespace g3 {
+
+constexpr int kCW = 8;                        // compute warps: 2 sets x 4
+constexpr int kSetW = 4;
+constexpr int kProdA = kCW, kProdB = kCW + 1, kReducer = kCW + 2, kBuilder0 = kCW + 3;
+constexpr int kBW = 5;                        // builder warps
+constexpr int kWarps = kCW + 3 + kBW;         // 16
+constexpr int kThreads = kWarps * 32;
+constexpr int kBuilderThreads = kBW * 32;
+constexpr int kMaxJobs = MXQ_GEMV_CHAIN_MAX_JOBS;
+constexpr uint32_t kMagic = 0x4D584334u;      // "MXC4"
+
+// one stage = one 16-row tile x one K chunk of 64 blocks (16 units), every tensor dense
+constexpr int kOffW = 0;                      // [16 rows][pw B]     weight words (pw = min(IC/4, 1024))
+constexpr int kOffWL = 16384;                 // [16 rows][pwl B]    weight_last (pwl = min(IC/16, 256))
+constexpr int kOffZS = 20480;                 // [16 rows][128 B]    zeros_and_scales of the metadata chunk
+constexpr int kOffZ2 = 22528;                 // [4 row groups][128 B] zeros_2nd
+constexpr int kOffS2 = 23040;                 // [4 row groups][pitch] scales_2nd (+ skew)
+constexpr int kPS2 = 416;                     // pitch of the per-row-group copies: 64 blocks x 6 B + 8 skew + pad
+constexpr int kOffS4 = kOffS2 + 4 * kPS2;     // 24704: 48 B around the tile's 16 fp16 scales_4b
+constexpr int kOffZ4 = kOffS4 + 48;           // 24752: 32 B around the tile's zeros_4b words
+constexpr int kStageBytes = 24832;
+static_assert(kOffZ4 + 32 <= kStageBytes && kStageBytes % 128 == 0, "stage layout");
+constexpr uint32_t kBytesBox = 2048 + 512;    // producer B: zeros_and_scales + zeros_2nd boxes
+
+constexpr int kRedDepth = 4;                  // tiles in flight between the compute warps and the reducer
+constexpr int kRedBytes = kRedDepth * kSetW * 16 * 4;
+constexpr int kMaxStages = 8;
+constexpr size_t kSmemMax = 227 * 1024 - 1024;
+
+struct JobD {                                 // 128 bytes
+  const unsigned char* S2;
+  const unsigned char* S4;
+  const unsigned char* Z4;
+  const __half* x;
+  __half* y;
+  int nblk, nch, nqb, ngrp;
+  int q, gxl, rot, dep;
+  int share, dep_target, publish, s2pitch;    // s2pitch: 0 = one copy per row group (pitch kPS2, skewed)
+  int oc, ximg_blocks, pw, pwl;               // pw / pwl: row pitch of the weight / weight_last boxes
+  int pad[6];
+};
+static_assert(sizeof(JobD) == 128, "JobD");
+
+struct PlanH {                                // 128 bytes
+  uint32_t magic;
+  int n, nstages, ximg_max;
+  int ncta, coop, smem, dbg;                  // dbg: profiling only (MXQ_CHAIN_DBG): 1 no arithmetic, 2 no copies, 4 no image, 8 trace
+  int pad[24];
+};
+static_assert(sizeof(PlanH) == 128, "PlanH");
+
+struct ChainParams {                          // passed by value (__grid_constant__): every job field is a
+  PlanH H;                                    // constant-bank operand
+  JobD jobs[kMaxJobs];
+};
+static_assert(sizeof(ChainParams) <= 32000, "kernel parameter space");
+
+// The plan blob: ChainParams, then 4 tensor maps per job (weight, weight_last, zeros_and_scales,
+// zeros_2nd).  The caller keeps a device copy of the blob for the maps (TMA descriptors are read from
+// global memory).
+constexpr size_t kMapsOffset = (sizeof(ChainParams) + 127) & ~size_t(127);
+constexpr size_t kPlanBytes = kMapsOffset + (size_t)kMaxJobs * 4 * sizeof(CUtensorMap);
+
+struct Bars {
+  uint64_t full[kMaxStages], empty[kMaxStages];
+  uint64_t imgfull[2], imgempty[2], redfull[kRedDepth], redempty[kRedDepth];
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// release at gpu scope: the y stores of the whole warp (ordered before by __syncwarp) become visible first
+__device__ __forceinline__ void red_release_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_cg16(const void* p) {   // L2 only: x may have been written by this launch
+  uint4 v;
+  asm volatile("ld.global.cg.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tma_box(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void imma(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                     uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ int imad(int a, int b, int c) {
+  int d;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t mask, uint32_t orv) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(orv));
+  return d;
+}
+// lo(a) * h + c with fp16 operands and an fp32 accumulator (the product is exact)
+__device__ __forceinline__ float fhfma(uint32_t a2, unsigned short h, float acc) {
+  unsigned short a;
+  asm("{.reg .b16 t; mov.b32 {%0,t}, %1;}" : "=h"(a) : "r"(a2));
+  asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc) : "h"(a), "h"(h));
+  return acc;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// Profiling only (MXQ_CHAIN_DBG & 8): clock64 stamps of CTA 1 -- [role][event index][stamp]; roles: compute
+// warp 0, producer A, reducer, builder warp 0
+constexpr int kTraceEvents = 96;
+__device__ long long g_ctrace[4 * kTraceEvents * 4];
+#define CTRACE(role, idx, k)                                                                       \
+  do {                                                                                             \
+    if (tr && (idx) < kTraceEvents) g_ctrace[((role) * kTraceEvents + (idx)) * 4 + (k)] = clock64(); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Activation image of one job (one batch row):
+//   [16 B zeros]
+//   [nb][4][32 B]   per 16-column group: 16 B of signed high bytes, 16 B of signed low bytes;
+//                   2-bit groups: register c, byte j = element 4j + c; pooled group: register
+//                   (e>>3)*2 + (e&1), byte (e&7)>>1 = element e
+//   tabI int4[nb]     -(sum_j X_j) * {64, 16, 4, 16}: the zero-point term for z1 masked IN PLACE
+//                     (zs & (3 << 2k) = z1 * 4^k) and for the nibble zero z4 (codes enter as 16 * q)
+//   tabF float4[nb]   2^(E-14) * {2^-6, 2^-6, 2^-6, 2^-4}
+// nb = nch * 64 blocks (zeros beyond the row).
+// X_j = rint(x_j * 2^(14-E)), E = exponent of 1.0078 * max|x| of the group, X = 256 * hi + lo with both
+// bytes signed.  Same quantities as csrc/gemv_mma.cu (error bound measured in tests/test_gpu_packed.py).
+// ---------------------------------------------------------------------------------------------
+template <int k>
+__device__ __forceinline__ void stage_group(const uint4 v0, const uint4 v1, unsigned char* dst, int* tI, float* tF) {
+  const uint32_t xw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+  uint32_t m2 = xw[0] & 0x7FFF7FFFu;
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m2 = P16<__half>::vmax(m2, xw[i] & 0x7FFF7FFFu);
+  float gmax = fmaxf(P16<__half>::lo(m2), P16<__half>::hi(m2));
+  gmax = fminf(gmax, 65504.f) * 1.0078125f;
+  const uint32_t eb = __float_as_uint(gmax) >> 23;          // biased exponent (>= 103 when gmax > 0)
+  const float up = gmax > 0.f ? __uint_as_float((268u - eb) << 23) : 0.f;
+  const float xsc = gmax > 0.f ? __uint_as_float((eb - (k < 3 ? 20u : 18u)) << 23) : 0.f;
+  // bits(fma(x, up, 1.5*2^23 + 128)) = 0x4B400080 + X: byte 0 ^ 0x80 = low byte, byte 1 = (X+128)>>8
+  uint32_t F[16];
+  uint32_t xs = 0;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const float f = __half2float(__ushort_as_half((unsigned short)(xw[e >> 1] >> (16 * (e & 1)))));
+    F[e] = __float_as_uint(__fmaf_rn(f, up, 12583040.0f));
+    xs += F[e];
+  }
+  xs -= 16u * 0x4B400080u;                                   // sum_j X_j (mod 2^32, exact)
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    int e0, e1, e2, e3;
+    if (k < 3) { e0 = c; e1 = 4 + c; e2 = 8 + c; e3 = 12 + c; }
+    else { const int b = (c >> 1) * 8 + (c & 1); e0 = b; e1 = b + 2; e2 = b + 4; e3 = b + 6; }
+    const uint32_t P = prmt_b32(F[e0], F[e1], 0x5140u);      // {lo0, lo1, hi0, hi1}
+    const uint32_t Q = prmt_b32(F[e2], F[e3], 0x5140u);
+    lo[c] = prmt_b32(P, Q, 0x5410u) ^ 0x80808080u;
+    hi[c] = prmt_b32(P, Q, 0x7632u);
+  }
+  reinterpret_cast<uint4*>(dst)[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  reinterpret_cast<uint4*>(dst)[1] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  constexpr int sh = k == 0 ? 6 : (k == 2 ? 2 : 4);
+  *tI = (int)((0u - xs) << sh);
+  *tF = xsc;
+}
+
+// which rows of job J this CTA owns
+struct Share {
+  bool active;
+  int grp_base, qc, T;
+};
+__device__ __forceinline__ Share cta_share(const JobD& J, int cta, int ncta) {
+  Share s;
+  int slice = cta + J.rot;
+  if (slice >= ncta) slice -= ncta;
+  s.active = slice < J.gxl;
+  s.grp_base = slice * J.q;
+  s.qc = min(J.q, J.ngrp - s.grp_base);
+  s.T = (s.qc + 3) >> 2;
+  return s;
+}
+
+// one 64-column block of this thread's two rows: three 2-bit groups + the pooled 4-bit group
+//   wa / wb   the block's 4 weight words of row a / row b,  wla / wlb weight_last
+//   zsa / zsb the block's 16-bit zeros_and_scales field of row a / b (junk above bit 15 allowed),
+//   z2        the block's zeros_2nd byte (junk above bit 7 allowed), s2[3] its second-order scales
+__device__ __forceinline__ void block_mac(const uint4 wa, const uint4 wb, const uint32_t wla, const uint32_t wlb,
+                                          const uint32_t zsa, const uint32_t zsb, const uint32_t z2,
+                                          const unsigned short (&s2)[3], const unsigned char* __restrict__ xb,
+                                          const uint32_t xstep, const int4 tI, const float4 tF, const float s4a,
+                                          const float s4b, const int z4a, const int z4b, const int c4, const int c16,
+                                          const int c64, const int c256, float& acc0, float& acc1) {
+  constexpr uint32_t M2 = 0xC0C0C0C0u, M4 = 0xF0F0F0F0u;
+  const uint32_t zsha = zsa >> 4, zshb = zsb >> 4;
+  const uint32_t z2s8 = (uint32_t)imad((int)z2, c256, 0), z2s4 = (uint32_t)imad((int)z2, c16, 0);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const uint4 X = *reinterpret_cast<const uint4*>(xb + k * xstep);
+    const uint32_t wka = k == 0 ? wa.x : (k == 1 ? wa.y : wa.z);
+    const uint32_t wkb = k == 0 ? wb.x : (k == 1 ? wb.y : wb.z);
+    int d[4] = {0, 0, 0, 0};
+    // codes c = 3, 2 (elements 4j + c of byte j), then c = 1, 0: all as 64 * q
+    imma(d, wka & M2, wkb & M2, (uint32_t)imad((int)wka, c4, 0) & M2, (uint32_t)imad((int)wkb, c4, 0) & M2, X.w, X.z);
+    imma(d, (uint32_t)imad((int)wka, c16, 0) & M2, (uint32_t)imad((int)wkb, c16, 0) & M2,
+         (uint32_t)imad((int)wka, c64, 0) & M2, (uint32_t)imad((int)wkb, c64, 0) & M2, X.y, X.x);
+    // S = s2 * (c - z2) = (cb + c) * s2 - (cb + z2) * s2, cb = 4 (k = 0, 2) or 16 (k = 1); both products are
+    // exact in fp32 (gemv_mxq_cuda.cu:136)
+    const uint32_t hz = k == 0 ? lop3_and_or(z2s8, 0x0300u, 0xC400u)
+                      : k == 1 ? lop3_and_or(z2s4, 0x00C0u, 0xCC00u)
+                               : lop3_and_or(z2s4, 0x0300u, 0xC400u);
+    const float S0 = fhfma(hz, s2[k], 0.f);                              // -(cb + z2) * s2
+    const int nxs = k == 0 ? tI.x : (k == 1 ? tI.y : tI.z);
+    const float xsc = k == 0 ? tF.x : (k == 1 ? tF.y : tF.z);
+    {
+      const uint32_t hc = k == 0 ? lop3_and_or(zsa, 0x0300u, 0x4400u)
+                        : k == 1 ? lop3_and_or(zsha, 0x00C0u, 0x4C00u)
+                                 : lop3_and_or(zsha, 0x0300u, 0x4400u);
+      const float Ssc = fhfma(hc, s2[k], S0) * xsc;
+      const int z1m = (int)(zsa & (3u << (2 * k)));                      // z1 * 4^k
+      const int dd = imad(z1m, nxs, imad(d[0], 256, d[1]));
+      acc0 = fmaf(Ssc, (float)dd, acc0);                                 // :153
+    }
+    {
+      const uint32_t hc = k == 0 ? lop3_and_or(zsb, 0x0300u, 0x4400u)
+                        : k == 1 ? lop3_and_or(zshb, 0x00C0u, 0x4C00u)
+                                 : lop3_and_or(zshb, 0x0300u, 0x4400u);
+      const float Ssc = fhfma(hc, s2[k], S0) * xsc;
+      const int z1m = (int)(zsb & (3u << (2 * k)));
+      const int dd = imad(z1m, nxs, imad(d[2], 256, d[3]));
+      acc1 = fmaf(Ssc, (float)dd, acc1);
+    }
+  }
+  {
+    const uint4 X = *reinterpret_cast<const uint4*>(xb + 3 * xstep);
+    int d[4] = {0, 0, 0, 0};
+    // nibbles as 16 * q: low nibbles (elements 0,2,4,6 / 8,..) shifted up, high nibbles in place
+    imma(d, (uint32_t)imad((int)wa.w, c16, 0) & M4, (uint32_t)imad((int)wb.w, c16, 0) & M4, wa.w & M4, wb.w & M4, X.x, X.y);
+    imma(d, (uint32_t)imad((int)wla, c16, 0) & M4, (uint32_t)imad((int)wlb, c16, 0) & M4, wla & M4, wlb & M4, X.z, X.w);
+    const int dda = imad(z4a, tI.w, imad(d[0], 256, d[1]));
+    const int ddb = imad(z4b, tI.w, imad(d[2], 256, d[3]));
+    acc0 = fmaf(s4a * tF.w, (float)dda, acc0);                           // :179,192
+    acc1 = fmaf(s4b * tF.w, (float)ddb, acc1);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __restrict__ maps, int* __restrict__ sync_ws,
+                  const int c4, const int c16, const int c64, const int c256) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int n = P.H.n, S = P.H.nstages, ncta = P.H.ncta, ximg_max = P.H.ximg_max, dbg = P.H.dbg;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cta = blockIdx.x;
+
+  unsigned char* stages = smem;
+  unsigned char* img = stages + (size_t)S * kStageBytes;
+  float* red = reinterpret_cast<float*>(img + 2 * (size_t)ximg_max);
+  Bars& bars = *reinterpret_cast<Bars*>(reinterpret_cast<unsigned char*>(red) + kRedBytes);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&bars.full[s], 2); mbar_init(&bars.empty[s], kSetW); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars.imgfull[b], kBW);
+      mbar_init(&bars.imgempty[b], kCW);
+    }
+    for (int b = 0; b < kRedDepth; ++b) {
+      mbar_init(&bars.redfull[b], kSetW);
+      mbar_init(&bars.redempty[b], 1);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp < kCW) {
+    // =========================================== compute ===========================================
+    const int g = lane >> 2, t = lane & 3;
+    const int set = warp >> 2, qw = warp & 3;
+    const int U = qw * 4 + t;                                 // this thread-column's unit inside a stage
+    const int rgl = g >> 1;                                   // row group of this thread's two rows
+    const int rowa = rgl * 4 + (g & 1), rowb = rowa + 2;      // tile rows (mma rows g and g + 8)
+    const uint32_t half = (uint32_t)(U >> 3);                 // blocks 32.. of a metadata chunk: high half / byte 1
+    const uint32_t oZSa = kOffZS + rowa * 128 + (U & 7) * 16, oZSb = oZSa + 2 * 128;
+    const uint32_t oZ2 = kOffZ2 + rgl * 128 + (U & 7) * 16;
+    const uint32_t zsh = half * 16, z2sh = half * 8;
+    const bool bact = (g >> 1) == t;                          // this lane feeds a non-zero B column
+    const uint32_t xlane = bact ? (uint32_t)(16 + U * 512 + (g & 1) * 16) : 0u;
+    const uint32_t xchunk = bact ? 64u * 128u : 0u, xblk = bact ? 128u : 0u, xstep = bact ? 32u : 0u;
+
+    int slot = 0, sphase = 0;                                 // ring position
+    int tau = 0;                                              // tile sequence number (reduce buffers, set choice)
+    int imgk = -1;                                            // image sequence number
+    const bool tr = (dbg & 8) && cta == 1 && warp == 0 && lane == 0;
+    int ev = 0;
+    for (int j = 0; j < n; ++j) {
+      const JobD& J = P.jobs[j];
+      const Share sh = cta_share(J, cta, ncta);
+      if (!sh.active) continue;
+      if (!J.share) {
+        if (imgk >= 0) {                                      // done with the previous image
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.imgempty[imgk & 1]);
+        }
+        ++imgk;
+        mbar_wait(&bars.imgfull[imgk & 1], (imgk >> 1) & 1);
+      }
+      const unsigned char* ximg = img + (size_t)(imgk & 1) * ximg_max;
+      const int nb = J.ximg_blocks;
+      const unsigned char* tabI = ximg + 16 + nb * 128;
+      const unsigned char* tabF = tabI + nb * 16;
+      const int nch = J.nch, nqb = J.nqb;
+      const int row0_cta = sh.grp_base * 4;
+      const uint32_t s2pitch = J.s2pitch ? (uint32_t)J.s2pitch : (uint32_t)kPS2;
+      const uint32_t s2odd = J.s2pitch ? 0u : (uint32_t)((J.nblk * 6) & 15);
+      const uint32_t oWa = kOffW + rowa * J.pw + U * 64, oWb = oWa + 2 * J.pw;
+      const uint32_t oWLa = kOffWL + rowa * J.pwl + U * 16, oWLb = oWLa + 2 * J.pwl;
+      for (int tile = 0; tile < sh.T; ++tile, ++tau) {
+        if ((tau & 1) != set) {                               // the other set's tile: skip its stages
+          slot += nch;
+          while (slot >= S) { slot -= S; sphase ^= 1; }
+          continue;
+        }
+        float acc0 = 0.f, acc1 = 0.f;
+        float s4a = 0.f, s4b = 0.f;
+        int z4a = 0, z4b = 0;
+        const int rg0 = sh.grp_base + tile * 4;
+        const uint32_t oS2 = kOffS2 + rgl * s2pitch + (((rg0 + rgl) & 1) ? s2odd : 0u) + U * 24;
+        for (int ch = 0; ch < nch; ++ch) {
+          const int nq = min(16, nqb - ch * 16);
+          CTRACE(0, ev, 0);
+          mbar_wait(&bars.full[slot], sphase);
+          CTRACE(0, ev, 1);
+          const unsigned char* s = stages + (size_t)slot * kStageBytes;
+          if (ch == 0) {                                      // 4-bit pool scale / zero of this thread's two rows
+            const int R = row0_cta + tile * 16;
+            const __half* s4p = reinterpret_cast<const __half*>(s + kOffS4 + ((rg0 & 1) ? 8 : 0));
+            s4a = __half2float(s4p[rowa]);
+            s4b = __half2float(s4p[rowb]);
+            const uint32_t* z4w = reinterpret_cast<const uint32_t*>(s + kOffZ4);
+            const int w0 = (R >> 3) & ~3;                     // first word of the 16-byte aligned copy
+            const int Ra = R + rowa, Rb = R + rowb;
+            z4a = (int)((z4w[(Ra >> 3) - w0] >> (4 * (Ra & 7))) & 0xF);
+            z4b = (int)((z4w[(Rb >> 3) - w0] >> (4 * (Rb & 7))) & 0xF);
+          }
+          if (qw * 4 < nq && !(dbg & 1)) {
+            // metadata of the thread-column's four blocks: one 16-byte load per tensor and row
+            const uint4 wl4a = *reinterpret_cast<const uint4*>(s + oWLa);
+            const uint4 wl4b = *reinterpret_cast<const uint4*>(s + oWLb);
+            const uint4 zs4a = *reinterpret_cast<const uint4*>(s + oZSa);
+            const uint4 zs4b = *reinterpret_cast<const uint4*>(s + oZSb);
+            const uint4 z24 = *reinterpret_cast<const uint4*>(s + oZ2);
+            const uint2 sA = *reinterpret_cast<const uint2*>(s + oS2);
+            const uint2 sB = *reinterpret_cast<const uint2*>(s + oS2 + 8);
+            const uint2 sC = *reinterpret_cast<const uint2*>(s + oS2 + 16);
+            const uint32_t s2w[6] = {sA.x, sA.y, sB.x, sB.y, sC.x, sC.y};
+            const unsigned char* xb0 = ximg + xlane + (uint32_t)ch * xchunk;
+            const unsigned char* tI0 = tabI + (ch * 64 + U * 4) * 16;
+            const unsigned char* tF0 = tabF + (ch * 64 + U * 4) * 16;
+            float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 wa = *reinterpret_cast<const uint4*>(s + oWa + i * 16);
+              const uint4 wb = *reinterpret_cast<const uint4*>(s + oWb + i * 16);
+              const uint32_t wla = i == 0 ? wl4a.x : i == 1 ? wl4a.y : i == 2 ? wl4a.z : wl4a.w;
+              const uint32_t wlb = i == 0 ? wl4b.x : i == 1 ? wl4b.y : i == 2 ? wl4b.z : wl4b.w;
+              const uint32_t zsa = (i == 0 ? zs4a.x : i == 1 ? zs4a.y : i == 2 ? zs4a.z : zs4a.w) >> zsh;
+              const uint32_t zsb = (i == 0 ? zs4b.x : i == 1 ? zs4b.y : i == 2 ? zs4b.z : zs4b.w) >> zsh;
+              const uint32_t z2 = (i == 0 ? z24.x : i == 1 ? z24.y : i == 2 ? z24.z : z24.w) >> z2sh;
+              unsigned short s2[3];
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                const int hidx = 3 * i + k;
+                s2[k] = (unsigned short)(s2w[hidx >> 1] >> (16 * (hidx & 1)));
+              }
+              const int4 tI = *reinterpret_cast<const int4*>(tI0 + i * 16);
+              const float4 tF = *reinterpret_cast<const float4*>(tF0 + i * 16);
+              block_mac(wa, wb, wla, wlb, zsa, zsb, z2, s2, xb0 + i * xblk, xstep, tI, tF, s4a, s4b, z4a, z4b, c4, c16,
+                        c64, c256, v0, v1);
+            }
+            if (U < nq) { acc0 += v0; acc1 += v1; }           // units beyond the row: zero codes, but stale scales
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.empty[slot]);
+          CTRACE(0, ev, 2);
+          if (++slot == S) { slot = 0; sphase ^= 1; }
+          if (ch + 1 < nch) { CTRACE(0, ev, 3); ++ev; }
+        }
+        // ---- the warp's K partial of this tile -> reducer ------------------------------------------
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+        const int p = tau % kRedDepth;
+        mbar_wait(&bars.redempty[p], ((tau / kRedDepth) & 1) ^ 1);
+        if (t == 0) {
+          float* rp = red + ((size_t)p * kSetW + qw) * 16;
+          rp[rowa] = acc0;
+          rp[rowb] = acc1;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.redfull[p]);
+        CTRACE(0, ev, 3);
+        ++ev;
+      }
+    }
+  } else if (warp == kProdA || warp == kProdB) {
+    // =========================================== producers =========================================
+    // A: weight + weight_last boxes.  B: zeros_and_scales + zeros_2nd boxes, scales_2nd, scales_4b, zeros_4b.
+    const bool isA = warp == kProdA;
+    int slot = 0, sphase = 0;
+    const bool tr = (dbg & 8) && cta == 1 && lane == 0 && isA;
+    int ev = 0;
+    for (int j = 0; j < n; ++j) {
+      const JobD& J = P.jobs[j];
+      const Share sh = cta_share(J, cta, ncta);
+      if (!sh.active) continue;
+      const int nblk = J.nblk, nch = J.nch, nqb = J.nqb;
+      const CUtensorMap* mp = maps + (size_t)j * 4;
+      const uint32_t bytesA = 16u * (uint32_t)(J.pw + J.pwl);
+      for (int tile = 0; tile < sh.T; ++tile) {
+        const int nrg = min(4, sh.qc - tile * 4);
+        const int rg0 = sh.grp_base + tile * 4;
+        const int row0 = rg0 * 4;
+        for (int ch = 0; ch < nch; ++ch) {
+          const int nq = min(16, nqb - ch * 16);
+          CTRACE(1, ev, 0);
+          mbar_wait(&bars.empty[slot], sphase ^ 1);
+          CTRACE(1, ev, 1);
+          unsigned char* s = stages + (size_t)slot * kStageBytes;
+          uint64_t* fb = &bars.full[slot];
+          if (elect_one()) {
+            if (dbg & 2) {
+              mbar_arrive(fb);
+            } else if (isA) {
+              mbar_arrive_expect_tx(fb, bytesA);
+              tma_box(s + kOffW, mp + 0, ch * 256, row0, fb);
+              tma_box(s + kOffWL, mp + 1, ch * 64, row0, fb);
+            } else {
+              // scales_2nd: row group r's piece starts at (rg0 + r) * nblk * 6 + ch * 384 (8-byte aligned)
+              uint32_t s2bytes;
+              const uint32_t piece = (uint32_t)nq * 24;
+              const uint32_t odd = (uint32_t)((nblk * 6) & 15);      // 0 or 8
+              if (J.s2pitch) {
+                s2bytes = (uint32_t)nrg * (uint32_t)J.s2pitch;
+              } else {
+                s2bytes = 0;
+                for (int r = 0; r < nrg; ++r) s2bytes += (piece + (((rg0 + r) & 1) ? odd : 0u) + 15u) & ~15u;
+              }
+              // scales_4b / zeros_4b: the 16-byte aligned range around the tile's entries, clipped to the tensor
+              const uint32_t s4off = ((uint32_t)rg0 * 8u) & ~15u;
+              const uint32_t s4bytes = min(48u, (uint32_t)J.oc * 2u - s4off);
+              const uint32_t z4off = (uint32_t)((row0 >> 3) & ~3) * 4u;
+              const uint32_t z4bytes = min(32u, (uint32_t)(J.oc >> 3) * 4u - z4off);
+              mbar_arrive_expect_tx(fb, kBytesBox + s2bytes + s4bytes + z4bytes);
+              tma_box(s + kOffZS, mp + 2, ch * 32, row0, fb);
+              tma_box(s + kOffZ2, mp + 3, ch * 32, rg0, fb);
+              if (J.s2pitch) {
+                bulk_g2s(s + kOffS2, J.S2 + (size_t)rg0 * (size_t)J.s2pitch, s2bytes, fb);
+              } else {
+                for (int r = 0; r < nrg; ++r) {
+                  const size_t off = (size_t)(rg0 + r) * ((size_t)nblk * 6) + (size_t)ch * 384;
+                  const uint32_t sk = ((rg0 + r) & 1) ? odd : 0u;
+                  bulk_g2s(s + kOffS2 + r * kPS2, J.S2 + (off - sk), (piece + sk + 15u) & ~15u, fb);
+                }
+              }
+              bulk_g2s(s + kOffS4, J.S4 + s4off, s4bytes, fb);
+              bulk_g2s(s + kOffZ4, J.Z4 + z4off, z4bytes, fb);
+            }
+          }
+          __syncwarp();
+          CTRACE(1, ev, 3);
+          ++ev;
+          if (++slot == S) { slot = 0; sphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == kReducer) {
+    // =========================================== reducer ===========================================
+    int tau = 0;
+    const int r = lane & 15, h = lane >> 4;
+    const bool tr = (dbg & 8) && cta == 1 && lane == 0;
+    for (int j = 0; j < n; ++j) {
+      const JobD& J = P.jobs[j];
+      const Share sh = cta_share(J, cta, ncta);
+      if (!sh.active) continue;
+      for (int tile = 0; tile < sh.T; ++tile) {
+        const int p = tau % kRedDepth;
+        CTRACE(2, tau, 0);
+        mbar_wait(&bars.redfull[p], (tau / kRedDepth) & 1);
+        CTRACE(2, tau, 1);
+        const float* rp = red + ((size_t)p * kSetW + h * 2) * 16 + r;
+        float sum = rp[0] + rp[16];
+        sum += __shfl_xor_sync(0xffffffffu, sum, 16);        // (warp 0 + warp 1) + (warp 2 + warp 3) on both halves
+        if (lane < 16 && tile * 4 + (r >> 2) < sh.qc)
+          J.y[(size_t)sh.grp_base * 4 + (size_t)tile * 16 + r] = __float2half_rn(sum);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.redempty[p]);
+        CTRACE(2, tau, 2);
+        ++tau;
+      }
+      // publish (only if a later job waits for this one): this CTA's rows of job j are in global memory
+      if (J.publish) {
+        __syncwarp();
+        if (lane == 0) red_release_add(sync_ws + j, 1);
+      }
+    }
+  } else {
+    // =========================================== image builders ====================================
+    // a thread converts one 64-column block (4 groups) per round
+    const int bt = (warp - kBuilder0) * 32 + lane;
+    int imgk = -1;
+    const bool tr = (dbg & 8) && cta == 1 && bt == 0;
+    for (int j = 0; j < n; ++j) {
+      const JobD& J = P.jobs[j];
+      const Share sh = cta_share(J, cta, ncta);
+      if (!sh.active || J.share) continue;
+      ++imgk;
+      const int bsel = imgk & 1;
+      CTRACE(3, imgk, 0);
+      mbar_wait(&bars.imgempty[bsel], ((imgk >> 1) & 1) ^ 1);
+      CTRACE(3, imgk, 1);
+      if (J.dep >= 0) {
+        const int* flag = sync_ws + J.dep;
+        const long long t0 = clock64();
+        while (ld_acquire(flag) < J.dep_target) {
+          if (clock64() - t0 > 40000000000LL) __trap();
+        }
+      }
+      unsigned char* xi = img + (size_t)bsel * ximg_max;
+      const int nb = J.ximg_blocks, nblk = J.nblk;
+      int* tI = reinterpret_cast<int*>(xi + 16 + (size_t)nb * 128);
+      float* tF = reinterpret_cast<float*>(xi + 16 + (size_t)nb * 144);
+      if (!(dbg & 4)) {
+        for (int b = bt; b < nb; b += kBuilderThreads) {
+          unsigned char* dst = xi + 16 + (size_t)b * 128;
+          if (b < nblk) {
+            const __half* xa = J.x + (size_t)b * 64;
+            const uint4 a0 = ld_cg16(xa), a1 = ld_cg16(xa + 8), a2 = ld_cg16(xa + 16), a3 = ld_cg16(xa + 24);
+            const uint4 a4 = ld_cg16(xa + 32), a5 = ld_cg16(xa + 40), a6 = ld_cg16(xa + 48), a7 = ld_cg16(xa + 56);
+            stage_group<0>(a0, a1, dst, tI + b * 4 + 0, tF + b * 4 + 0);
+            stage_group<1>(a2, a3, dst + 32, tI + b * 4 + 1, tF + b * 4 + 1);
+            stage_group<2>(a4, a5, dst + 64, tI + b * 4 + 2, tF + b * 4 + 2);
+            stage_group<3>(a6, a7, dst + 96, tI + b * 4 + 3, tF + b * 4 + 3);
+          } else {                                            // blocks beyond the row (last chunk): zeros
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) reinterpret_cast<uint4*>(dst)[i] = z;
+            reinterpret_cast<uint4*>(tI)[b] = z;
+            reinterpret_cast<uint4*>(tF)[b] = z;
+          }
+        }
+      }
+      if (bt < 4) reinterpret_cast<uint32_t*>(xi)[bt] = 0u;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.imgfull[bsel]);
+      CTRACE(3, imgk, 2);
+    }
+  }
+
+  // ---- the last CTA out re-arms the counters (graph replays pass the same arguments) --------------
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int ticket = atomicAdd(sync_ws + kMaxJobs, 1);
+    if (ticket == (int)gridDim.x - 1) {
+      for (int j = 0; j < n; ++j) sync_ws[j] = 0;
+      sync_ws[kMaxJobs] = 0;
+      __threadfence();
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  return reinterpret_cast<EncodeTiledFn>(fn);
+}
+
+// int32 [rows, words] row-major, dense box [box_rows x box_words], zero fill out of bounds
+static int make_map(EncodeTiledFn enc, CUtensorMap* map, const void* ptr, int64_t rows, int64_t words, int box_rows,
+                    int box_words) {
+  cuuint64_t dims[2] = {(cuuint64_t)words, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)words * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_words, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MXQ_OK : MXQ_E_UNSUPPORTED;
+}
+
+}  // namespace g3
+}  // namespace mxq
+
+using namespace mxq;
+
+extern "C" size_t mxq_gemv_chain_plan_bytes(void) { return g3::kPlanBytes; }
+
+extern "C" int mxq_gemv_chain_plan(const mxq_gemv_job_t* jobs, int n, void* plan_host) {
+  if (!jobs || !plan_host) return MXQ_E_NULL;
+  if (reinterpret_cast<uintptr_t>(plan_host) & 63) return MXQ_E_ALIGN;
+  if (n <= 0 || n > g3::kMaxJobs) return MXQ_E_SHAPE;
+  g3::EncodeTiledFn enc = g3::get_encode();
+  if (!enc) return MXQ_E_UNSUPPORTED;
+  memset(plan_host, 0, g3::kPlanBytes);
+  g3::ChainParams* P = reinterpret_cast<g3::ChainParams*>(plan_host);
+  CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(reinterpret_cast<unsigned char*>(plan_host) + g3::kMapsOffset);
+  g3::PlanH& H = P->H;
+  g3::JobD* D = P->jobs;
+  const int ncta = kNumSMs;
+  int ximg_max = 0, coop = 0, next = 0;
+  for (int j = 0; j < n; ++j) {
+    const mxq_gemv_job_t& a = jobs[j];
+    const mxq_packed_t& w = a.w;
+    MXQ_CHECK_PTR(a.x);
+    MXQ_CHECK_PTR(a.y);
+    MXQ_CHECK_PTR(w.weight);
+    if (!w.weight_last || !w.zeros_and_scales || !w.zeros_2nd || !w.scales_2nd || !w.scales_4b || !w.zeros_4b)
+      return MXQ_E_NULL;
+    if ((reinterpret_cast<uintptr_t>(w.weight_last) | reinterpret_cast<uintptr_t>(w.zeros_and_scales) |
+         reinterpret_cast<uintptr_t>(w.zeros_2nd) | reinterpret_cast<uintptr_t>(w.scales_2nd) |
+         reinterpret_cast<uintptr_t>(w.scales_4b) | reinterpret_cast<uintptr_t>(w.zeros_4b)) & 15)
+      return MXQ_E_ALIGN;
+    if (a.IC <= 0 || a.OC <= 0 || a.IC % 256 || a.OC % 32 || a.IC > 32768 || a.OC > (1 << 24)) return MXQ_E_UNSUPPORTED;
+    if (a.dep >= j || a.dep < -1) return MXQ_E_SHAPE;
+    g3::JobD& d = D[j];
+    d.S2 = reinterpret_cast<const unsigned char*>(w.scales_2nd);
+    d.S4 = reinterpret_cast<const unsigned char*>(w.scales_4b);
+    d.Z4 = reinterpret_cast<const unsigned char*>(w.zeros_4b);
+    d.x = reinterpret_cast<const __half*>(a.x);
+    d.y = reinterpret_cast<__half*>(a.y);
+    d.nblk = (int)(a.IC / 64);
+    d.nch = (d.nblk + 63) / 64;
+    d.nqb = d.nblk / 4;
+    d.ngrp = (int)(a.OC / 4);
+    d.oc = (int)a.OC;
+    d.q = (int)ceil_div(d.ngrp, ncta);
+    d.gxl = (int)ceil_div(d.ngrp, d.q);
+    d.dep = a.dep;
+    d.dep_target = a.dep >= 0 ? D[a.dep].gxl : 0;
+    if (a.dep >= 0) {
+      coop = 1;
+      D[a.dep].publish = 1;
+    }
+    // whole rows in one chunk and 16-byte aligned row groups: one scales_2nd copy per stage
+    d.s2pitch = (d.nch == 1 && (d.nblk * 6) % 16 == 0) ? d.nblk * 6 : 0;
+    d.ximg_blocks = d.nch * 64;
+    const int bw = d.nblk * 4 < 256 ? d.nblk * 4 : 256, bwl = d.nblk < 64 ? d.nblk : 64;   // box widths in words
+    d.pw = bw * 4;
+    d.pwl = bwl * 4;
+    // jobs that read the same x with the same shape share one activation image and one CTA assignment
+    d.share = j > 0 && jobs[j - 1].x == a.x && jobs[j - 1].IC == a.IC && jobs[j - 1].OC == a.OC && jobs[j - 1].dep == a.dep;
+    if (d.share) {
+      d.rot = D[j - 1].rot;
+    } else {
+      d.rot = (ncta - next) % ncta;                 // active CTAs of this job: next .. next + gxl - 1 (mod ncta)
+      next = (next + d.gxl) % ncta;
+    }
+    const int ximg = ((16 + d.ximg_blocks * 160) + 127) & ~127;
+    if (ximg > ximg_max) ximg_max = ximg;
+    int rc = g3::make_map(enc, maps + j * 4 + 0, w.weight, a.OC, (int64_t)d.nblk * 4, 16, bw);
+    if (!rc) rc = g3::make_map(enc, maps + j * 4 + 1, w.weight_last, a.OC, d.nblk, 16, bwl);
+    if (!rc) rc = g3::make_map(enc, maps + j * 4 + 2, w.zeros_and_scales, a.OC, (int64_t)d.nch * 32, 16, 32);
+    if (!rc) rc = g3::make_map(enc, maps + j * 4 + 3, w.zeros_2nd, a.OC / 4, (int64_t)d.nch * 32, 4, 32);
+    if (rc) return rc;
+  }
+  const size_t fixed = 2 * (size_t)ximg_max + g3::kRedBytes + sizeof(g3::Bars) + 128;
+  if (fixed + 2 * (size_t)g3::kStageBytes > g3::kSmemMax) return MXQ_E_UNSUPPORTED;
+  int S = (int)((g3::kSmemMax - fixed) / g3::kStageBytes);
+  if (S > g3::kMaxStages) S = g3::kMaxStages;
+  H.magic = g3::kMagic;
+  H.n = n;
+  H.nstages = S;
+  H.ximg_max = ximg_max;
+  H.ncta = ncta;
+  H.coop = coop;
+  if (const char* e = getenv("MXQ_CHAIN_DBG")) H.dbg = atoi(e);
+  H.smem = (int)((size_t)S * g3::kStageBytes + fixed);
+  return MXQ_OK;
+}
+
+extern "C" int mxq_gemv_chain_run(const void* plan_host, const void* plan_dev, int32_t* sync_ws, unsigned flags,
+                                  void* stream) {
+  (void)flags;
+  if (!plan_host || !plan_dev || !sync_ws) return MXQ_E_NULL;
+  if (reinterpret_cast<uintptr_t>(plan_dev) & 63) return MXQ_E_ALIGN;
+  const g3::ChainParams& P = *reinterpret_cast<const g3::ChainParams*>(plan_host);
+  const g3::PlanH& H = P.H;
+  if (H.magic != g3::kMagic || H.n <= 0 || H.n > g3::kMaxJobs) return MXQ_E_SHAPE;
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return (int)e;
+  if (sms < H.ncta) return MXQ_E_UNSUPPORTED;       // the plan assumes one resident CTA per B200 SM
+  e = cudaFuncSetAttribute(g3::gemv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H.smem);
+  if (e != cudaSuccess) return (int)e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)H.ncta);
+  cfg.blockDim = dim3(g3::kThreads);
+  cfg.dynamicSmemBytes = (size_t)H.smem;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = H.coop ? 1 : 0;
+  const CUtensorMap* maps =
+      reinterpret_cast<const CUtensorMap*>(reinterpret_cast<const unsigned char*>(plan_dev) + g3::kMapsOffset);
+  e = cudaLaunchKernelEx(&cfg, g3::gemv_chain_kernel, P, maps, reinterpret_cast<int*>(sync_ws), 4, 16, 64, 256);
+  return e == cudaSuccess ? MXQ_OK : (int)e;
+}
+
+// profiling aid, not part of the documented surface
+extern "C" __attribute__((visibility("default"))) int mxq_debug_chain_trace(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g3::g_ctrace, sizeof(long long) * 4 * g3::kTraceEvents * 4);
+}

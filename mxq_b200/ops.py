@@ -415,6 +415,61 @@ def gemv_grouped(x: torch.Tensor, ps: list, outs: list | None = None, pdl: bool 
     return outs
 
 
+class GemvChain:
+    """A sequence of batch-1 decode GEMVs as ONE persistent launch (mxq_gemv_chain_*).
+
+    jobs: list of (x, packed, y, dep) -- x fp16 [IC] or [1, IC], y fp16 [OC] or [1, OC] (buffers owned by the
+    caller and kept alive by this object), dep = -1 (x ready at launch) or the index of an earlier job
+    whose y this job's x is (or depends on).  Jobs are otherwise unordered.  The plan is built once;
+    `run()` launches it on the current stream (capturable in a CUDA graph).  Longer chains than
+    MXQ_GEMV_CHAIN_MAX_JOBS are cut into several launches (stream order covers dependencies across them).
+    Raises RuntimeError with MXQ_E_UNSUPPORTED for shapes the chain kernel does not take (IC % 256 or OC % 32):
+    callers fall back to `gemv` per linear."""
+
+    def __init__(self, jobs: list, validate: bool = True):
+        import ctypes as C
+        if not jobs:
+            raise ValueError("GemvChain needs at least one job")
+        lib = L.lib()
+        self._keep = []
+        self._launches = []
+        dev = jobs[0][0].device
+        cap = L.GEMV_CHAIN_MAX_JOBS
+        for lo in range(0, len(jobs), cap):
+            part = jobs[lo:lo + cap]
+            arr = (L.GemvJobC * len(part))()
+            for i, (x, p, y, dep) in enumerate(part):
+                OC, IC = _check_packed(p) if validate else _packed_dims(p)
+                L.require_cuda(x, y, p["weight"])
+                if x.device != dev:
+                    raise RuntimeError("all jobs of a chain must live on one device")
+                if x.dtype != torch.float16 or x.numel() != IC or not x.is_contiguous():
+                    raise ValueError(f"job {lo + i}: x must be contiguous fp16 with {IC} elements")
+                if y.dtype != torch.float16 or y.numel() != OC or not y.is_contiguous():
+                    raise ValueError(f"job {lo + i}: y must be contiguous fp16 with {OC} elements")
+                d = -1 if dep is None else int(dep)
+                if d >= lo + i:
+                    raise ValueError(f"job {lo + i}: dep must name an earlier job")
+                # a dependency on a job of an earlier launch is covered by stream order
+                arr[i] = L.GemvJobC(x.data_ptr(), y.data_ptr(), L.packed_struct(p), IC, OC, d - lo if d >= lo else -1, 0)
+                self._keep.append((x, p, y))
+            host = torch.zeros(int(lib.mxq_gemv_chain_plan_bytes()) + 64, dtype=torch.uint8)
+            host = host[(-host.data_ptr()) % 64:][:int(lib.mxq_gemv_chain_plan_bytes())]      # 64-byte aligned view
+            with L.on(x):                         # the tensor maps are encoded against the jobs' device
+                L.check(lib.mxq_gemv_chain_plan(arr, len(part), host.data_ptr()), "mxq_gemv_chain_plan")
+            sync = torch.zeros(L.GEMV_CHAIN_SYNC_WORDS, dtype=torch.int32, device=dev)
+            self._launches.append((host, host.to(dev), sync))
+        self.device = dev
+        self.n = len(jobs)
+
+    def run(self):
+        lib = L.lib()
+        with L.on(self._launches[0][2]) as st:
+            for host, plan_dev, sync in self._launches:
+                rc = lib.mxq_gemv_chain_run(host.data_ptr(), plan_dev.data_ptr(), sync.data_ptr(), 0, st)
+                L.check(rc, "mxq_gemv_chain_run")
+
+
 def gemm_workspace_bytes(M: int, IC: int, OC: int) -> int:
     return max(int(L.lib().mxq_gemm_workspace_bytes(M, IC, OC)), 16)
 

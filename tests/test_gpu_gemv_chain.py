@@ -1,0 +1,135 @@
+"""GPU parity for the persistent decode-GEMV chain (csrc/gemv_chain.cu, mxq_gemv_chain_*): one launch for a
+list of batch-1 gemv_mxq_forward_cuda calls (gemv_mxq_cuda.cu:225-273).  Every job is checked against the
+fp64 oracle decode with north_star's per-element bound |err| <= 1e-3 * sum|w||x| (+ the fp16 store), and
+against exact arithmetic on the block-floating activations the kernel really multiplies."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mxq_oracle as O
+from tests.gpu_util import packed_to_dev
+from tests.test_gpu_packed import _block_float, _outlier_x, _per_element_bound
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(y, x16, p, what=""):
+    ref = O.gemm_mxq_f32(x16, p)[0]
+    per = _per_element_bound(x16, p)[0]
+    y = y.astype(np.float64)
+    bound = 1e-3 * per + np.abs(ref) * 2.0 ** -11 + 2.0 ** -25      # + half an ulp of the fp16 store (subnormal floor)
+    err = np.abs(y - ref)
+    assert (err <= bound).all(), f"{what}: worst err/bound {float((err / bound).max()):.3f}"
+    ref_bf = (_block_float(x16) @ O.decode_mxq(p).astype(np.float64).T)[0]
+    assert (np.abs(y - ref_bf) <= np.abs(ref_bf) * 2.0 ** -11 + 2.0 ** -25 + 1e-6 * per).all(), \
+        f"{what}: kernel != exact integer arithmetic on the converted activations"
+
+
+def _mk(cuda, shapes, seed=0):
+    ps = [O.random_packed(oc, ic, seed=seed + 7 * i + oc + ic) for i, (oc, ic) in enumerate(shapes)]
+    return ps, [packed_to_dev(p, cuda) for p in ps]
+
+
+def test_chain_independent_mixed_shapes(cuda):
+    """Ragged everything: partial 16-row tiles, a short last CTA, 1 / 2 / 3 metadata chunks per row
+    (IC = 256, 4096, 8192, 11008 = 43 quad-blocks), q/k/v-style jobs sharing one activation."""
+    from mxq_b200 import ops
+    shapes = [(256, 4096), (256, 4096), (256, 4096), (4128, 256), (128, 11008), (32, 256), (1184, 4096), (96, 8192),
+              (4096, 4096), (160, 1024), (11008, 4096), (4096, 11008)]
+    ps, pd = _mk(cuda, shapes)
+    xs = {ic: _outlier_x(1, ic, seed=ic) for ic in {s[1] for s in shapes}}
+    xd = {ic: torch.from_numpy(x).to(cuda) for ic, x in xs.items()}
+    ys = [torch.full((1, oc), float("nan"), dtype=torch.float16, device=cuda) for oc, _ in shapes]
+    chain = ops.GemvChain([(xd[ic], p, y, -1) for (oc, ic), p, y in zip(shapes, pd, ys)])
+    chain.run()
+    torch.cuda.synchronize()
+    for i, ((oc, ic), p, y) in enumerate(zip(shapes, ps, ys)):
+        _check(y.cpu().numpy()[0], xs[ic], p, f"job {i} {oc}x{ic}")
+    # the kernel re-arms its own counters
+    assert all(int(s.abs().sum()) == 0 for _, _, s in chain._launches)
+
+
+def test_chain_reruns_and_graph_replay_are_bit_identical(cuda):
+    from mxq_b200 import ops
+    shapes = [(512, 4096), (1024, 4096), (512, 11008), (4096, 4096)]
+    ps, pd = _mk(cuda, shapes, seed=5)
+    xd = {ic: torch.from_numpy(_outlier_x(1, ic, seed=ic + 1)).to(cuda) for ic in (4096, 11008)}
+    ys = [torch.zeros(oc, dtype=torch.float16, device=cuda) for oc, _ in shapes]
+    chain = ops.GemvChain([(xd[ic][0], p, y, -1) for (oc, ic), p, y in zip(shapes, pd, ys)])
+    chain.run()
+    torch.cuda.synchronize()
+    first = [y.clone() for y in ys]
+    for y in ys:
+        y.zero_()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        chain.run()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            chain.run()
+            chain.run()
+    for _ in range(3):
+        for y in ys:
+            y.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        for a, b in zip(first, ys):
+            assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+
+
+def test_chain_dependent_jobs(cuda):
+    """x of job j+1 IS y of job j (ping-pong buffers are reused, so a missing ordering would read a
+    half-written or stale vector): every link is checked against the oracle applied to the chain's own
+    intermediate result."""
+    from mxq_b200 import ops
+    dims = [4096, 11008, 4096, 4096, 256, 4096]
+    shapes = [(dims[i + 1], dims[i]) for i in range(len(dims) - 1)]
+    ps, pd = _mk(cuda, shapes, seed=11)
+    x0 = _outlier_x(1, dims[0], seed=2)
+    bufs = [torch.from_numpy(x0).to(cuda)[0].clone()] + [torch.zeros(d, dtype=torch.float16, device=cuda) for d in dims[1:]]
+    # scale the weights down so that five links stay inside fp16
+    for p, q in zip(ps, pd):
+        for k in ("scales_2nd", "scales_4b"):
+            p[k] = (p[k].astype(np.float32) * 0.2).astype(np.float16)
+            q[k].copy_(torch.from_numpy(p[k]))
+    chain = ops.GemvChain([(bufs[i], pd[i], bufs[i + 1], i - 1) for i in range(len(shapes))])
+    for rep in range(3):
+        for b in bufs[1:]:
+            b.fill_(float("nan"))
+        chain.run()
+        torch.cuda.synchronize()
+        vals = [b.cpu().numpy() for b in bufs]
+        assert all(np.isfinite(v).all() for v in vals)
+        for i, p in enumerate(ps):
+            _check(vals[i + 1], vals[i][None, :], p, f"rep {rep} link {i}")
+
+
+def test_chain_longer_than_one_launch(cuda):
+    from mxq_b200 import ops
+    from mxq_b200 import _lib as L
+    n = L.GEMV_CHAIN_MAX_JOBS + 5
+    ps, pd = _mk(cuda, [(64, 256)] * 3, seed=3)
+    x = _outlier_x(1, 256, seed=4)
+    xd = torch.from_numpy(x).to(cuda)
+    ys = [torch.zeros(1, 64, dtype=torch.float16, device=cuda) for _ in range(n)]
+    chain = ops.GemvChain([(xd, pd[i % 3], ys[i], -1) for i in range(n)])
+    assert len(chain._launches) == 2
+    chain.run()
+    torch.cuda.synchronize()
+    for i in (0, 1, 2, n - 6, n - 1):
+        _check(ys[i].cpu().numpy()[0], x, ps[i % 3], f"job {i}")
+
+
+def test_chain_rejects_unsupported_shapes(cuda):
+    from mxq_b200 import ops
+    ps, pd = _mk(cuda, [(64, 320)])
+    x = torch.zeros(320, dtype=torch.float16, device=cuda)
+    y = torch.zeros(64, dtype=torch.float16, device=cuda)
+    with pytest.raises(RuntimeError):
+        ops.GemvChain([(x, pd[0], y, -1)])
+    with pytest.raises(ValueError):
+        ops.GemvChain([(x[:256], pd[0], y, -1)])
+    ps, pd = _mk(cuda, [(40, 256)])                       # OC % 32 != 0
+    with pytest.raises(RuntimeError):
+        ops.GemvChain([(x[:256], pd[0], torch.zeros(40, dtype=torch.float16, device=cuda), -1)])
