@@ -48,11 +48,12 @@
 namespace mxq {
 namespace g3 {
 
-constexpr int kCW = 8;                        // compute warps: 2 sets x 4
+constexpr int kSets = 3;                      // compute warp sets; set s owns the tiles tau % kSets == s
 constexpr int kSetW = 4;
-constexpr int kProdA = kCW, kProdB = kCW + 1, kReducer = kCW + 2, kBuilder0 = kCW + 3;
-constexpr int kBW = 5;                        // builder warps
-constexpr int kWarps = kCW + 3 + kBW;         // 16
+constexpr int kCW = kSets * kSetW;            // compute warps
+constexpr int kProdA = kCW, kProdB = kCW + 1, kBuilder0 = kCW + 2;
+constexpr int kBW = 2;                        // builder warps
+constexpr int kWarps = kCW + 2 + kBW;         // 16
 constexpr int kThreads = kWarps * 32;
 constexpr int kBuilderThreads = kBW * 32;
 constexpr int kMaxJobs = MXQ_GEMV_CHAIN_MAX_JOBS;
@@ -71,9 +72,13 @@ constexpr int kStageBytes = 24832;
 static_assert(kOffZ4 + 32 <= kStageBytes && kStageBytes % 128 == 0, "stage layout");
 constexpr uint32_t kBytesBox = 2048 + 512;    // producer B: zeros_and_scales + zeros_2nd boxes
 
-constexpr int kRedDepth = 4;                  // tiles in flight between the compute warps and the reducer
-constexpr int kRedBytes = kRedDepth * kSetW * 16 * 4;
+constexpr int kRedBytes = kSets * 2 * kSetW * 16 * 4;   // per set: two parities x 4 warps x 16 rows
 constexpr int kMaxStages = 8;
+#ifndef MXQ_CHAIN_BACKOFF
+#define MXQ_CHAIN_BACKOFF 0
+#endif
+constexpr bool kWaitBackoff = MXQ_CHAIN_BACKOFF != 0;
+constexpr int kMaxTiles = 256;                // 16-row tiles of one CTA over the whole chain
 constexpr size_t kSmemMax = 227 * 1024 - 1024;
 
 struct JobD {                                 // 128 bytes
@@ -112,8 +117,34 @@ constexpr size_t kPlanBytes = kMapsOffset + (size_t)kMaxJobs * 4 * sizeof(CUtens
 
 struct Bars {
   uint64_t full[kMaxStages], empty[kMaxStages];
-  uint64_t imgfull[2], imgempty[2], redfull[kRedDepth], redempty[kRedDepth];
+  uint64_t imgfull[2], imgempty[2];
 };
+
+// Blocking wait with a suspend-time hint: the warp sleeps in hardware until the phase completes instead of
+// spinning.  With 16 warps of which most are waiting at any time, hint-less try_wait loops took three of
+// four issue slots from the working warp of a scheduler (every traced step ran ~4x slower than alone).
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  int spins = 0;
+  uint32_t ns = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)          // up to 1 ms per attempt
+        : "memory");
+    if (!ok) {
+      if (++spins > 4000000) __trap();                           // seconds: a missing arrive / copy, not a slow peer
+      if (kWaitBackoff) {                                        // back off: a polling warp takes issue slots
+        ns = ns < 128u ? ns + 32u : 128u;
+        __nanosleep(ns);
+      }
+    }
+  } while (!ok);
+}
+#define mbar_wait mbar_wait_sleep
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
@@ -169,7 +200,7 @@ __device__ __forceinline__ bool elect_one() {
 // Profiling only (MXQ_CHAIN_DBG & 8): clock64 stamps of CTA 1 -- [role][event index][stamp]; roles: compute
 // warp 0, producer A, reducer, builder warp 0
 constexpr int kTraceEvents = 96;
-__device__ long long g_ctrace[4 * kTraceEvents * 4];
+__device__ long long g_ctrace[5 * kTraceEvents * 4];
 #define CTRACE(role, idx, k)                                                                       \
   do {                                                                                             \
     if (tr && (idx) < kTraceEvents) g_ctrace[((role) * kTraceEvents + (idx)) * 4 + (k)] = clock64(); \
@@ -177,19 +208,22 @@ __device__ long long g_ctrace[4 * kTraceEvents * 4];
 
 // ---------------------------------------------------------------------------------------------
 // Activation image of one job (one batch row):
-//   [16 B zeros]
-//   [nb][4][32 B]   per 16-column group: 16 B of signed high bytes, 16 B of signed low bytes;
-//                   2-bit groups: register c, byte j = element 4j + c; pooled group: register
-//                   (e>>3)*2 + (e&1), byte (e&7)>>1 = element e
-//   tabI int4[nb]     -(sum_j X_j) * {64, 16, 4, 16}: the zero-point term for z1 masked IN PLACE
-//                     (zs & (3 << 2k) = z1 * 4^k) and for the nibble zero z4 (codes enter as 16 * q)
-//   tabF float4[nb]   2^(E-14) * {2^-6, 2^-6, 2^-6, 2^-4}
-// nb = nch * 64 blocks (zeros beyond the row).
+//   per quad of units Q = block / 16 (the four units of one compute-warp visit), 2048 B:
+//     [i = block % 4][k = group][t = unit % 4][h][16 B]   signed high (h = 0) / low (h = 1) bytes of the group
+//                   (2-bit groups: register c, byte j = element 4j + c; pooled group: register
+//                   (e>>3)*2 + (e&1), byte (e&7)>>1 = element e) -- the 8 lanes that feed one mma's B operand
+//                   (4 thread-columns t x high / low) read 128 contiguous bytes
+//   tabI int4[nb], tabF float4[nb]  indexed [Q][i][t]:
+//     tabI  -(sum_j X_j) * {64, 16, 4, 16}: the zero-point term for z1 masked IN PLACE
+//           (zs & (3 << 2k) = z1 * 4^k) and for the nibble zero z4 (codes enter as 16 * q)
+//     tabF  2^(E-14) * {2^-6, 2^-6, 2^-6, 2^-4}
+// nb = nch * 64 blocks (zeros beyond the row); block = 16 Q + 4 t + i.
 // X_j = rint(x_j * 2^(14-E)), E = exponent of 1.0078 * max|x| of the group, X = 256 * hi + lo with both
 // bytes signed.  Same quantities as csrc/gemv_mma.cu (error bound measured in tests/test_gpu_packed.py).
 // ---------------------------------------------------------------------------------------------
 template <int k>
 __device__ __forceinline__ void stage_group(const uint4 v0, const uint4 v1, unsigned char* dst, int* tI, float* tF) {
+  // dst: the group's high bytes; the low bytes follow 16 B later
   const uint32_t xw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
   uint32_t m2 = xw[0] & 0x7FFF7FFFu;
 #pragma unroll
@@ -250,7 +284,7 @@ __device__ __forceinline__ Share cta_share(const JobD& J, int cta, int ncta) {
 __device__ __forceinline__ void block_mac(const uint4 wa, const uint4 wb, const uint32_t wla, const uint32_t wlb,
                                           const uint32_t zsa, const uint32_t zsb, const uint32_t z2,
                                           const unsigned short (&s2)[3], const unsigned char* __restrict__ xb,
-                                          const uint32_t xstep, const int4 tI, const float4 tF, const float s4a,
+                                          const bool bact, const int4 tI, const float4 tF, const float s4a,
                                           const float s4b, const int z4a, const int z4b, const int c4, const int c16,
                                           const int c64, const int c256, float& acc0, float& acc1) {
   constexpr uint32_t M2 = 0xC0C0C0C0u, M4 = 0xF0F0F0F0u;
@@ -258,7 +292,8 @@ __device__ __forceinline__ void block_mac(const uint4 wa, const uint4 wb, const 
   const uint32_t z2s8 = (uint32_t)imad((int)z2, c256, 0), z2s4 = (uint32_t)imad((int)z2, c16, 0);
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const uint4 X = *reinterpret_cast<const uint4*>(xb + k * xstep);
+    uint4 X = make_uint4(0u, 0u, 0u, 0u);                               // only 8 lanes feed a non-zero B column
+    if (bact) X = *reinterpret_cast<const uint4*>(xb + k * 128);
     const uint32_t wka = k == 0 ? wa.x : (k == 1 ? wa.y : wa.z);
     const uint32_t wkb = k == 0 ? wb.x : (k == 1 ? wb.y : wb.z);
     int d[4] = {0, 0, 0, 0};
@@ -294,7 +329,8 @@ __device__ __forceinline__ void block_mac(const uint4 wa, const uint4 wb, const 
     }
   }
   {
-    const uint4 X = *reinterpret_cast<const uint4*>(xb + 3 * xstep);
+    uint4 X = make_uint4(0u, 0u, 0u, 0u);
+    if (bact) X = *reinterpret_cast<const uint4*>(xb + 3 * 128);
     int d[4] = {0, 0, 0, 0};
     // nibbles as 16 * q: low nibbles (elements 0,2,4,6 / 8,..) shifted up, high nibbles in place
     imma(d, (uint32_t)imad((int)wa.w, c16, 0) & M4, (uint32_t)imad((int)wb.w, c16, 0) & M4, wa.w & M4, wb.w & M4, X.x, X.y);
@@ -318,16 +354,54 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
   unsigned char* img = stages + (size_t)S * kStageBytes;
   float* red = reinterpret_cast<float*>(img + 2 * (size_t)ximg_max);
   Bars& bars = *reinterpret_cast<Bars*>(reinterpret_cast<unsigned char*>(red) + kRedBytes);
-
+  // job table for the compute / reducer / builder warps: a constant-bank miss per job (a new 128-byte
+  // descriptor every ~2 us) showed up as a 1300-cycle gap between two jobs of a compute warp; the producers,
+  // which run ahead, keep reading the constant bank (uniform operands for the TMA instructions)
+  JobD* jobs = reinterpret_cast<JobD*>(reinterpret_cast<unsigned char*>(&bars) + ((sizeof(Bars) + 127) & ~size_t(127)));
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&P.jobs[0]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(jobs);
+    for (int i = threadIdx.x; i < n * (int)(sizeof(JobD) / 4); i += kThreads) dst[i] = src[i];
+  }
+  // This CTA's tiles in chain order, one 16-byte record each: the compute warps walk this list instead of
+  // re-deriving their share of every job (the job loop cost a compute warp ~1200 cycles per job).
+  //   x = job | tile << 8 | nrg << 16 | flags << 24 (1: first tile of the job here, 2: the job needs a new image)
+  //   y = first row group of the tile,  z = number of K chunks,  w = image sequence number
+  uint4* tiles = reinterpret_cast<uint4*>(jobs + n);
+  int* tcount = reinterpret_cast<int*>(tiles + kMaxTiles);   // [kMaxJobs] tiles per job, then [1] total
+  int* tnew = tcount + kMaxJobs + 1;                         // [kMaxJobs] 1 if the job needs a new image here
+  __syncthreads();                                           // the shared-memory job table is complete
+  if (threadIdx.x < n) {
+    const JobD& J = jobs[threadIdx.x];
+    const Share sh = cta_share(J, cta, ncta);
+    tcount[threadIdx.x] = sh.active ? sh.T : 0;
+    tnew[threadIdx.x] = (sh.active && !J.share) ? 1 : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x < n) {
+    const int j = threadIdx.x;
+    int off = 0, imgk = -1;
+    for (int k = 0; k < j; ++k) {
+      off += tcount[k];
+      imgk += tnew[k];
+    }
+    imgk += tnew[j];
+    const JobD& J = jobs[j];
+    const Share sh = cta_share(J, cta, ncta);
+    const int T = tcount[j];
+    for (int tile = 0; tile < T; ++tile) {
+      const int nrg = min(4, sh.qc - tile * 4);
+      const uint32_t flags = tile == 0 ? (J.share ? 1u : 3u) : 0u;
+      tiles[off + tile] = make_uint4((uint32_t)j | ((uint32_t)tile << 8) | ((uint32_t)nrg << 16) | (flags << 24),
+                                     (uint32_t)(sh.grp_base + tile * 4), (uint32_t)J.nch, (uint32_t)imgk);
+    }
+    if (j == n - 1) tcount[kMaxJobs] = off + T;
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&bars.full[s], 2); mbar_init(&bars.empty[s], kSetW); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bars.imgfull[b], kBW);
       mbar_init(&bars.imgempty[b], kCW);
-    }
-    for (int b = 0; b < kRedDepth; ++b) {
-      mbar_init(&bars.redfull[b], kSetW);
-      mbar_init(&bars.redempty[b], 1);
     }
     mbar_fence_init();
   }
@@ -337,6 +411,9 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
     // =========================================== compute ===========================================
     const int g = lane >> 2, t = lane & 3;
     const int set = warp >> 2, qw = warp & 3;
+    int tmod = 0;                                             // tau % kSets
+    int nset = 0;                                             // tiles this set has finished
+    int since = 0;                                            // stages skipped since the last observed `full` phase
     const int U = qw * 4 + t;                                 // this thread-column's unit inside a stage
     const int rgl = g >> 1;                                   // row group of this thread's two rows
     const int rowa = rgl * 4 + (g & 1), rowb = rowa + 2;      // tile rows (mma rows g and g + 8)
@@ -345,55 +422,85 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
     const uint32_t oZ2 = kOffZ2 + rgl * 128 + (U & 7) * 16;
     const uint32_t zsh = half * 16, z2sh = half * 8;
     const bool bact = (g >> 1) == t;                          // this lane feeds a non-zero B column
-    const uint32_t xlane = bact ? (uint32_t)(16 + U * 512 + (g & 1) * 16) : 0u;
-    const uint32_t xchunk = bact ? 64u * 128u : 0u, xblk = bact ? 128u : 0u, xstep = bact ? 32u : 0u;
+    const uint32_t xlane = (uint32_t)(qw * 2048 + t * 32 + (g & 1) * 16);   // + i * 512 + k * 128 (bact lanes only)
+    // Thread-columns 2, 3 walk their four blocks in the order 2, 3, 0, 1: the weight loads of one instruction
+    // then hit four different 16-byte bank groups of a row instead of two (the units of t and t + 2 are
+    // 128 B apart).  sw selects the swapped halves of every per-visit metadata vector.
+    const bool sw = (t & 2) != 0;
+    const uint32_t lo32 = sw ? 32u : 0u, hi32 = sw ? 0u : 32u;
 
     int slot = 0, sphase = 0;                                 // ring position
-    int tau = 0;                                              // tile sequence number (reduce buffers, set choice)
-    int imgk = -1;                                            // image sequence number
     const bool tr = (dbg & 8) && cta == 1 && warp == 0 && lane == 0;
     int ev = 0;
-    for (int j = 0; j < n; ++j) {
-      const JobD& J = P.jobs[j];
-      const Share sh = cta_share(J, cta, ncta);
-      if (!sh.active) continue;
-      if (!J.share) {
-        if (imgk >= 0) {                                      // done with the previous image
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars.imgempty[imgk & 1]);
+    const int ntile = tcount[kMaxJobs];
+    // per-job state, reloaded at the first tile of a job
+    const unsigned char* ximg = img;
+    const unsigned char* tabI = img;
+    const unsigned char* tabF = img;
+    __half* yj = nullptr;
+    int nqb = 0, publish = 0, lastimg = -1;
+    uint32_t s2pitch = kPS2, s2odd = 0, oWa = 0, oWb = 0, oWLa = 0, oWLb = 0;
+    for (int e = 0; e < ntile; ++e) {
+      const uint4 E = tiles[e];
+      const int j = (int)(E.x & 0xFFu), nrg = (int)((E.x >> 16) & 0xFFu), nch = (int)E.z;
+      const int rg0 = (int)E.y;
+      if (E.x & (1u << 24)) {                                 // first tile of a job
+        CTRACE(4, j, 0);
+        const JobD& J = jobs[j];
+        if (E.x & (2u << 24)) {                               // the job has its own activation image
+          const int imgk = (int)E.w;
+          if (lastimg >= 0) {                                 // done with the previous image
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.imgempty[lastimg & 1]);
+          }
+          lastimg = imgk;
+          mbar_wait(&bars.imgfull[imgk & 1], (imgk >> 1) & 1);
+          ximg = img + (size_t)(imgk & 1) * ximg_max;
         }
-        ++imgk;
-        mbar_wait(&bars.imgfull[imgk & 1], (imgk >> 1) & 1);
+        CTRACE(4, j, 2);
+        const int nb = J.ximg_blocks;
+        tabI = ximg + nb * 128;
+        tabF = tabI + nb * 16;
+        nqb = J.nqb;
+        publish = J.publish;
+        yj = J.y;
+        s2pitch = J.s2pitch ? (uint32_t)J.s2pitch : (uint32_t)kPS2;
+        s2odd = J.s2pitch ? 0u : (uint32_t)((J.nblk * 6) & 15);
+        oWa = kOffW + rowa * J.pw + U * 64;
+        oWb = oWa + 2 * J.pw;
+        oWLa = kOffWL + rowa * J.pwl + U * 16;
+        oWLb = oWLa + 2 * J.pwl;
+        CTRACE(4, j, 3);
       }
-      const unsigned char* ximg = img + (size_t)(imgk & 1) * ximg_max;
-      const int nb = J.ximg_blocks;
-      const unsigned char* tabI = ximg + 16 + nb * 128;
-      const unsigned char* tabF = tabI + nb * 16;
-      const int nch = J.nch, nqb = J.nqb;
-      const int row0_cta = sh.grp_base * 4;
-      const uint32_t s2pitch = J.s2pitch ? (uint32_t)J.s2pitch : (uint32_t)kPS2;
-      const uint32_t s2odd = J.s2pitch ? 0u : (uint32_t)((J.nblk * 6) & 15);
-      const uint32_t oWa = kOffW + rowa * J.pw + U * 64, oWb = oWa + 2 * J.pw;
-      const uint32_t oWLa = kOffWL + rowa * J.pwl + U * 16, oWLb = oWLa + 2 * J.pwl;
-      for (int tile = 0; tile < sh.T; ++tile, ++tau) {
-        if ((tau & 1) != set) {                               // the other set's tile: skip its stages
-          slot += nch;
-          while (slot >= S) { slot -= S; sphase ^= 1; }
+      {
+        const bool mine = tmod == set;
+        if (++tmod == kSets) tmod = 0;
+        if (!mine) {
+          // Another set's tile: skip its stages -- but a parity wait is only meaningful if the previous
+          // phase of that barrier is known to be complete, so at least one `full` phase in every S
+          // consecutive stages is observed (the producers fill in order: seeing stage u implies all before).
+          for (int ch = 0; ch < nch; ++ch) {
+            if (++since == S) {
+              mbar_wait(&bars.full[slot], sphase);
+              since = 0;
+            }
+            if (++slot == S) { slot = 0; sphase ^= 1; }
+          }
           continue;
         }
         float acc0 = 0.f, acc1 = 0.f;
         float s4a = 0.f, s4b = 0.f;
         int z4a = 0, z4b = 0;
-        const int rg0 = sh.grp_base + tile * 4;
         const uint32_t oS2 = kOffS2 + rgl * s2pitch + (((rg0 + rgl) & 1) ? s2odd : 0u) + U * 24;
         for (int ch = 0; ch < nch; ++ch) {
           const int nq = min(16, nqb - ch * 16);
           CTRACE(0, ev, 0);
           mbar_wait(&bars.full[slot], sphase);
+          since = 0;
           CTRACE(0, ev, 1);
           const unsigned char* s = stages + (size_t)slot * kStageBytes;
           if (ch == 0) {                                      // 4-bit pool scale / zero of this thread's two rows
-            const int R = row0_cta + tile * 16;
+            const int R = rg0 * 4;
             const __half* s4p = reinterpret_cast<const __half*>(s + kOffS4 + ((rg0 & 1) ? 8 : 0));
             s4a = __half2float(s4p[rowa]);
             s4b = __half2float(s4p[rowb]);
@@ -413,30 +520,37 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
             const uint2 sA = *reinterpret_cast<const uint2*>(s + oS2);
             const uint2 sB = *reinterpret_cast<const uint2*>(s + oS2 + 8);
             const uint2 sC = *reinterpret_cast<const uint2*>(s + oS2 + 16);
-            const uint32_t s2w[6] = {sA.x, sA.y, sB.x, sB.y, sC.x, sC.y};
-            const unsigned char* xb0 = ximg + xlane + (uint32_t)ch * xchunk;
-            const unsigned char* tI0 = tabI + (ch * 64 + U * 4) * 16;
-            const unsigned char* tF0 = tabF + (ch * 64 + U * 4) * 16;
+            // blocks in processing order: (0, 1, 2, 3) or (2, 3, 0, 1)
+            const uint32_t wlA[4] = {sw ? wl4a.z : wl4a.x, sw ? wl4a.w : wl4a.y, sw ? wl4a.x : wl4a.z, sw ? wl4a.y : wl4a.w};
+            const uint32_t wlB[4] = {sw ? wl4b.z : wl4b.x, sw ? wl4b.w : wl4b.y, sw ? wl4b.x : wl4b.z, sw ? wl4b.y : wl4b.w};
+            const uint32_t zsA[4] = {sw ? zs4a.z : zs4a.x, sw ? zs4a.w : zs4a.y, sw ? zs4a.x : zs4a.z, sw ? zs4a.y : zs4a.w};
+            const uint32_t zsB[4] = {sw ? zs4b.z : zs4b.x, sw ? zs4b.w : zs4b.y, sw ? zs4b.x : zs4b.z, sw ? zs4b.y : zs4b.w};
+            const uint32_t z2v[4] = {sw ? z24.z : z24.x, sw ? z24.w : z24.y, sw ? z24.x : z24.z, sw ? z24.y : z24.w};
+            const uint32_t s2w[6] = {sw ? sB.y : sA.x, sw ? sC.x : sA.y, sw ? sC.y : sB.x,
+                                     sw ? sA.x : sB.y, sw ? sA.y : sC.x, sw ? sB.x : sC.y};
+            const unsigned char* xb0 = ximg + xlane + (uint32_t)ch * 8192u;
+            const unsigned char* tI0 = tabI + (ch * 64 + qw * 16 + t) * 16;      // + block * 64
+            const unsigned char* tF0 = tabF + (ch * 64 + qw * 16 + t) * 16;
             float v0 = 0.f, v1 = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const uint4 wa = *reinterpret_cast<const uint4*>(s + oWa + i * 16);
-              const uint4 wb = *reinterpret_cast<const uint4*>(s + oWb + i * 16);
-              const uint32_t wla = i == 0 ? wl4a.x : i == 1 ? wl4a.y : i == 2 ? wl4a.z : wl4a.w;
-              const uint32_t wlb = i == 0 ? wl4b.x : i == 1 ? wl4b.y : i == 2 ? wl4b.z : wl4b.w;
-              const uint32_t zsa = (i == 0 ? zs4a.x : i == 1 ? zs4a.y : i == 2 ? zs4a.z : zs4a.w) >> zsh;
-              const uint32_t zsb = (i == 0 ? zs4b.x : i == 1 ? zs4b.y : i == 2 ? zs4b.z : zs4b.w) >> zsh;
-              const uint32_t z2 = (i == 0 ? z24.x : i == 1 ? z24.y : i == 2 ? z24.z : z24.w) >> z2sh;
+              // i-th block in processing order = block (i ^ 2) for the swapped thread-columns
+              const uint32_t o32 = (i & 2) ? hi32 : lo32;                        // 32 * (block >> 1)
+              const uint4 wa = *reinterpret_cast<const uint4*>(s + oWa + o32 + (i & 1) * 16);
+              const uint4 wb = *reinterpret_cast<const uint4*>(s + oWb + o32 + (i & 1) * 16);
+              const uint32_t wla = wlA[i], wlb = wlB[i];
+              const uint32_t zsa = zsA[i] >> zsh, zsb = zsB[i] >> zsh;
+              const uint32_t z2 = z2v[i] >> z2sh;
               unsigned short s2[3];
 #pragma unroll
               for (int k = 0; k < 3; ++k) {
                 const int hidx = 3 * i + k;
                 s2[k] = (unsigned short)(s2w[hidx >> 1] >> (16 * (hidx & 1)));
               }
-              const int4 tI = *reinterpret_cast<const int4*>(tI0 + i * 16);
-              const float4 tF = *reinterpret_cast<const float4*>(tF0 + i * 16);
-              block_mac(wa, wb, wla, wlb, zsa, zsb, z2, s2, xb0 + i * xblk, xstep, tI, tF, s4a, s4b, z4a, z4b, c4, c16,
-                        c64, c256, v0, v1);
+              const int4 tI = *reinterpret_cast<const int4*>(tI0 + o32 * 4 + (i & 1) * 64);
+              const float4 tF = *reinterpret_cast<const float4*>(tF0 + o32 * 4 + (i & 1) * 64);
+              block_mac(wa, wb, wla, wlb, zsa, zsb, z2, s2, xb0 + o32 * 32 + (i & 1) * 512, bact, tI, tF, s4a, s4b, z4a, z4b,
+                        c4, c16, c64, c256, v0, v1);
             }
             if (U < nq) { acc0 += v0; acc1 += v1; }           // units beyond the row: zero codes, but stale scales
           }
@@ -446,20 +560,30 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
           if (++slot == S) { slot = 0; sphase ^= 1; }
           if (ch + 1 < nch) { CTRACE(0, ev, 3); ++ev; }
         }
-        // ---- the warp's K partial of this tile -> reducer ------------------------------------------
+        // ---- K partials of the set's 4 warps -> one of them adds in a fixed order and stores y -------
         acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1);
         acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
         acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
         acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
-        const int p = tau % kRedDepth;
-        mbar_wait(&bars.redempty[p], ((tau / kRedDepth) & 1) ^ 1);
+        float* rbuf = red + ((size_t)(set * 2 + (nset & 1)) * kSetW) * 16;
         if (t == 0) {
-          float* rp = red + ((size_t)p * kSetW + qw) * 16;
-          rp[rowa] = acc0;
-          rp[rowb] = acc1;
+          rbuf[qw * 16 + rowa] = acc0;
+          rbuf[qw * 16 + rowb] = acc1;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.redfull[p]);
+        // The buffer of parity p is rewritten two tiles later, after another pass through this barrier,
+        // which the warp that adds tile n only reaches after it has read the buffer.
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + set), "n"(kSetW * 32) : "memory");
+        if ((nset & 3) == qw) {
+          const int r = lane & 15, h = lane >> 4;
+          float sum = rbuf[(h * 2) * 16 + r] + rbuf[(h * 2 + 1) * 16 + r];
+          sum += __shfl_xor_sync(0xffffffffu, sum, 16);      // (warp 0 + warp 1) + (warp 2 + warp 3) on both halves
+          if (lane < 16 && (r >> 2) < nrg) yj[(size_t)rg0 * 4 + r] = __float2half_rn(sum);
+          if (publish) {                                      // a later job waits for this one: count the tile
+            __syncwarp();
+            if (lane == 0) red_release_add(sync_ws + j, 1);
+          }
+        }
+        ++nset;
         CTRACE(0, ev, 3);
         ++ev;
       }
@@ -535,36 +659,6 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
         }
       }
     }
-  } else if (warp == kReducer) {
-    // =========================================== reducer ===========================================
-    int tau = 0;
-    const int r = lane & 15, h = lane >> 4;
-    const bool tr = (dbg & 8) && cta == 1 && lane == 0;
-    for (int j = 0; j < n; ++j) {
-      const JobD& J = P.jobs[j];
-      const Share sh = cta_share(J, cta, ncta);
-      if (!sh.active) continue;
-      for (int tile = 0; tile < sh.T; ++tile) {
-        const int p = tau % kRedDepth;
-        CTRACE(2, tau, 0);
-        mbar_wait(&bars.redfull[p], (tau / kRedDepth) & 1);
-        CTRACE(2, tau, 1);
-        const float* rp = red + ((size_t)p * kSetW + h * 2) * 16 + r;
-        float sum = rp[0] + rp[16];
-        sum += __shfl_xor_sync(0xffffffffu, sum, 16);        // (warp 0 + warp 1) + (warp 2 + warp 3) on both halves
-        if (lane < 16 && tile * 4 + (r >> 2) < sh.qc)
-          J.y[(size_t)sh.grp_base * 4 + (size_t)tile * 16 + r] = __float2half_rn(sum);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.redempty[p]);
-        CTRACE(2, tau, 2);
-        ++tau;
-      }
-      // publish (only if a later job waits for this one): this CTA's rows of job j are in global memory
-      if (J.publish) {
-        __syncwarp();
-        if (lane == 0) red_release_add(sync_ws + j, 1);
-      }
-    }
   } else {
     // =========================================== image builders ====================================
     // a thread converts one 64-column block (4 groups) per round
@@ -572,7 +666,7 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
     int imgk = -1;
     const bool tr = (dbg & 8) && cta == 1 && bt == 0;
     for (int j = 0; j < n; ++j) {
-      const JobD& J = P.jobs[j];
+      const JobD& J = jobs[j];
       const Share sh = cta_share(J, cta, ncta);
       if (!sh.active || J.share) continue;
       ++imgk;
@@ -584,34 +678,40 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
         const int* flag = sync_ws + J.dep;
         const long long t0 = clock64();
         while (ld_acquire(flag) < J.dep_target) {
+          __nanosleep(64);
           if (clock64() - t0 > 40000000000LL) __trap();
         }
       }
       unsigned char* xi = img + (size_t)bsel * ximg_max;
       const int nb = J.ximg_blocks, nblk = J.nblk;
-      int* tI = reinterpret_cast<int*>(xi + 16 + (size_t)nb * 128);
-      float* tF = reinterpret_cast<float*>(xi + 16 + (size_t)nb * 144);
+      int* tI = reinterpret_cast<int*>(xi + (size_t)nb * 128);
+      float* tF = reinterpret_cast<float*>(xi + (size_t)nb * 144);
       if (!(dbg & 4)) {
         for (int b = bt; b < nb; b += kBuilderThreads) {
-          unsigned char* dst = xi + 16 + (size_t)b * 128;
+          // block b = 16 Q + 4 t + i -> image slot [Q][i][k][t][h], table slot [Q][i][t]
+          const int Q = b >> 4, tq = (b >> 2) & 3, iq = b & 3;
+          unsigned char* dst = xi + (size_t)Q * 2048 + iq * 512 + tq * 32;       // + k * 128 + h * 16
+          const int ts = (Q * 16 + iq * 4 + tq) * 4;
           if (b < nblk) {
             const __half* xa = J.x + (size_t)b * 64;
             const uint4 a0 = ld_cg16(xa), a1 = ld_cg16(xa + 8), a2 = ld_cg16(xa + 16), a3 = ld_cg16(xa + 24);
             const uint4 a4 = ld_cg16(xa + 32), a5 = ld_cg16(xa + 40), a6 = ld_cg16(xa + 48), a7 = ld_cg16(xa + 56);
-            stage_group<0>(a0, a1, dst, tI + b * 4 + 0, tF + b * 4 + 0);
-            stage_group<1>(a2, a3, dst + 32, tI + b * 4 + 1, tF + b * 4 + 1);
-            stage_group<2>(a4, a5, dst + 64, tI + b * 4 + 2, tF + b * 4 + 2);
-            stage_group<3>(a6, a7, dst + 96, tI + b * 4 + 3, tF + b * 4 + 3);
+            stage_group<0>(a0, a1, dst, tI + ts + 0, tF + ts + 0);
+            stage_group<1>(a2, a3, dst + 128, tI + ts + 1, tF + ts + 1);
+            stage_group<2>(a4, a5, dst + 256, tI + ts + 2, tF + ts + 2);
+            stage_group<3>(a6, a7, dst + 384, tI + ts + 3, tF + ts + 3);
           } else {                                            // blocks beyond the row (last chunk): zeros
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) reinterpret_cast<uint4*>(dst)[i] = z;
-            reinterpret_cast<uint4*>(tI)[b] = z;
-            reinterpret_cast<uint4*>(tF)[b] = z;
+            for (int k = 0; k < 4; ++k) {
+              reinterpret_cast<uint4*>(dst + k * 128)[0] = z;
+              reinterpret_cast<uint4*>(dst + k * 128)[1] = z;
+            }
+            *reinterpret_cast<uint4*>(tI + ts) = z;
+            *reinterpret_cast<uint4*>(tF + ts) = z;
           }
         }
       }
-      if (bt < 4) reinterpret_cast<uint32_t*>(xi)[bt] = 0u;
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.imgfull[bsel]);
       CTRACE(3, imgk, 2);
@@ -705,7 +805,11 @@ extern "C" int mxq_gemv_chain_plan(const mxq_gemv_job_t* jobs, int n, void* plan
     d.q = (int)ceil_div(d.ngrp, ncta);
     d.gxl = (int)ceil_div(d.ngrp, d.q);
     d.dep = a.dep;
-    d.dep_target = a.dep >= 0 ? D[a.dep].gxl : 0;
+    if (a.dep >= 0) {                                // number of 16-row tiles of that job over all CTAs
+      const g3::JobD& pj = D[a.dep];
+      const int qlast = pj.ngrp - (pj.gxl - 1) * pj.q;
+      d.dep_target = (pj.gxl - 1) * ((pj.q + 3) / 4) + (qlast + 3) / 4;
+    }
     if (a.dep >= 0) {
       coop = 1;
       D[a.dep].publish = 1;
@@ -724,7 +828,7 @@ extern "C" int mxq_gemv_chain_plan(const mxq_gemv_job_t* jobs, int n, void* plan
       d.rot = (ncta - next) % ncta;                 // active CTAs of this job: next .. next + gxl - 1 (mod ncta)
       next = (next + d.gxl) % ncta;
     }
-    const int ximg = ((16 + d.ximg_blocks * 160) + 127) & ~127;
+    const int ximg = d.ximg_blocks * 160;
     if (ximg > ximg_max) ximg_max = ximg;
     int rc = g3::make_map(enc, maps + j * 4 + 0, w.weight, a.OC, (int64_t)d.nblk * 4, 16, bw);
     if (!rc) rc = g3::make_map(enc, maps + j * 4 + 1, w.weight_last, a.OC, d.nblk, 16, bwl);
@@ -732,7 +836,11 @@ extern "C" int mxq_gemv_chain_plan(const mxq_gemv_job_t* jobs, int n, void* plan
     if (!rc) rc = g3::make_map(enc, maps + j * 4 + 3, w.zeros_2nd, a.OC / 4, (int64_t)d.nch * 32, 4, 32);
     if (rc) return rc;
   }
-  const size_t fixed = 2 * (size_t)ximg_max + g3::kRedBytes + sizeof(g3::Bars) + 128;
+  const size_t fixed = 2 * (size_t)ximg_max + g3::kRedBytes + ((sizeof(g3::Bars) + 127) & ~size_t(127)) +
+                       (size_t)n * sizeof(g3::JobD) + (size_t)g3::kMaxTiles * 16 + (2 * g3::kMaxJobs + 1) * 4 + 128;
+  int tiles_max = 0;                                  // 16-row tiles of a CTA with a full share of every job
+  for (int j = 0; j < n; ++j) tiles_max += (D[j].q + 3) / 4;
+  if (tiles_max > g3::kMaxTiles) return MXQ_E_UNSUPPORTED;
   if (fixed + 2 * (size_t)g3::kStageBytes > g3::kSmemMax) return MXQ_E_UNSUPPORTED;
   int S = (int)((g3::kSmemMax - fixed) / g3::kStageBytes);
   if (S > g3::kMaxStages) S = g3::kMaxStages;
@@ -781,5 +889,5 @@ extern "C" int mxq_gemv_chain_run(const void* plan_host, const void* plan_dev, i
 
 // profiling aid, not part of the documented surface
 extern "C" __attribute__((visibility("default"))) int mxq_debug_chain_trace(long long* host_out) {
-  return (int)cudaMemcpyFromSymbol(host_out, g3::g_ctrace, sizeof(long long) * 4 * g3::kTraceEvents * 4);
+  return (int)cudaMemcpyFromSymbol(host_out, g3::g_ctrace, sizeof(long long) * 5 * g3::kTraceEvents * 4);
 }

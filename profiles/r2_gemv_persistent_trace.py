@@ -16,11 +16,11 @@ NEV = 96
 
 
 def trace():
-    buf = (C.c_longlong * (4 * NEV * 4))()
+    buf = (C.c_longlong * (5 * NEV * 4))()
     lib = L.lib()
     lib.mxq_debug_chain_trace.argtypes = [C.c_void_p]
     assert lib.mxq_debug_chain_trace(C.cast(buf, C.c_void_p)) == 0
-    return np.frombuffer(buf, dtype=np.int64).reshape(4, NEV, 4).copy()
+    return np.frombuffer(buf, dtype=np.int64).reshape(5, NEV, 4).copy()
 
 
 def main():
@@ -50,6 +50,10 @@ def main():
         for e in range(24):
             r = t[2, e] - t0
             print(f"  r{e:02d} {r[0]:7d} {r[1]:7d} {r[2]:7d}   wait {r[1]-r[0]:5d} work {r[2]-r[1]:5d}")
+        print("compute warp 0 per job: [loop top, after share, after image handshake, before tile loop]")
+        for e in range(12):
+            r = t[4, e] - t0
+            print(f"  j{e:02d} {r[0]:7d} {r[1]:7d} {r[2]:7d} {r[3]:7d}")
         print("builder: [wait begin, got, done]")
         for e in range(16):
             r = t[3, e] - t0
