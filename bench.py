@@ -558,17 +558,45 @@ def run_components(ctx, pk, with_cpu=True):
             ops.gemv(xin[4096], layer[3], out=yout[4096], validate=False, pdl=True)
             ops.gemv_grouped(xin[4096], layer[4:6], outs=yg, validate=False, pdl=True)
             ops.gemv(xin[11008], layer[6], out=yout[4096], validate=False, pdl=True)
-    gemv = {"workload": "batch-1 decode GEMV over the 56 packed linears of 8 Llama-2-7B layers (0.6 GB of distinct packed weights, "
-                        "one CUDA graph, programmatic dependent launch)"}
+    gemv = {"workload": "batch-1 decode GEMV over the 56 packed linears of 8 Llama-2-7B layers (0.6 GB of distinct packed weights); "
+                        "headline = ONE persistent launch (mxq_gemv_chain), per-linear launches (CUDA graph, PDL) beside it"}
     try:
+        # --- the persistent chain: 4 activation vectors per layer (q/k/v | o | gate/up | down), distinct outputs
+        xl = [{"attn": torch.randn(4096, device=dev).half(), "o": torch.randn(4096, device=dev).half(),
+               "mlp": torch.randn(4096, device=dev).half(), "down": torch.randn(11008, device=dev).half()} for _ in range(nl)]
+        xkey = ["attn", "attn", "attn", "o", "mlp", "mlp", "down"]
+        ych = [[torch.empty(oc, device=dev, dtype=torch.float16) for oc, _ in shapes] for _ in range(nl)]
+        jobs = [(xl[li][xkey[i]], layer[i], ych[li][i], -1) for li, layer in enumerate(packs) for i in range(len(shapes))]
+        chain = ops.GemvChain(jobs, validate=False)
+        nrep = 4        # several chain launches per graph: one launch per graph would time the replay overhead (~8 us)
+        ms = graph_time(torch, lambda _: chain.run(), nrep, warm=1, reps=5)
+        ach = gbytes / ms / 1e6
+        tr, src = ncu_traffic("gemv_chain_kernel", "gemv_chain_32x4096x4096")
+        gemv["roofline"] = {"bound": "hbm", "kernel": "gemv_chain_kernel (persistent: TMA stage ring + IMMA m16n8k32, csrc/gemv_chain.cu)",
+                            "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                            "traffic": tr, "traffic_source": (src or "") + " (32 x 4096x4096 jobs in one launch: 202,178,560 algorithmic bytes)",
+                            "algorithmic_bytes": gbytes, "ms_per_8_layers": ms, "launches": 1,
+                            "note": "independent jobs: the weight-stream rate of one launch over 56 linears"}
+        # the same 56 linears as a DEPENDENT chain: q/k/v <- x, o <- q, gate/up <- o, down <- gate, next layer <- down
+        dj, prev, xcur = [], -1, xl[0]["attn"]
+        for li, layer in enumerate(packs):
+            base = len(dj)
+            q, k_, v, o, gt, up, dn = ych[li]
+            dj += [(xcur, layer[0], q, prev), (xcur, layer[1], k_, prev), (xcur, layer[2], v, prev), (q, layer[3], o, base),
+                   (o, layer[4], gt, base + 3), (o, layer[5], up, base + 3), (gt, layer[6], dn, base + 4)]
+            prev, xcur = base + 6, dn
+        dchain = ops.GemvChain(dj, validate=False)
+        msd = graph_time(torch, lambda _: dchain.run(), nrep, warm=1, reps=5)
+        gemv["chain_dependent"] = {"ms_per_8_layers": msd, "GBps": gbytes / msd / 1e6, "frac_hbm": gbytes / msd / 1e6 / pk["hbm"],
+                                   "note": "every linear waits for its producer inside the launch (32 dependency points): "
+                                           "the latency of a real decode step, not a bandwidth figure"}
+        del chain, dchain
         ms = graph_time(torch, gemv_all, 1, warm=1, reps=5)
         ach = gbytes / ms / 1e6
         tr, src = ncu_traffic("gemv_mxq_kernel", "gemv_4096x4096")
-        gemv["per_linear"] = {"ms_per_8_layers": ms, "launches": nl * len(shapes),
-                              "roofline": {"bound": "hbm", "kernel": "gemv_mxq_kernel<1> (TMA-ring kernel; the IMMA kernel is opt-in, see imma_kernel below)",
-                                           "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                                           "traffic": tr, "traffic_source": (src or "") + " (per 4096x4096 launch: 6,318,080 algorithmic bytes)",
-                                           "algorithmic_bytes": gbytes}}
+        gemv["per_linear"] = {"ms_per_8_layers": ms, "launches": nl * len(shapes), "GBps": ach, "frac_hbm": ach / pk["hbm"],
+                              "kernel": "gemv_mxq_kernel<1> (TMA-ring kernel, one launch per linear, PDL)",
+                              "traffic": tr, "traffic_source": (src or "") + " (per 4096x4096 launch: 6,318,080 algorithmic bytes)"}
         ms = graph_time(torch, gemv_grouped_all, 1, warm=1, reps=5)
         ach = gbytes / ms / 1e6
         gemv["grouped"] = {"ms_per_8_layers": ms, "launches": nl * 4, "GBps": ach, "frac_hbm": ach / pk["hbm"],
@@ -579,8 +607,7 @@ def run_components(ctx, pk, with_cpu=True):
             m1 = graph_time(torch, gemv_all, 1, warm=1, reps=5)
             m2 = graph_time(torch, gemv_grouped_all, 1, warm=1, reps=5)
             gemv["imma_kernel"] = {"per_linear_GBps": gbytes / m1 / 1e6, "grouped_GBps": gbytes / m2 / 1e6,
-                                   "note": "MXQ_GEMV_IMPL=mma: IMMA m16n8k32 inner products + per-warp cp.async rings; faster on same-shape "
-                                           "chains of 4096-wide linears, slower on this mixed chain (DESIGN.md section 9)"}
+                                   "note": "MXQ_GEMV_IMPL=mma: IMMA m16n8k32 inner products + per-warp cp.async rings, one launch per linear"}
         finally:
             os.environ.pop("MXQ_GEMV_IMPL", None)
     except Exception as e:

@@ -47,6 +47,9 @@ def test_ncu_traffic_lookup_reads_the_committed_capture():
     assert t is not None and "r2_ncu_traffic.csv" in src
     # the capture of the SHIPPED instantiation: <__half, 16, 2>, 128 x 2048 tokens x 4096 channels x 2 B read once
     assert "16, 2" in src and 0.999 < t / (128 * 2048 * 4096 * 2) < 1.01
+    # the persistent decode chain: 32 x 4096^2 jobs of 6,318,080 packed + activation bytes each, read once
+    t, src = bench.ncu_traffic("gemv_chain_kernel", "gemv_chain_32x4096x4096")
+    assert t is not None and 0.99 < t / (32 * 6318080) < 1.06
     assert bench.ncu_traffic("no_such_kernel")[0] is None
     pk = bench.peaks()
     assert pk["hbm"] > 1000 and pk["tf_burst"] > 100 and pk["src"] in ("measured", "fallback")
