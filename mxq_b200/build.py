@@ -63,6 +63,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     common = list(COMMON)
     if os.environ.get("MXQ_DEBUG") == "1":      # watchdog traps + pinned-host records in the GEMM barriers
         common.append("-DMXQ_DEBUG")
+    if os.environ.get("MXQ_CHAIN_TRACE") == "1":  # clock64 stamps in the persistent GEMV chain (profiles/r2_gemv_persistent_trace.py)
+        common.append("-DMXQ_CHAIN_TRACE")
     os.makedirs(OBJ, exist_ok=True)
     jobs = []
     objs = []

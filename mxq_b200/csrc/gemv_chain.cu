@@ -197,14 +197,22 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// Profiling only (MXQ_CHAIN_DBG & 8): clock64 stamps of CTA 1 -- [role][event index][stamp]; roles: compute
-// warp 0, producer A, reducer, builder warp 0
+// Profiling only (built with -DMXQ_CHAIN_TRACE, run with MXQ_CHAIN_DBG & 8): clock64 stamps of CTA 1 --
+// [role][event index][stamp]; roles: compute warp 0, producer A, -, builder warp 0, compute warp 0 per job.
+// Compiled out by default: the predicated stamps sat in the per-tile paths of every warp.
 constexpr int kTraceEvents = 96;
+#ifdef MXQ_CHAIN_TRACE
 __device__ long long g_ctrace[5 * kTraceEvents * 4];
 #define CTRACE(role, idx, k)                                                                       \
   do {                                                                                             \
     if (tr && (idx) < kTraceEvents) g_ctrace[((role) * kTraceEvents + (idx)) * 4 + (k)] = clock64(); \
   } while (0)
+#else
+#define CTRACE(role, idx, k) \
+  do {                       \
+    (void)tr;                \
+  } while (0)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Activation image of one job (one batch row):
@@ -675,6 +683,9 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
       mbar_wait(&bars.imgempty[bsel], ((imgk >> 1) & 1) ^ 1);
       CTRACE(3, imgk, 1);
       if (J.dep >= 0) {
+        // (letting all 12 compute warps build a dependent job's image instead -- they are idle until x exists --
+        // was measured: 303 -> 313 us on the 56-linear decoder chain; the conversion is not what a dependency
+        // point costs, the drain / publish / acquire / refill around it is)
         const int* flag = sync_ws + J.dep;
         const long long t0 = clock64();
         while (ld_acquire(flag) < J.dep_target) {
@@ -889,5 +900,10 @@ extern "C" int mxq_gemv_chain_run(const void* plan_host, const void* plan_dev, i
 
 // profiling aid, not part of the documented surface
 extern "C" __attribute__((visibility("default"))) int mxq_debug_chain_trace(long long* host_out) {
+#ifdef MXQ_CHAIN_TRACE
   return (int)cudaMemcpyFromSymbol(host_out, g3::g_ctrace, sizeof(long long) * 5 * g3::kTraceEvents * 4);
+#else
+  (void)host_out;
+  return MXQ_E_UNSUPPORTED;                        // build with MXQ_CHAIN_TRACE=1 (mxq_b200/build.py)
+#endif
 }

@@ -32,10 +32,11 @@ def _mk(cuda, shapes, seed=0):
 
 def test_chain_independent_mixed_shapes(cuda):
     """Ragged everything: partial 16-row tiles, a short last CTA, 1 / 2 / 3 metadata chunks per row
-    (IC = 256, 4096, 8192, 11008 = 43 quad-blocks), q/k/v-style jobs sharing one activation."""
+    (IC = 256, 4096, 8192, 11008 = 43 quad-blocks), 70B-wide rows (28672 columns: 7 chunks per tile, a
+    3-stage ring), q/k/v-style jobs sharing one activation."""
     from mxq_b200 import ops
     shapes = [(256, 4096), (256, 4096), (256, 4096), (4128, 256), (128, 11008), (32, 256), (1184, 4096), (96, 8192),
-              (4096, 4096), (160, 1024), (11008, 4096), (4096, 11008)]
+              (4096, 4096), (160, 1024), (11008, 4096), (4096, 11008), (64, 28672), (32, 16384)]
     ps, pd = _mk(cuda, shapes)
     xs = {ic: _outlier_x(1, ic, seed=ic) for ic in {s[1] for s in shapes}}
     xd = {ic: torch.from_numpy(x).to(cuda) for ic, x in xs.items()}
