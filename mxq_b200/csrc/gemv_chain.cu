@@ -371,13 +371,17 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
     uint32_t* dst = reinterpret_cast<uint32_t*>(jobs);
     for (int i = threadIdx.x; i < n * (int)(sizeof(JobD) / 4); i += kThreads) dst[i] = src[i];
   }
-  // This CTA's tiles in chain order, one 16-byte record each: the compute warps walk this list instead of
-  // re-deriving their share of every job (the job loop cost a compute warp ~1200 cycles per job).
-  //   x = job | tile << 8 | nrg << 16 | flags << 24 (1: first tile of the job here, 2: the job needs a new image)
-  //   y = first row group of the tile,  z = number of K chunks,  w = image sequence number
+  // This CTA's tiles in chain order.  Pass 1, a thread per job: tiles[tau] = {job | nrg << 16, first row
+  // group, K chunks | first stage-use << 8, image sequence number}.  Pass 2, a thread per tile: the record a
+  // compute warp of set tau % kSets reads for its tile -- what changed since the set's PREVIOUS tile
+  // (tau - kSets) is folded in, so a warp touches one 16-byte record per tile it owns and none for the others
+  // (walking every tile and every job cost a compute warp ~350 instructions per owned tile, half a visit):
+  //   x = job | nrg << 16 | job changed << 24 | images to step through << 25
+  //   y = first row group,  z = K chunks | stages to skip before the tile << 8,  w = image sequence number
   uint4* tiles = reinterpret_cast<uint4*>(jobs + n);
-  int* tcount = reinterpret_cast<int*>(tiles + kMaxTiles);   // [kMaxJobs] tiles per job, then [1] total
-  int* tnew = tcount + kMaxJobs + 1;                         // [kMaxJobs] 1 if the job needs a new image here
+  uint4* recs = tiles + kMaxTiles;
+  int* tcount = reinterpret_cast<int*>(recs + kMaxTiles);    // [kMaxJobs] tiles per job, [1] total, [1] images
+  int* tnew = tcount + kMaxJobs + 2;                         // [kMaxJobs] 1 if the job needs a new image here
   __syncthreads();                                           // the shared-memory job table is complete
   if (threadIdx.x < n) {
     const JobD& J = jobs[threadIdx.x];
@@ -388,9 +392,10 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
   __syncthreads();
   if (threadIdx.x < n) {
     const int j = threadIdx.x;
-    int off = 0, imgk = -1;
+    int off = 0, imgk = -1, use0 = 0;
     for (int k = 0; k < j; ++k) {
       off += tcount[k];
+      use0 += tcount[k] * jobs[k].nch;
       imgk += tnew[k];
     }
     imgk += tnew[j];
@@ -399,11 +404,25 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
     const int T = tcount[j];
     for (int tile = 0; tile < T; ++tile) {
       const int nrg = min(4, sh.qc - tile * 4);
-      const uint32_t flags = tile == 0 ? (J.share ? 1u : 3u) : 0u;
-      tiles[off + tile] = make_uint4((uint32_t)j | ((uint32_t)tile << 8) | ((uint32_t)nrg << 16) | (flags << 24),
-                                     (uint32_t)(sh.grp_base + tile * 4), (uint32_t)J.nch, (uint32_t)imgk);
+      tiles[off + tile] = make_uint4((uint32_t)j | ((uint32_t)nrg << 16), (uint32_t)(sh.grp_base + tile * 4),
+                                     (uint32_t)J.nch | ((uint32_t)(use0 + tile * J.nch) << 8), (uint32_t)imgk);
     }
-    if (j == n - 1) tcount[kMaxJobs] = off + T;
+    if (j == n - 1) {
+      tcount[kMaxJobs] = off + T;
+      tcount[kMaxJobs + 1] = imgk + 1;
+    }
+  }
+  __syncthreads();
+  for (int tau = threadIdx.x; tau < tcount[kMaxJobs]; tau += kThreads) {
+    const uint4 E = tiles[tau];
+    uint32_t jobchg = 1, skip = E.z >> 8, steps = E.w + 1;
+    if (tau >= kSets) {
+      const uint4 Pv = tiles[tau - kSets];
+      jobchg = (Pv.x & 0xFFu) != (E.x & 0xFFu);
+      skip = (E.z >> 8) - ((Pv.z >> 8) + (Pv.z & 0xFFu));
+      steps = E.w - Pv.w;
+    }
+    recs[tau] = make_uint4(E.x | (jobchg << 24) | (steps << 25), E.y, (E.z & 0xFFu) | (skip << 8), E.w);
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&bars.full[s], 2); mbar_init(&bars.empty[s], kSetW); }
@@ -419,9 +438,7 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
     // =========================================== compute ===========================================
     const int g = lane >> 2, t = lane & 3;
     const int set = warp >> 2, qw = warp & 3;
-    int tmod = 0;                                             // tau % kSets
     int nset = 0;                                             // tiles this set has finished
-    int since = 0;                                            // stages skipped since the last observed `full` phase
     const int U = qw * 4 + t;                                 // this thread-column's unit inside a stage
     const int rgl = g >> 1;                                   // row group of this thread's two rows
     const int rowa = rgl * 4 + (g & 1), rowb = rowa + 2;      // tile rows (mma rows g and g + 8)
@@ -437,38 +454,46 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
     const bool sw = (t & 2) != 0;
     const uint32_t lo32 = sw ? 32u : 0u, hi32 = sw ? 0u : 32u;
 
-    int slot = 0, sphase = 0;                                 // ring position
+    // Every set has its OWN ring of D stages (slots set * D ..): all uses of a slot belong to one set, which
+    // waits for every one of them in order -- a parity wait can never be a phase behind.  (A ring shared by
+    // the sets needs waits on stages a set does not own; the producers may refill such a stage before a busy
+    // set has looked, and the parity then answers for the wrong phase: wrong results, later a hang.)
+    const int D = S >= 2 * kSets ? 2 : 1;
+    int kown = 0;                                             // stages this set has consumed
     const bool tr = (dbg & 8) && cta == 1 && warp == 0 && lane == 0;
     int ev = 0;
-    const int ntile = tcount[kMaxJobs];
-    // per-job state, reloaded at the first tile of a job
+    const int ntile = tcount[kMaxJobs], nimg = tcount[kMaxJobs + 1];
+    // per-job state, reloaded when the job changes between two tiles of this set
     const unsigned char* ximg = img;
     const unsigned char* tabI = img;
     const unsigned char* tabF = img;
     __half* yj = nullptr;
-    int nqb = 0, publish = 0, lastimg = -1;
+    int nqb = 0, publish = 0, lastimg = -1, nbcur = 0;
     uint32_t s2pitch = kPS2, s2odd = 0, oWa = 0, oWb = 0, oWLa = 0, oWLb = 0;
-    for (int e = 0; e < ntile; ++e) {
-      const uint4 E = tiles[e];
-      const int j = (int)(E.x & 0xFFu), nrg = (int)((E.x >> 16) & 0xFFu), nch = (int)E.z;
-      const int rg0 = (int)E.y;
-      if (E.x & (1u << 24)) {                                 // first tile of a job
-        CTRACE(4, j, 0);
-        const JobD& J = jobs[j];
-        if (E.x & (2u << 24)) {                               // the job has its own activation image
-          const int imgk = (int)E.w;
-          if (lastimg >= 0) {                                 // done with the previous image
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars.imgempty[lastimg & 1]);
-          }
-          lastimg = imgk;
-          mbar_wait(&bars.imgfull[imgk & 1], (imgk >> 1) & 1);
-          ximg = img + (size_t)(imgk & 1) * ximg_max;
+    // every compute warp passes through EVERY image in order (release the previous one, observe the next
+    // one's barrier phase) whether its set uses it or not: the builders recycle a buffer only when all 12
+    // warps have released it, and a parity wait must not skip a phase
+    auto step_images = [&](int upto) {
+      while (lastimg < upto) {
+        if (lastimg >= 0) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.imgempty[lastimg & 1]);
         }
-        CTRACE(4, j, 2);
-        const int nb = J.ximg_blocks;
-        tabI = ximg + nb * 128;
-        tabF = tabI + nb * 16;
+        ++lastimg;
+        mbar_wait(&bars.imgfull[lastimg & 1], (lastimg >> 1) & 1);
+      }
+    };
+    for (int e = set; e < ntile; e += kSets) {
+      const uint4 E = recs[e];
+      const int j = (int)(E.x & 0xFFu), nrg = (int)((E.x >> 16) & 0xFFu), nch = (int)(E.z & 0xFFu);
+      const int rg0 = (int)E.y;
+      if (E.x >> 25) {                                        // new activation image(s) since this set's last tile
+        step_images((int)E.w);
+        ximg = img + (size_t)(lastimg & 1) * ximg_max;
+      }
+      if (E.x & (1u << 24)) {                                 // another job than this set's last tile
+        const JobD& J = jobs[j];
+        nbcur = J.ximg_blocks;
         nqb = J.nqb;
         publish = J.publish;
         yj = J.y;
@@ -478,33 +503,23 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
         oWb = oWa + 2 * J.pw;
         oWLa = kOffWL + rowa * J.pwl + U * 16;
         oWLb = oWLa + 2 * J.pwl;
-        CTRACE(4, j, 3);
+      }
+      if (E.x & (0xFFu << 24)) {                              // the tables follow the image: job or image changed
+        tabI = ximg + nbcur * 128;
+        tabF = tabI + nbcur * 16;
       }
       {
-        const bool mine = tmod == set;
-        if (++tmod == kSets) tmod = 0;
-        if (!mine) {
-          // Another set's tile: skip its stages -- but a parity wait is only meaningful if the previous
-          // phase of that barrier is known to be complete, so at least one `full` phase in every S
-          // consecutive stages is observed (the producers fill in order: seeing stage u implies all before).
-          for (int ch = 0; ch < nch; ++ch) {
-            if (++since == S) {
-              mbar_wait(&bars.full[slot], sphase);
-              since = 0;
-            }
-            if (++slot == S) { slot = 0; sphase ^= 1; }
-          }
-          continue;
-        }
         float acc0 = 0.f, acc1 = 0.f;
         float s4a = 0.f, s4b = 0.f;
         int z4a = 0, z4b = 0;
         const uint32_t oS2 = kOffS2 + rgl * s2pitch + (((rg0 + rgl) & 1) ? s2odd : 0u) + U * 24;
         for (int ch = 0; ch < nch; ++ch) {
           const int nq = min(16, nqb - ch * 16);
+          const int slot = set * D + (kown & (D - 1));
+          const uint32_t sphase = (uint32_t)(kown >> (D - 1)) & 1u;
+          ++kown;
           CTRACE(0, ev, 0);
           mbar_wait(&bars.full[slot], sphase);
-          since = 0;
           CTRACE(0, ev, 1);
           const unsigned char* s = stages + (size_t)slot * kStageBytes;
           if (ch == 0) {                                      // 4-bit pool scale / zero of this thread's two rows
@@ -565,7 +580,6 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars.empty[slot]);
           CTRACE(0, ev, 2);
-          if (++slot == S) { slot = 0; sphase ^= 1; }
           if (ch + 1 < nch) { CTRACE(0, ev, 3); ++ev; }
         }
         // ---- K partials of the set's 4 warps -> one of them adds in a fixed order and stores y -------
@@ -596,26 +610,62 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
         ++ev;
       }
     }
+    step_images(nimg - 1);                                    // images that only other sets used
   } else if (warp == kProdA || warp == kProdB) {
     // =========================================== producers =========================================
     // A: weight + weight_last boxes.  B: zeros_and_scales + zeros_2nd boxes, scales_2nd, scales_4b, zeros_4b.
+    // Issue order: the tiles of a wave (kSets consecutive tiles, one per set) are filled chunk by chunk in
+    // turn, so a tile of several K chunks -- which only fits its set's ring two chunks at a time -- does not
+    // keep the in-order producer from prefetching the other sets' tiles.
     const bool isA = warp == kProdA;
-    int slot = 0, sphase = 0;
+    const int D = S >= 2 * kSets ? 2 : 1;
+    const int ntile = tcount[kMaxJobs];
+    int kset[kSets];                                          // stages issued per set (unrolled: registers)
+#pragma unroll
+    for (int q = 0; q < kSets; ++q) kset[q] = 0;
     const bool tr = (dbg & 8) && cta == 1 && lane == 0 && isA;
     int ev = 0;
-    for (int j = 0; j < n; ++j) {
-      const JobD& J = P.jobs[j];
-      const Share sh = cta_share(J, cta, ncta);
-      if (!sh.active) continue;
-      const int nblk = J.nblk, nch = J.nch, nqb = J.nqb;
-      const CUtensorMap* mp = maps + (size_t)j * 4;
-      const uint32_t bytesA = 16u * (uint32_t)(J.pw + J.pwl);
-      for (int tile = 0; tile < sh.T; ++tile) {
-        const int nrg = min(4, sh.qc - tile * 4);
-        const int rg0 = sh.grp_base + tile * 4;
-        const int row0 = rg0 * 4;
-        for (int ch = 0; ch < nch; ++ch) {
-          const int nq = min(16, nqb - ch * 16);
+    for (int w0 = 0; w0 < ntile; w0 += kSets) {
+      // the wave's tiles and their jobs, read once (registers: the loops over q are unrolled)
+      int nchq[kSets], nrgq[kSets], rg0q[kSets], nblkq[kSets], nqbq[kSets], s2pq[kSets], ocq[kSets];
+      uint32_t bytesAq[kSets];
+      const unsigned char* S2q[kSets];
+      const unsigned char* S4q[kSets];
+      const unsigned char* Z4q[kSets];
+      const CUtensorMap* mpq[kSets];
+      int maxch = 0;
+#pragma unroll
+      for (int q = 0; q < kSets; ++q) {
+        nchq[q] = 0;
+        if (w0 + q < ntile) {
+          const uint4 E = tiles[w0 + q];
+          const int j = (int)(E.x & 0xFFu);
+          const JobD& J = jobs[j];
+          nchq[q] = (int)(E.z & 0xFFu);
+          nrgq[q] = (int)((E.x >> 16) & 0xFFu);
+          rg0q[q] = (int)E.y;
+          nblkq[q] = J.nblk;
+          nqbq[q] = J.nqb;
+          s2pq[q] = J.s2pitch;
+          ocq[q] = J.oc;
+          bytesAq[q] = 16u * (uint32_t)(J.pw + J.pwl);
+          S2q[q] = J.S2;
+          S4q[q] = J.S4;
+          Z4q[q] = J.Z4;
+          mpq[q] = maps + (size_t)j * 4;
+          maxch = max(maxch, nchq[q]);
+        }
+      }
+      for (int ch = 0; ch < maxch; ++ch) {
+#pragma unroll
+        for (int q = 0; q < kSets; ++q) {
+          if (ch >= nchq[q]) continue;
+          const int nrg = nrgq[q], rg0 = rg0q[q], row0 = rg0 * 4;
+          const int nblk = nblkq[q], nq = min(16, nqbq[q] - ch * 16);
+          const CUtensorMap* mp = mpq[q];
+          const int slot = q * D + (kset[q] & (D - 1));
+          const uint32_t sphase = (uint32_t)(kset[q] >> (D - 1)) & 1u;
+          ++kset[q];
           CTRACE(1, ev, 0);
           mbar_wait(&bars.empty[slot], sphase ^ 1);
           CTRACE(1, ev, 1);
@@ -625,7 +675,7 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
             if (dbg & 2) {
               mbar_arrive(fb);
             } else if (isA) {
-              mbar_arrive_expect_tx(fb, bytesA);
+              mbar_arrive_expect_tx(fb, bytesAq[q]);
               tma_box(s + kOffW, mp + 0, ch * 256, row0, fb);
               tma_box(s + kOffWL, mp + 1, ch * 64, row0, fb);
             } else {
@@ -633,37 +683,36 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
               uint32_t s2bytes;
               const uint32_t piece = (uint32_t)nq * 24;
               const uint32_t odd = (uint32_t)((nblk * 6) & 15);      // 0 or 8
-              if (J.s2pitch) {
-                s2bytes = (uint32_t)nrg * (uint32_t)J.s2pitch;
+              if (s2pq[q]) {
+                s2bytes = (uint32_t)nrg * (uint32_t)s2pq[q];
               } else {
                 s2bytes = 0;
                 for (int r = 0; r < nrg; ++r) s2bytes += (piece + (((rg0 + r) & 1) ? odd : 0u) + 15u) & ~15u;
               }
               // scales_4b / zeros_4b: the 16-byte aligned range around the tile's entries, clipped to the tensor
               const uint32_t s4off = ((uint32_t)rg0 * 8u) & ~15u;
-              const uint32_t s4bytes = min(48u, (uint32_t)J.oc * 2u - s4off);
+              const uint32_t s4bytes = min(48u, (uint32_t)ocq[q] * 2u - s4off);
               const uint32_t z4off = (uint32_t)((row0 >> 3) & ~3) * 4u;
-              const uint32_t z4bytes = min(32u, (uint32_t)(J.oc >> 3) * 4u - z4off);
+              const uint32_t z4bytes = min(32u, (uint32_t)(ocq[q] >> 3) * 4u - z4off);
               mbar_arrive_expect_tx(fb, kBytesBox + s2bytes + s4bytes + z4bytes);
               tma_box(s + kOffZS, mp + 2, ch * 32, row0, fb);
               tma_box(s + kOffZ2, mp + 3, ch * 32, rg0, fb);
-              if (J.s2pitch) {
-                bulk_g2s(s + kOffS2, J.S2 + (size_t)rg0 * (size_t)J.s2pitch, s2bytes, fb);
+              if (s2pq[q]) {
+                bulk_g2s(s + kOffS2, S2q[q] + (size_t)rg0 * (size_t)s2pq[q], s2bytes, fb);
               } else {
                 for (int r = 0; r < nrg; ++r) {
                   const size_t off = (size_t)(rg0 + r) * ((size_t)nblk * 6) + (size_t)ch * 384;
                   const uint32_t sk = ((rg0 + r) & 1) ? odd : 0u;
-                  bulk_g2s(s + kOffS2 + r * kPS2, J.S2 + (off - sk), (piece + sk + 15u) & ~15u, fb);
+                  bulk_g2s(s + kOffS2 + r * kPS2, S2q[q] + (off - sk), (piece + sk + 15u) & ~15u, fb);
                 }
               }
-              bulk_g2s(s + kOffS4, J.S4 + s4off, s4bytes, fb);
-              bulk_g2s(s + kOffZ4, J.Z4 + z4off, z4bytes, fb);
+              bulk_g2s(s + kOffS4, S4q[q] + s4off, s4bytes, fb);
+              bulk_g2s(s + kOffZ4, Z4q[q] + z4off, z4bytes, fb);
             }
           }
           __syncwarp();
           CTRACE(1, ev, 3);
           ++ev;
-          if (++slot == S) { slot = 0; sphase ^= 1; }
         }
       }
     }
@@ -848,11 +897,11 @@ extern "C" int mxq_gemv_chain_plan(const mxq_gemv_job_t* jobs, int n, void* plan
     if (rc) return rc;
   }
   const size_t fixed = 2 * (size_t)ximg_max + g3::kRedBytes + ((sizeof(g3::Bars) + 127) & ~size_t(127)) +
-                       (size_t)n * sizeof(g3::JobD) + (size_t)g3::kMaxTiles * 16 + (2 * g3::kMaxJobs + 1) * 4 + 128;
+                       (size_t)n * sizeof(g3::JobD) + (size_t)g3::kMaxTiles * 32 + (2 * g3::kMaxJobs + 2) * 4 + 128;
   int tiles_max = 0;                                  // 16-row tiles of a CTA with a full share of every job
   for (int j = 0; j < n; ++j) tiles_max += (D[j].q + 3) / 4;
   if (tiles_max > g3::kMaxTiles) return MXQ_E_UNSUPPORTED;
-  if (fixed + 2 * (size_t)g3::kStageBytes > g3::kSmemMax) return MXQ_E_UNSUPPORTED;
+  if (fixed + g3::kSets * (size_t)g3::kStageBytes > g3::kSmemMax) return MXQ_E_UNSUPPORTED;   // one stage per compute set
   int S = (int)((g3::kSmemMax - fixed) / g3::kStageBytes);
   if (S > g3::kMaxStages) S = g3::kMaxStages;
   H.magic = g3::kMagic;
