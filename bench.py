@@ -413,7 +413,8 @@ def run_e2e_nas_quant(ctx, args, job_bytes):
             "h2d_bytes_per_step": int(h_ids.numel() * 8), "d2h_bytes_per_step": int(d2h_layer * n_layers),
             "breakdown_ms_rank0": {"layer_forwards_incl_statistics_hooks": timers.get("forward_ms"),
                                    "fasterquant_and_pack": timers.get("quant_ms"), "results_to_host": d2h_ms,
-                                   "rest (capture, embedding, host driver)": ms - timers.get("forward_ms", 0.0) - timers.get("quant_ms", 0.0) - d2h_ms},
+                                   "calibration_capture (embedding forwards)": timers.get("capture_ms"),
+                                   "rest (host driver gaps)": ms - timers.get("forward_ms", 0.0) - timers.get("quant_ms", 0.0) - d2h_ms - timers.get("capture_ms", 0.0)},
             "wall_s": wall, "layers_this_rank": n_layers, "forward_batch": bsz,
             "api": "mxq_b200.prune.nas_quant(args, model, tokenizer, dev, dataloader=..., batch_size=16) on a random-init "
                    "Llama-2-7B (this rank's layers), args.pack=True; token ids from pinned host memory, fp16 + packed results to pinned host memory",

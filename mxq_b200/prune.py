@@ -23,8 +23,13 @@ def find_layers(module, layers=(nn.Linear,), name=''):
     return res
 
 
+class _StopForward(Exception):
+    """Raised by the statistics hook of the last quantizable linear of a layer in the FIRST forward."""
+
+
 @torch.no_grad()
-def nas_quant(args, model, tokenizer, dev, dataloader=None, batch_size: int = 1, timers: dict | None = None):
+def nas_quant(args, model, tokenizer, dev, dataloader=None, batch_size: int = 1, timers: dict | None = None,
+              early_exit: bool = True):
     """prune.py:326-425: calibration capture (Catcher), per layer: MXQGPT per linear, forward hooks
     feeding add_batch during the layer forwards over all samples, fasterquant (blocksize 16), a
     second forward with the quantized weights, in/out swap.
@@ -34,7 +39,12 @@ def nas_quant(args, model, tokenizer, dev, dataloader=None, batch_size: int = 1,
     reference runs one at a time, :400-402,416-417; statistics and outputs are identical, the dense
     forwards just stop being launch-bound); ``timers`` -- dict that receives the device time of the
     layer forwards (incl. the statistics hooks) and of fasterquant(+pack) in ms; ``args.pack`` --
-    also attach the packed 2/4-bit tensors of every linear as ``module.mxq_packed``."""
+    also attach the packed 2/4-bit tensors of every linear as ``module.mxq_packed``; ``early_exit`` --
+    the outputs of the first forward of a layer are never read (the reference overwrites them with
+    the second forward's, :400-402 vs :416-417), so once the LAST linear of the layer has seen its
+    input (its statistics are taken in a pre-hook) the rest of that forward -- for Llama the
+    down_proj GEMM, 22 % of the layer's linear FLOPs -- is skipped.  Which linear is last is
+    observed on the first batch of every layer class (hook firing order)."""
     print('Starting ...')
     if dataloader is None:
         # the reference downloads wikitext2 here (prune.py:329, lib/data.py: needs the `datasets`
@@ -57,23 +67,12 @@ def nas_quant(args, model, tokenizer, dev, dataloader=None, batch_size: int = 1,
             self.module = module
 
         def forward(self, inp, **kwargs):
-            inps[cache['i']] = inp
-            cache['i'] += 1
+            b = inp.shape[0]
+            inps[cache['i']:cache['i'] + b] = inp
+            cache['i'] += b
             cache['kwargs'] = kwargs
             raise ValueError
 
-    layers[0] = Catcher(layers[0])
-    for batch in dataloader:
-        try:
-            model(batch[0].to(dev))
-        except ValueError:
-            pass
-    layers[0] = layers[0].module
-    torch.cuda.empty_cache()
-    outs = torch.zeros_like(inps)
-    kwargs = {k: v for k, v in cache['kwargs'].items() if k in ("attention_mask", "position_ids", "position_embeddings")}
-    print('Ready.')
-    bs = max(1, int(batch_size))
     marks = []                      # (phase, start event, end event)
 
     def timed(phase):
@@ -84,13 +83,48 @@ def nas_quant(args, model, tokenizer, dev, dataloader=None, batch_size: int = 1,
         a.record()
         return b
 
+    layers[0] = Catcher(layers[0])
+    end_capture = timed("capture")
+    bs = max(1, int(batch_size))
+    # the reference captures one sample per model call (:350-355); with batch_size > 1 (and a sample count it
+    # divides, so that every later layer forward sees the batch shape the captured kwargs were made for) the
+    # embedding / rotary / mask prologue runs once per batch
+    cap = bs if args.nsamples % bs == 0 else 1
+    pend = []
+    for batch in dataloader:
+        pend.append(batch[0].to(dev))
+        if len(pend) < cap:
+            continue
+        try:
+            model(torch.cat(pend, dim=0) if len(pend) > 1 else pend[0])
+        except ValueError:
+            pass
+        pend = []
+    for ids in pend:                                   # a dataloader shorter than announced: one at a time
+        try:
+            model(ids)
+        except ValueError:
+            pass
+    layers[0] = layers[0].module
+    if end_capture is not None:
+        end_capture.record()
+    # (the reference calls torch.cuda.empty_cache() here and after the last layer, prune.py:364,423 -- a
+    # device-wide synchronisation plus cudaFree of every cached block, needed for its 64-460 MB Hessians)
+    outs = torch.zeros_like(inps)
+    kwargs = {k: v for k, v in cache['kwargs'].items() if k in ("attention_mask", "position_ids", "position_embeddings")}
+    print('Ready.')
     def forward_all(layer):
         end = timed("forward")
         for j in range(0, args.nsamples, bs):
-            out = layer(inps[j:j + bs], **kwargs)
+            try:
+                out = layer(inps[j:j + bs], **kwargs)
+            except _StopForward:                       # first forward only: its outputs are never read
+                continue
             outs[j:j + bs] = out[0] if isinstance(out, tuple) else out
         if end is not None:
             end.record()
+
+    last_linear = {}                # layer class -> name of the linear whose hook fires last
 
     for i in range(len(layers)):
         layer = layers[i]
@@ -102,15 +136,31 @@ def nas_quant(args, model, tokenizer, dev, dataloader=None, batch_size: int = 1,
         subset = find_layers(layer)
         gpts = {name: MXQGPT(subset[name]) for name in subset}
 
+        order = []
+
         def add_batch(name):
             def tmp(_, inp, out):
+                order.append(name)
                 gpts[name].add_batch(inp[0].data, out.data)
             return tmp
 
-        handles = [subset[name].register_forward_hook(add_batch(name)) for name in gpts]
+        def add_batch_and_stop(name):
+            def tmp(_, inp):
+                gpts[name].add_batch(inp[0].data)
+                raise _StopForward
+            return tmp
+
+        last = last_linear.get(type(layer)) if early_exit else None
+        if last is not None and last not in gpts:
+            last = None
+        handles = [subset[name].register_forward_hook(add_batch(name)) for name in gpts if name != last]
+        if last is not None:
+            handles.append(subset[last].register_forward_pre_hook(add_batch_and_stop(last)))
         forward_all(layer)
         for h in handles:
             h.remove()
+        if early_exit and last is None and len(order) >= len(gpts) and len(set(order[-len(gpts):])) == len(gpts):
+            last_linear[type(layer)] = order[-1]       # every linear fired once per batch: the last one is known
         end = timed("quant")
         for name in gpts:
             print(i, name)
@@ -127,7 +177,6 @@ def nas_quant(args, model, tokenizer, dev, dataloader=None, batch_size: int = 1,
         inps, outs = outs, inps
 
     model.config.use_cache = use_cache
-    torch.cuda.empty_cache()
     if timers is not None:
         torch.cuda.synchronize()
         for phase, a, b in marks:

@@ -101,6 +101,44 @@ def test_nas_quant_live(cuda, pack, capsys):
     assert torch.isfinite(a).all() and not torch.equal(a, b)
 
 
+def test_nas_quant_early_exit_and_batched_capture_keep_the_statistics(cuda, monkeypatch):
+    """The two extensions that save forward time -- stopping a layer's FIRST forward once its last linear has
+    seen its input, and capturing / forwarding several calibration samples per call -- must leave every
+    linear's calibration statistic (and therefore the quantized model) unchanged."""
+    from mxq_b200 import prune
+    from mxq_b200.mxqgpt import MXQGPT
+    base = tiny_llama(cuda)
+
+    def run(early_exit, batch_size):
+        model = copy.deepcopy(base)
+        stats = []
+        orig = MXQGPT.fasterquant
+
+        def spy(self, *a, **k):
+            stats.append((self.nsamples, self.diagH.clone()))
+            return orig(self, *a, **k)
+        monkeypatch.setattr(MXQGPT, "fasterquant", spy)
+        args = argparse.Namespace(nsamples=NSAMPLES, seed=0, save=None, pack=False)
+        prune.nas_quant(args, model, None, cuda, dataloader=calib(cuda), batch_size=batch_size, early_exit=early_exit)
+        monkeypatch.setattr(MXQGPT, "fasterquant", orig)
+        return stats, snapshot(model)
+
+    ref_stats, ref_w = run(False, 1)
+    assert len(ref_stats) == LAYERS * 7
+    for early_exit, bsz in ((True, 1), (True, NSAMPLES), (False, NSAMPLES)):
+        stats, w = run(early_exit, bsz)
+        assert len(stats) == len(ref_stats)
+        for (n0, d0), (n1, d1) in zip(ref_stats, stats):
+            assert n0 == n1 == NSAMPLES
+            if bsz == 1:
+                assert torch.equal(d0, d1)                                   # same calls, same order
+            else:
+                assert torch.allclose(d0, d1, rtol=2e-3, atol=0) and torch.equal(d0 == 0, d1 == 0)
+        if bsz == 1:
+            for k in ref_w:
+                assert np.array_equal(ref_w[k].view(np.uint16), w[k].view(np.uint16)), k
+
+
 def test_nas_quant_needs_dataloader_offline(cuda):
     from mxq_b200 import prune
     model = tiny_llama(cuda)
