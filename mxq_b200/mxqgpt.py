@@ -68,7 +68,8 @@ class MXQGPT:
         # the zero-initialised diagonal reproduces that
         colstat = self.diagH
         if pack:
-            Wq, self.packed = ops.ptq_quant_pack(W, colstat)
+            # self.packed may hold pre-allocated output tensors (nas_quant carves them from one arena)
+            Wq, self.packed = ops.ptq_quant_pack(W, colstat, packed=self.packed)
         else:
             Wq = ops.ptq_quant(W, colstat, low_bits=2, group=width)
         self.layer.weight.data = Wq.reshape(self.layer.weight.shape).to(self.layer.weight.data.dtype)
