@@ -36,7 +36,7 @@ class _StopForward(Exception):
 
 @torch.no_grad()
 def nas_quant(args, model, tokenizer, dev, dataloader=None, batch_size: int = 1, timers: dict | None = None,
-              early_exit: bool = True):
+              early_exit: bool = True, layer_callback=None):
     """prune.py:326-425: calibration capture (Catcher), per layer: MXQGPT per linear, forward hooks
     feeding add_batch during the layer forwards over all samples, fasterquant (blocksize 16), a
     second forward with the quantized weights, in/out swap.
@@ -51,7 +51,10 @@ def nas_quant(args, model, tokenizer, dev, dataloader=None, batch_size: int = 1,
     the second forward's, :400-402 vs :416-417), so once the LAST linear of the layer has seen its
     input (its statistics are taken in a pre-hook) the rest of that forward -- for Llama the
     down_proj GEMM, 22 % of the layer's linear FLOPs -- is skipped.  Which linear is last is
-    observed on the first batch of every layer class (hook firing order)."""
+    observed on the first batch of every layer class (hook firing order); ``layer_callback(i, layer)``
+    -- called right after layer i's linears are quantized (their weights / ``mxq_packed`` are final),
+    before its second forward: a caller that streams the results out (device -> host, disk) can overlap
+    that with the remaining forwards."""
     print('Starting ...')
     if dataloader is None:
         # the reference downloads wikitext2 here (prune.py:329, lib/data.py: needs the `datasets`
@@ -201,6 +204,8 @@ def nas_quant(args, model, tokenizer, dev, dataloader=None, batch_size: int = 1,
             gpts[name].free()
         if end is not None:
             end.record()
+        if layer_callback is not None:
+            layer_callback(i, layer)
         forward_all(layer)
         layers[i] = layer
         inps, outs = outs, inps
