@@ -64,7 +64,7 @@ MXQ_API int mxq_fakequant_fwd(const void* x, void* out, uint8_t* codes, int64_t 
  *  - pooled_mask (optional, uint8[cols / group]): only the POOL flag (0x80) is read -- WHICH groups share
  *    the row's 4-bit statistic (mxq_allocate_bits); every other group is `low_bits` wide.  NULL = the
  *    positional recipe.  Exactly the arithmetic of mxq_fakequant_fwd (bit-identical outputs).
- *  group 16 or 128; rows of at most 3072 16-byte chunks; 16-bit dtypes with low_bits == 2. */
+ *  group 16 or 128; rows of at most 6144 16-byte chunks; 16-bit dtypes with low_bits == 2. */
 MXQ_API int mxq_fakequant_fwd_multi(const void* const* x, void* const* out, const int64_t* rows, int n, int64_t cols,
                                     int dtype, int group, int low_bits, const uint8_t* pooled_mask, void* stream);
 

@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kFQThreads) fakequant_fwd_kernel(const FQParam
 // row, the row's 16-byte chunks stay in registers between the pooled min/max and the quantize
 // pass, so the kernel is a single load -> reduce -> compute -> store stream with nothing staged
 // in shared memory but the per-warp partial statistics.  Measured faster than the TMA ring above
-// on B200 for rows of up to 3072 chunks (profiles/): more independent loads in flight per SM and
+// on B200 for rows of up to 3072 chunks (profiles/; 512-thread instantiations carry 70B rows of up to 6144 chunks): more independent loads in flight per SM and
 // no per-stage block barrier.
 // -------------------------------------------------------------------------------------------
 // Up to kFQMaxTensors weights of the same row length in ONE launch (QAT quantizes q/k/v/o, then gate/up,
@@ -478,6 +478,9 @@ static bool launch_fq_row_tab(const FQRowTable& tab, int c, int low_bits, cudaSt
   else if (c <= 1536) fakequant_row_kernel<T, 256, 6, G, kMask><<<g, 256, 0, st>>>(tab, c, low_bits);
   else if (c <= 2048) fakequant_row_kernel<T, 256, 8, G, kMask><<<g, 256, 0, st>>>(tab, c, low_bits);
   else if (c <= 3072) fakequant_row_kernel<T, 256, 12, G, kMask><<<g, 256, 0, st>>>(tab, c, low_bits);
+  // 70B rows (down_proj: 28672 columns = 3584 bf16 chunks) on 512 threads
+  else if (c <= 4096) fakequant_row_kernel<T, 512, 8, G, kMask><<<g, 512, 0, st>>>(tab, c, low_bits);
+  else if (c <= 6144) fakequant_row_kernel<T, 512, 12, G, kMask><<<g, 512, 0, st>>>(tab, c, low_bits);
   else return false;
   return true;
 }
@@ -652,7 +655,7 @@ extern "C" int mxq_fakequant_fwd(const void* x, void* out, uint8_t* codes, int64
   if (grid > p.num_sets) grid = p.num_sets;
   cudaStream_t st = as_stream(stream);
   const bool ref = group_bits == nullptr;
-  // reference recipe at group 16 without code output: the row-resident kernel (rows of up to 3072
+  // reference recipe at group 16 without code output: the row-resident kernel (rows of up to 6144
   // chunks; the packed 16-bit arithmetic exists for 2-bit groups only).  MXQ_FQ_RING forces the ring.
   // The same kernel instantiated for groups of 128 columns serves BASELINE's "group 128" (the
   // positional recipe over 512-column blocks): bit-identical to the mask-driven ring kernel on B200
@@ -660,7 +663,7 @@ extern "C" int mxq_fakequant_fwd(const void* x, void* out, uint8_t* codes, int64
   // 4096^2 fp32 / bf16 weight.  MXQ_FQ_ROW_G128=0 restores the ring.
   const char* e128 = getenv("MXQ_FQ_ROW_G128");
   const bool row16 = group == 16, row128 = group == 128 && !(e128 && atoi(e128) == 0);
-  if (ref && (row16 || row128) && !codes && p.cpr <= 3072 && rows >= kNumSMs && (esize == 4 || low_bits == 2) &&
+  if (ref && (row16 || row128) && !codes && p.cpr <= 6144 && rows >= kNumSMs && (esize == 4 || low_bits == 2) &&
       !getenv("MXQ_FQ_RING")) {
     bool ok = false;
     switch (dtype) {
@@ -690,7 +693,7 @@ extern "C" int mxq_fakequant_fwd_multi(const void* const* x, void* const* out, c
   if ((group != 16 && group != 128) || cols % (4 * group) || cols > (1 << 24)) return MXQ_E_SHAPE;
   if (low_bits < 1 || low_bits > 8 || (esize == 2 && low_bits != 2)) return MXQ_E_UNSUPPORTED;
   const int cpr = (int)(cols * esize / 16);
-  if (cpr > 3072) return MXQ_E_UNSUPPORTED;      // longer rows: mxq_fakequant_fwd (shared-memory ring)
+  if (cpr > 6144) return MXQ_E_UNSUPPORTED;      // longer rows: mxq_fakequant_fwd (shared-memory ring)
   cudaStream_t st = as_stream(stream);
   for (int i0 = 0; i0 < n; i0 += kFQMaxTensors) {
     FQRowTable tab{};

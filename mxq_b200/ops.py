@@ -35,7 +35,7 @@ def fakequant_fwd(x: torch.Tensor, num_bits: int = 2, group: int = 16, group_bit
     x = x.contiguous()
     rows, cols = x.shape
     if uniform_low and group_bits is not None and not return_codes and group in (16, 128) and cols % (4 * group) == 0 \
-            and cols * x.element_size() <= 3072 * 16 and (x.element_size() == 4 or num_bits == 2):
+            and cols * x.element_size() <= 6144 * 16 and (x.element_size() == 4 or num_bits == 2):
         return fakequant_fwd_multi([x], num_bits, group, pooled_mask=group_bits)[0]
     if cols % 64 and group_bits is None and group == 16:
         # the reference itself fails here: W_4b has K/64*16 columns (utils_quant.py:347,368)

@@ -38,7 +38,8 @@ def test_golden_forward_backward(cuda, fq):
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16", "fp16"])
-@pytest.mark.parametrize("shape", [(160, 11008), (200, 8192), (256, 4096), (150, 1536), (1000, 256), (148, 64)])
+@pytest.mark.parametrize("shape", [(160, 11008), (200, 8192), (256, 4096), (150, 1536), (1000, 256), (148, 64),
+                                   (150, 28672), (152, 16384)])     # 70B rows: the 512-thread instantiations
 def test_row_kernel_vs_oracle_and_ring(cuda, dtype, shape, monkeypatch):
     """rows >= 148 without code output take the row-resident kernel (every chunks-per-thread
     variant); it must equal the oracle and the TMA-ring kernel (MXQ_FQ_RING) bit for bit."""
