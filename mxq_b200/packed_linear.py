@@ -8,6 +8,7 @@ consumer of the packed 2/4-bit layout is the raw ``gemv_mxq_forward_cuda`` bindi
                        decode-sized inputs to the GEMV kernel and prefill-sized ones to the
                        tcgen05 dequant-GEMM
   pack_linear          nn.Linear (fp16) -> MXQLinear, optionally with the calibration statistic
+  decode_chain         several batch-1 MXQLinear calls as ONE persistent launch (ops.GemvChain)
   convert_model        swap every nn.Linear that nas_quant(args.pack=True) annotated
   save_packed / load_packed   the packed tensors of a converted model, as one torch file
 
@@ -119,6 +120,26 @@ def pack_linear(linear: nn.Linear, colstat: torch.Tensor | None = None, importan
     W = W.half()
     perm = ops.importance_permutation(ops.allocate_group_bits(W, colstat)) if importance else None
     return MXQLinear.from_packed(ops.pack(W, colstat, group_perm=perm), group_perm=perm)
+
+
+def decode_chain(jobs: list) -> "ops.GemvChain":
+    """Batch-1 decode of several packed linears as ONE persistent launch (csrc/gemv_chain.cu).
+
+    jobs: list of (MXQLinear, x, y, dep) -- x fp16 [in_features] (or [1, in_features]) and y fp16
+    [out_features] are buffers the caller keeps and refills between runs; dep = -1 if x exists when the
+    chain is launched, or the index of an earlier job whose y this x is (or is computed from by an earlier
+    job).  q/k/v (one x), gate/up (one x), the experts of an MoE layer or the same linear of several
+    sequences are the natural lists; a list may also chain linears on each other's outputs.  Returns the
+    chain; ``chain.run()`` launches it on the current stream (capturable in a CUDA graph).  Linears with
+    an importance permutation (``group_perm``) are not supported here: call them directly."""
+    out = []
+    for lin, x, y, dep in jobs:
+        if not isinstance(lin, MXQLinear):
+            raise TypeError("decode_chain takes MXQLinear modules")
+        if lin.group_perm is not None:
+            raise ValueError("decode_chain: linears with group_perm run through MXQLinear.forward")
+        out.append((x, lin.packed, y, dep))
+    return ops.GemvChain(out)
 
 
 def convert_model(model: nn.Module) -> nn.Module:

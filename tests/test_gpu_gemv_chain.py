@@ -106,6 +106,33 @@ def test_chain_dependent_jobs(cuda):
             _check(vals[i + 1], vals[i][None, :], p, f"rep {rep} link {i}")
 
 
+def test_chain_extreme_activations(cuda):
+    """The block-floating conversion at its edges: an all-zero vector, fp16-max groups next to zero and
+    subnormal-only groups, one non-zero element per group, negative zeros."""
+    from mxq_b200 import ops
+    ps, pd = _mk(cuda, [(256, 4096)], seed=21)
+    rng = np.random.default_rng(5)
+    xs = []
+    x = np.zeros((1, 4096), np.float16); xs.append(x)
+    x = np.zeros((1, 4096), np.float16); x[0, :16] = 65504.0; x[0, 16:32] = -65504.0; x[0, 48:64] = 6e-8; x[0, 64] = -0.0
+    xs.append(x)
+    x = np.zeros((1, 4096), np.float16); x[0, ::16] = rng.standard_normal(256).astype(np.float16); xs.append(x)
+    x = (rng.standard_normal((1, 4096)) * 1e-6).astype(np.float16); xs.append(x)          # subnormal range only
+    x = np.full((1, 4096), 3.0, np.float16); xs.append(x)
+    # keep |y| inside fp16 for the fp16-max case: small scales
+    for k in ("scales_2nd", "scales_4b"):
+        ps[0][k] = (ps[0][k].astype(np.float32) * 1e-3).astype(np.float16)
+        pd[0][k].copy_(torch.from_numpy(ps[0][k]))
+    xd = [torch.from_numpy(x).to(cuda) for x in xs]
+    ys = [torch.full((256,), float("nan"), dtype=torch.float16, device=cuda) for _ in xs]
+    ops.GemvChain([(a, pd[0], y, -1) for a, y in zip(xd, ys)]).run()
+    torch.cuda.synchronize()
+    assert torch.equal(ys[0], torch.zeros_like(ys[0]))
+    for i, (x, y) in enumerate(zip(xs, ys)):
+        assert torch.isfinite(y).all(), i
+        _check(y.cpu().numpy(), x, ps[0], f"case {i}")
+
+
 def test_chain_longer_than_one_launch(cuda):
     from mxq_b200 import ops
     from mxq_b200 import _lib as L

@@ -126,3 +126,27 @@ def test_importance_allocation_folded_into_the_packed_path(cuda):
     assert torch.equal(fresh[0].group_perm, m.group_perm)
     x1 = torch.randn(1, IC, device=cuda).half()
     assert torch.equal(fresh[0](x1), m(x1))
+
+
+def test_decode_chain_matches_module_forward(cuda):
+    """q/k/v sharing one activation plus an o_proj that reads q's output, as ONE launch: same numbers as the
+    modules called one by one (both kernels add exact integer group sums; the fp32 summation order differs)."""
+    from mxq_b200.packed_linear import decode_chain, pack_linear
+    torch.manual_seed(3)
+    lins = [pack_linear(torch.nn.Linear(512, 256, bias=False).half().to(cuda)) for _ in range(3)]
+    o = pack_linear(torch.nn.Linear(256, 512, bias=False).half().to(cuda))
+    x = torch.randn(512, device=cuda).half()
+    ys = [torch.zeros(256, dtype=torch.float16, device=cuda) for _ in range(3)]
+    yo = torch.zeros(512, dtype=torch.float16, device=cuda)
+    chain = decode_chain([(lins[0], x, ys[0], -1), (lins[1], x, ys[1], -1), (lins[2], x, ys[2], -1), (o, ys[0], yo, 0)])
+    for _ in range(2):                                   # buffers are refilled between runs
+        x.copy_(torch.randn(512, device=cuda).half())
+        chain.run()
+        torch.cuda.synchronize()
+        for lin, y in zip(lins, ys):
+            want = lin(x[None, :])[0].float()
+            assert torch.allclose(y.float(), want, rtol=2e-3, atol=2e-3 * float(want.abs().max()))
+        want = o(ys[0][None, :])[0].float()
+        assert torch.allclose(yo.float(), want, rtol=2e-3, atol=2e-3 * float(want.abs().max()))
+    with pytest.raises(TypeError):
+        decode_chain([(torch.nn.Linear(4, 4), x, ys[0], -1)])
