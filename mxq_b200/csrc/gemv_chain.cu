@@ -88,7 +88,7 @@ struct JobD {                                 // 128 bytes
   const __half* x;
   __half* y;
   int nblk, nch, nqb, ngrp;
-  int q, gxl, rot, dep;
+  int tbase, trem, rot, dep;                   // 16-row tiles per CTA: tbase, +1 on the first trem slices
   int share, dep_target, publish, s2pitch;    // s2pitch: 0 = one copy per row group (pitch kPS2, skewed)
   int oc, ximg_blocks, pw, pwl;               // pw / pwl: row pitch of the weight / weight_last boxes
   int pad[6];
@@ -278,9 +278,15 @@ __device__ __forceinline__ Share cta_share(const JobD& J, int cta, int ncta) {
   Share s;
   int slice = cta + J.rot;
   if (slice >= ncta) slice -= ncta;
-  s.active = slice < J.gxl;
-  s.grp_base = slice * J.q;
-  s.qc = min(J.q, J.ngrp - s.grp_base);
+  // whole 16-row tiles only (OC % 32 == 0): slice s owns tbase (+1 if s < trem) consecutive tiles.  Cutting the
+  // rows into equal ROW-GROUP shares instead (7 row groups = a full and a three-quarter tile for 4096 rows on
+  // 148 CTAs) spent 13 % of the mma work on padding rows; the uneven tile counts even out over the jobs of
+  // a chain because `rot` moves the heavier slices on by trem every job.
+  const int cnt = J.tbase + (slice < J.trem ? 1 : 0);
+  const int start = slice * J.tbase + min(slice, J.trem);
+  s.active = cnt > 0;
+  s.grp_base = start * 4;
+  s.qc = cnt * 4;
   s.T = (s.qc + 3) >> 2;
   return s;
 }
@@ -862,14 +868,11 @@ extern "C" int mxq_gemv_chain_plan(const mxq_gemv_job_t* jobs, int n, void* plan
     d.nqb = d.nblk / 4;
     d.ngrp = (int)(a.OC / 4);
     d.oc = (int)a.OC;
-    d.q = (int)ceil_div(d.ngrp, ncta);
-    d.gxl = (int)ceil_div(d.ngrp, d.q);
+    const int t_total = d.ngrp / 4;                  // 16-row tiles (OC % 32 == 0: every tile is full)
+    d.tbase = t_total / ncta;
+    d.trem = t_total % ncta;
     d.dep = a.dep;
-    if (a.dep >= 0) {                                // number of 16-row tiles of that job over all CTAs
-      const g3::JobD& pj = D[a.dep];
-      const int qlast = pj.ngrp - (pj.gxl - 1) * pj.q;
-      d.dep_target = (pj.gxl - 1) * ((pj.q + 3) / 4) + (qlast + 3) / 4;
-    }
+    d.dep_target = a.dep >= 0 ? D[a.dep].ngrp / 4 : 0;     // number of 16-row tiles of that job over all CTAs
     if (a.dep >= 0) {
       coop = 1;
       D[a.dep].publish = 1;
@@ -882,11 +885,11 @@ extern "C" int mxq_gemv_chain_plan(const mxq_gemv_job_t* jobs, int n, void* plan
     d.pwl = bwl * 4;
     // jobs that read the same x with the same shape share one activation image and one CTA assignment
     d.share = j > 0 && jobs[j - 1].x == a.x && jobs[j - 1].IC == a.IC && jobs[j - 1].OC == a.OC && jobs[j - 1].dep == a.dep;
-    if (d.share) {
-      d.rot = D[j - 1].rot;
-    } else {
-      d.rot = (ncta - next) % ncta;                 // active CTAs of this job: next .. next + gxl - 1 (mod ncta)
-      next = (next + d.gxl) % ncta;
+    if (d.share && d.tbase == 0) {
+      d.rot = D[j - 1].rot;                         // fewer tiles than CTAs: the same CTAs as the image's owner
+    } else {                                        // (with tbase >= 1 every CTA is active under any rotation)
+      d.rot = (ncta - next) % ncta;                 // slice 0 of this job = CTA `next`
+      next = (next + d.trem) % ncta;                // the slices with an extra tile move on
     }
     const int ximg = d.ximg_blocks * 160;
     if (ximg > ximg_max) ximg_max = ximg;
@@ -899,7 +902,7 @@ extern "C" int mxq_gemv_chain_plan(const mxq_gemv_job_t* jobs, int n, void* plan
   const size_t fixed = 2 * (size_t)ximg_max + g3::kRedBytes + ((sizeof(g3::Bars) + 127) & ~size_t(127)) +
                        (size_t)n * sizeof(g3::JobD) + (size_t)g3::kMaxTiles * 32 + (2 * g3::kMaxJobs + 2) * 4 + 128;
   int tiles_max = 0;                                  // 16-row tiles of a CTA with a full share of every job
-  for (int j = 0; j < n; ++j) tiles_max += (D[j].q + 3) / 4;
+  for (int j = 0; j < n; ++j) tiles_max += D[j].tbase + (D[j].trem ? 1 : 0);
   if (tiles_max > g3::kMaxTiles) return MXQ_E_UNSUPPORTED;
   if (fixed + g3::kSets * (size_t)g3::kStageBytes > g3::kSmemMax) return MXQ_E_UNSUPPORTED;   // one stage per compute set
   int S = (int)((g3::kSmemMax - fixed) / g3::kStageBytes);
