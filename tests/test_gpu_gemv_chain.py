@@ -133,6 +133,55 @@ def test_chain_extreme_activations(cuda):
         _check(y.cpu().numpy(), x, ps[0], f"case {i}")
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_chain_random_dependency_graphs(cuda, seed):
+    """Random DAGs over mixed shapes: a job reads either a fresh vector or the output of a random earlier job
+    of the right width; siblings that read the same producer share its image; some producers are tiny (fewer
+    tiles than CTAs, so most CTAs never publish them).  Every job is checked against the oracle applied to the
+    input it actually read."""
+    from mxq_b200 import ops
+    rng = np.random.default_rng(100 + seed)
+    widths = [256, 1024, 4096]
+    n = 28
+    shapes, deps = [], []
+    for j in range(n):
+        cands = [i for i in range(j) if True]
+        if j > 0 and rng.random() < 0.7:
+            d = int(rng.choice(cands))
+            ic = shapes[d][0]
+        else:
+            d, ic = -1, int(rng.choice(widths))
+        oc = int(rng.choice(widths + [32, 160]))
+        if oc not in widths:                      # odd widths cannot feed another job
+            pass
+        shapes.append((oc, ic))
+        deps.append(d)
+    # producers must have a width another job can read: re-draw consumers of odd-width producers as fresh inputs
+    for j in range(n):
+        if deps[j] >= 0 and shapes[deps[j]][0] % 256:
+            deps[j] = -1
+            shapes[j] = (shapes[j][0], int(rng.choice(widths)))
+    ps, pd = _mk(cuda, shapes, seed=300 + seed)
+    for p, q in zip(ps, pd):                      # keep chains of several links inside fp16
+        for k in ("scales_2nd", "scales_4b"):
+            p[k] = (p[k].astype(np.float32) * 0.15).astype(np.float16)
+            q[k].copy_(torch.from_numpy(p[k]))
+    fresh = {w: torch.from_numpy(_outlier_x(1, w, seed=w + seed)[0]).to(cuda) for w in widths}
+    ys = [torch.zeros(oc, dtype=torch.float16, device=cuda) for oc, _ in shapes]
+    jobs = [((ys[deps[j]] if deps[j] >= 0 else fresh[shapes[j][1]]), pd[j], ys[j], deps[j]) for j in range(n)]
+    chain = ops.GemvChain(jobs)
+    for rep in range(2):
+        for y in ys:
+            y.fill_(float("nan"))
+        chain.run()
+        torch.cuda.synchronize()
+        vals = [y.cpu().numpy() for y in ys]
+        for j in range(n):
+            xin = vals[deps[j]] if deps[j] >= 0 else fresh[shapes[j][1]].cpu().numpy()
+            assert np.isfinite(vals[j]).all(), (rep, j)
+            _check(vals[j], xin[None, :], ps[j], f"seed {seed} rep {rep} job {j} dep {deps[j]} {shapes[j]}")
+
+
 def test_chain_longer_than_one_launch(cuda):
     from mxq_b200 import ops
     from mxq_b200 import _lib as L
