@@ -8,18 +8,24 @@
 // so per-linear launches cannot exceed ~0.45 of the HBM rate.  Here the weight stream never stops at a
 // linear boundary:
 //
-//   * one CTA per SM, 16 warps: 8 compute warps, 2 producers, 1 reducer, 5 activation-image builders;
-//   * the producers stream the CTA's rows of ALL jobs back to back through a ring of shared-memory
-//     stages.  One stage = one 16-row tile x one K chunk of <= 4096 columns of every packed tensor
-//     (25 KB) and costs 7-10 TMA operations: weight / weight_last / zeros_and_scales / zeros_2nd arrive
-//     as 2-D tensor-map boxes (cp.async.bulk.tensor; rows beyond the tensor and columns beyond the row
-//     are zero-filled, so every box has the same byte count), scales_2nd / scales_4b / zeros_4b -- whose
-//     pieces are only 8-byte aligned in the reference layout -- as 1-D bulk copies of the enclosing
-//     16-byte aligned range (the consumer adds the skew).  An earlier version issued one bulk copy per
-//     row (52 per stage): a UBLKCP costs its warp 60-100 cycles, the stage took 2.9 us;
-//   * compute warp w = (set, q): the two sets alternate 16-row tiles, so the two compute warps of a
-//     scheduler are out of phase (one reduces / waits while the other multiplies); warp q of a set owns
-//     the four 256-column units 4q .. 4q+3 of every stage of its tiles.  Thread (g, t) of the warp
+//   * one CTA per SM, 16 warps: 12 compute warps (3 sets of 4), 2 producers, 2 activation-image builders;
+//   * a job's rows are cut into whole 16-row tiles, tbase (+1 on the first trem slices) per CTA; the heavier
+//     slices rotate by trem per job so that the counts even out over a chain (equal row-group shares put a
+//     full and a three-quarter tile on every CTA for 4096 rows: 13 % of the mma work on padding).  A
+//     prologue turns the job list into one 16-byte record per tile of this CTA;
+//   * the producers stream the CTA's tiles of ALL jobs back to back into shared-memory stages.  One stage =
+//     one tile x one K chunk of <= 4096 columns of every packed tensor (25 KB) and costs 7-10 TMA operations:
+//     weight / weight_last / zeros_and_scales / zeros_2nd arrive as 2-D tensor-map boxes
+//     (cp.async.bulk.tensor; rows beyond the tensor and columns beyond the row are zero-filled, so every box
+//     has the same byte count), scales_2nd / scales_4b / zeros_4b -- whose pieces are only 8-byte aligned in
+//     the reference layout -- as 1-D bulk copies of the enclosing 16-byte aligned range (the consumer adds the
+//     skew).  An earlier version issued one bulk copy per row (52 per stage): a UBLKCP costs its warp 60-100
+//     cycles, the stage took 2.9 us;
+//   * compute set s owns the tiles tau % 3 == s and a private ring of two stages -- every use of a slot
+//     belongs to one set, which waits for all of them in order, so a parity wait can never be a phase behind
+//     (a ring shared by the sets was tried first: waits on foreign stages are racy, see the kernel); the three
+//     warps of a scheduler are out of phase (one reduces / waits while the others multiply).  Warp q of a set
+//     owns the four 256-column units 4q .. 4q+3 of every stage of its tiles.  Thread (g, t) of the warp
 //     multiplies two rows of one second-order row group with the four consecutive 64-column blocks of
 //     unit 4q + t: all its metadata for the visit comes from ONE 16-byte load per tensor and row.
 //     Inner products on mma.sync.m16n8k32 (IMMA.16832.U8.S8) as in csrc/gemv_mma.cu (the quad's thread
@@ -28,9 +34,9 @@
 //     code c of a byte is masked in place at bits 7:6 after a multiply by 4^(3-c) (IMAD on the FMA pipe
 //     instead of SHF on the half-rate ALU pipe), i.e. all codes enter the mma as 64 * q, and the factor
 //     2^-6 (2^-4 for the 4-bit nibbles) is folded into the activation image's group scales;
-//   * the 4 K-partials of a tile go through a shared-memory exchange (4 tiles deep) to the reducer warp,
-//     which adds them in a fixed order (deterministic), stores y and, if a later job depends on this one,
-//     publishes the CTA's share with a release increment of the job's counter;
+//   * the 4 K-partials of a tile meet in shared memory behind a named barrier of the set; one of the four
+//     warps adds them in a fixed order (deterministic), stores y and, if a later job depends on this one,
+//     counts the tile in the job's global counter with a release increment;
 //   * the builders convert x_j into the block-floating image of job j+1 while job j computes.  A job
 //     may name an earlier job `dep` whose y it reads as x (a real dependent chain): the builders then
 //     wait for the counter of `dep` (acquire) -- the weight stream of the waiting job is already in
