@@ -938,7 +938,9 @@ extern "C" int mxq_gemv_chain_run(const void* plan_host, const void* plan_dev, i
   e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return (int)e;
   if (sms < H.ncta) return MXQ_E_UNSUPPORTED;       // the plan assumes one resident CTA per B200 SM
-  e = cudaFuncSetAttribute(g3::gemv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H.smem);
+  // one opt-in limit for every chain (the largest a plan can ask for): concurrent callers with different
+  // plans never lower each other's limit between this call and their launch
+  e = cudaFuncSetAttribute(g3::gemv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g3::kSmemMax);
   if (e != cudaSuccess) return (int)e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)H.ncta);
