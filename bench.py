@@ -16,8 +16,9 @@ back to the host, the calibration activations produced on the device by the laye
 `components` carries the other BASELINE configs measured in the same run, each with its own
 `roofline` (achieved / peak / frac / ncu traffic), `cpu_baseline` and `e2e`:
   configs[0] fake-quant forward + STE backward (fp32, bf16, "group 128")         -- rank 0
-  configs[2] decode GEMV (+ the reference's own kernel and cuBLAS fp16 on the same box) and
-             prefill dequant-GEMM at M = 2048                                    -- rank 0
+  configs[2] decode GEMV: the 56 linears of 8 layers as ONE persistent launch (mxq_gemv_chain; the roofline),
+             with decoder dependencies inside the launch, per-linear / grouped launches, the reference's own
+             kernel and cuBLAS fp16 on the same box; prefill dequant-GEMM at M = 2048      -- rank 0
   configs[3] one LLM-QAT `2 32 32` step, data parallel (NCCL all-reduce) over all ranks
   configs[4] Llama-2-70B-shape dequant-GEMM, output columns sharded over all ranks, exchanged by
              NCCL all-gather / fused peer stores / fused NVSwitch multicast stores
