@@ -131,7 +131,7 @@ struct Bars {
 // four issue slots from the working warp of a scheduler (every traced step ran ~4x slower than alone).
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
-  int spins = 0;
+  long long t0 = 0;
   uint32_t ns = 0;
   do {
     asm volatile(
@@ -142,7 +142,11 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
         : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)          // up to 1 ms per attempt
         : "memory");
     if (!ok) {
-      if (++spins > 4000000) __trap();                           // seconds: a missing arrive / copy, not a slow peer
+      // a barrier that does not complete for ~10 s is a missing arrive / copy, not a slow peer: trap instead
+      // of wedging the GPU (time-slicing or a debugger pause cannot reach that on a healthy launch)
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000LL) __trap();
       if (kWaitBackoff) {                                        // back off: a polling warp takes issue slots
         ns = ns < 128u ? ns + 32u : 128u;
         __nanosleep(ns);
