@@ -29,9 +29,10 @@ def main():
     ps = [rand_packed(oc, ic) for _ in range(n)]
     yy = [torch.empty(oc, device=dev, dtype=torch.float16) for _ in range(n)]
     xs = [torch.randn(ic, device=dev).half() for _ in range(n)]
+    dep = os.environ.get("TRACE_DEP") == "1"       # job i reads the output of job i - 1 (square shapes only)
     for dbg in ([int(a) for a in sys.argv[3:]] or (8, 9, 10, 15)):
         os.environ["MXQ_CHAIN_DBG"] = str(dbg)
-        c = ops.GemvChain([(xs[i], p, y, -1) for i, (p, y) in enumerate(zip(ps, yy))], validate=False)
+        c = ops.GemvChain([((yy[i - 1] if dep and i else xs[i]), p, y, (i - 1 if dep else -1)) for i, (p, y) in enumerate(zip(ps, yy))], validate=False)
         for _ in range(3):
             c.run()
         torch.cuda.synchronize()
