@@ -844,8 +844,7 @@ extern "C" int mxq_gemv_chain_plan(const mxq_gemv_job_t* jobs, int n, void* plan
   if (!jobs || !plan_host) return MXQ_E_NULL;
   if (reinterpret_cast<uintptr_t>(plan_host) & 63) return MXQ_E_ALIGN;
   if (n <= 0 || n > g3::kMaxJobs) return MXQ_E_SHAPE;
-  g3::EncodeTiledFn enc = g3::get_encode();
-  if (!enc) return MXQ_E_UNSUPPORTED;
+  g3::EncodeTiledFn enc = nullptr;                 // looked up after the first job has passed validation
   memset(plan_host, 0, g3::kPlanBytes);
   g3::ChainParams* P = reinterpret_cast<g3::ChainParams*>(plan_host);
   CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(reinterpret_cast<unsigned char*>(plan_host) + g3::kMapsOffset);
@@ -903,6 +902,10 @@ extern "C" int mxq_gemv_chain_plan(const mxq_gemv_job_t* jobs, int n, void* plan
     }
     const int ximg = d.ximg_blocks * 160;
     if (ximg > ximg_max) ximg_max = ximg;
+    if (!enc) {
+      enc = g3::get_encode();
+      if (!enc) return MXQ_E_UNSUPPORTED;             // no driver (CPU-only host): cuTensorMapEncodeTiled is unavailable
+    }
     int rc = g3::make_map(enc, maps + j * 4 + 0, w.weight, a.OC, (int64_t)d.nblk * 4, 16, bw);
     if (!rc) rc = g3::make_map(enc, maps + j * 4 + 1, w.weight_last, a.OC, d.nblk, 16, bwl);
     if (!rc) rc = g3::make_map(enc, maps + j * 4 + 2, w.zeros_and_scales, a.OC, (int64_t)d.nch * 32, 16, 32);

@@ -52,6 +52,25 @@ def test_argument_errors_without_gpu():
     assert L.mxq_gemv(p16, pk, p16, 1, 100, 64, None) == -2
     assert L.mxq_pack(p16, None, 8, 64, pk, p16, 4096, None) == -2                            # OC % 16
     assert L.mxq_awq_gemv(p16, p16, p16, p16, p16, 1, 128, 8, 48, None) == -5
+    # persistent decode chain: the plan is host code; every argument error is reported before a driver is needed
+    nplan = L.mxq_gemv_chain_plan_bytes()
+    assert nplan > 64 * 128
+    plan = (C.c_char * (nplan + 64))()
+    pp = (C.addressof(plan) + 63) & ~63
+    job = _lib.GemvJobC(p16, p16, pk, 4096, 4096, -1, 0)
+    jobs = (_lib.GemvJobC * 2)(job, job)
+    assert L.mxq_gemv_chain_plan(None, 1, pp) == -1
+    assert L.mxq_gemv_chain_plan(jobs, 1, pp + 8) == -4                                       # plan not 64-byte aligned
+    assert L.mxq_gemv_chain_plan(jobs, 0, pp) == -2 and L.mxq_gemv_chain_plan(jobs, 65, pp) == -2
+    jobs[0].IC = 4096 + 64                                                                    # IC % 256
+    assert L.mxq_gemv_chain_plan(jobs, 1, pp) == -5
+    jobs[0].IC, jobs[0].OC = 4096, 4096 + 8                                                   # OC % 32
+    assert L.mxq_gemv_chain_plan(jobs, 1, pp) == -5
+    jobs[0].OC, jobs[1].dep = 4096, 1                                                         # dep must name an EARLIER job
+    assert L.mxq_gemv_chain_plan(jobs, 2, pp) in (-2, -5)                                     # (-5 first on a host without a driver)
+    jobs[0].x = None
+    assert L.mxq_gemv_chain_plan(jobs, 1, pp) == -1
+    assert L.mxq_gemv_chain_run(None, pp, pp, 0, None) == -1
     assert L.mxq_ptq_workspace_bytes(4096, 4096) >= 4096 + 4096 * 8
     assert L.mxq_colsumsq_workspace_bytes(262144, 4096) > 0
 
