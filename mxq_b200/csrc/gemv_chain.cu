@@ -629,7 +629,8 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
     step_images(nimg - 1);                                    // images that only other sets used
   } else if (warp == kProdA || warp == kProdB) {
     // =========================================== producers =========================================
-    // A: weight + weight_last boxes.  B: zeros_and_scales + zeros_2nd boxes, scales_2nd, scales_4b, zeros_4b.
+    // A: the four tensor-map boxes (weight, weight_last, zeros_and_scales, zeros_2nd).  B: the 1-D bulk copies with
+    // their address arithmetic (scales_2nd, scales_4b, zeros_4b).
     // Issue order: the tiles of a wave (kSets consecutive tiles, one per set) are filled chunk by chunk in
     // turn, so a tile of several K chunks -- which only fits its set's ring two chunks at a time -- does not
     // keep the in-order producer from prefetching the other sets' tiles.
@@ -691,9 +692,11 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
             if (dbg & 2) {
               mbar_arrive(fb);
             } else if (isA) {
-              mbar_arrive_expect_tx(fb, bytesAq[q]);
+              mbar_arrive_expect_tx(fb, bytesAq[q] + kBytesBox);
               tma_box(s + kOffW, mp + 0, ch * 256, row0, fb);
               tma_box(s + kOffWL, mp + 1, ch * 64, row0, fb);
+              tma_box(s + kOffZS, mp + 2, ch * 32, row0, fb);
+              tma_box(s + kOffZ2, mp + 3, ch * 32, rg0, fb);
             } else {
               // scales_2nd: row group r's piece starts at (rg0 + r) * nblk * 6 + ch * 384 (8-byte aligned)
               uint32_t s2bytes;
@@ -710,9 +713,7 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
               const uint32_t s4bytes = min(48u, (uint32_t)ocq[q] * 2u - s4off);
               const uint32_t z4off = (uint32_t)((row0 >> 3) & ~3) * 4u;
               const uint32_t z4bytes = min(32u, (uint32_t)(ocq[q] >> 3) * 4u - z4off);
-              mbar_arrive_expect_tx(fb, kBytesBox + s2bytes + s4bytes + z4bytes);
-              tma_box(s + kOffZS, mp + 2, ch * 32, row0, fb);
-              tma_box(s + kOffZ2, mp + 3, ch * 32, rg0, fb);
+              mbar_arrive_expect_tx(fb, s2bytes + s4bytes + z4bytes);
               if (s2pq[q]) {
                 bulk_g2s(s + kOffS2, S2q[q] + (size_t)rg0 * (size_t)s2pq[q], s2bytes, fb);
               } else {
