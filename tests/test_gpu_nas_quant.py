@@ -139,6 +139,29 @@ def test_nas_quant_early_exit_and_batched_capture_keep_the_statistics(cuda, monk
                 assert np.array_equal(ref_w[k].view(np.uint16), w[k].view(np.uint16)), k
 
 
+def test_nas_quant_layer_callback_sees_final_weights(cuda):
+    """layer_callback(i, layer) fires once per layer, after its linears were replaced and (args.pack) annotated,
+    before the layer's second forward: what a caller needs to stream results out under the remaining forwards."""
+    from mxq_b200 import prune
+    model = tiny_llama(cuda)
+    originals = snapshot(model)
+    seen = []
+
+    def cb(i, layer):
+        lins = prune.find_layers(layer)
+        assert all(hasattr(m, "mxq_packed") for m in lins.values())
+        seen.append((i, {n: m.weight.data.clone() for n, m in lins.items()}))
+
+    args = argparse.Namespace(nsamples=NSAMPLES, seed=0, save=None, pack=True)
+    prune.nas_quant(args, model, None, cuda, dataloader=calib(cuda), batch_size=2, layer_callback=cb)
+    assert [i for i, _ in seen] == list(range(LAYERS))
+    for i, ws in seen:
+        for n, w in ws.items():
+            assert torch.equal(w, prune.find_layers(model.model.layers[i])[n].weight.data)
+            assert not np.array_equal(w.cpu().numpy(), originals[(i, n)])
+    check_model(model, originals, True)
+
+
 def test_nas_quant_needs_dataloader_offline(cuda):
     from mxq_b200 import prune
     model = tiny_llama(cuda)
