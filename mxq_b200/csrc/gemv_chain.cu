@@ -208,7 +208,8 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // Profiling only (built with -DMXQ_CHAIN_TRACE, run with MXQ_CHAIN_DBG & 8): clock64 stamps of CTA 1 --
-// [role][event index][stamp]; roles: compute warp 0, producer A, -, builder warp 0, compute warp 0 per job.
+// [role][event index][stamp]; roles: compute warp 0, producer A, (globaltimer at entry / exit of EVERY CTA,
+// two per CTA: profiles/r2_gemv_chain_spread.py), builder warp 0, compute warp 0 per job.
 // Compiled out by default: the predicated stamps sat in the per-tile paths of every warp.
 constexpr int kTraceEvents = 96;
 #ifdef MXQ_CHAIN_TRACE
@@ -217,7 +218,18 @@ __device__ long long g_ctrace[5 * kTraceEvents * 4];
   do {                                                                                             \
     if (tr && (idx) < kTraceEvents) g_ctrace[((role) * kTraceEvents + (idx)) * 4 + (k)] = clock64(); \
   } while (0)
+#define CTRACE_CTA(k)                                                                              \
+  do {                                                                                             \
+    if ((dbg & 8) && threadIdx.x == 0 && cta * 2 + (k) < kTraceEvents * 4) {                       \
+      long long t_;                                                                                \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                       \
+      g_ctrace[2 * kTraceEvents * 4 + cta * 2 + (k)] = t_;                                         \
+    }                                                                                              \
+  } while (0)
 #else
+#define CTRACE_CTA(k) \
+  do {                \
+  } while (0)
 #define CTRACE(role, idx, k) \
   do {                       \
     (void)tr;                \
@@ -374,6 +386,7 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cta = blockIdx.x;
 
+  CTRACE_CTA(0);
   unsigned char* stages = smem;
   unsigned char* img = stages + (size_t)S * kStageBytes;
   float* red = reinterpret_cast<float*>(img + 2 * (size_t)ximg_max);
@@ -797,6 +810,7 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
 
   // ---- the last CTA out re-arms the counters (graph replays pass the same arguments) --------------
   __syncthreads();
+  CTRACE_CTA(1);
   if (threadIdx.x == 0) {
     __threadfence();
     const int ticket = atomicAdd(sync_ws + kMaxJobs, 1);
