@@ -588,14 +588,19 @@ def run_components(ctx, pk, with_cpu=True):
         jobs = [(xl[li][xkey[i]], layer[i], ych[li][i], -1) for li, layer in enumerate(packs) for i in range(len(shapes))]
         chain = ops.GemvChain(jobs, validate=False)
         nrep = 4        # several chain launches per graph: one launch per graph would time the replay overhead (~8 us)
-        ms = graph_time(torch, lambda _: chain.run(), nrep, warm=1, reps=5)
+        ms0 = graph_time(torch, lambda _: chain.run(), nrep, warm=1, reps=5)
+        # back-to-back decode steps: MXQ_GEMV_CHAIN_PDL lets a launch build its tile lists and prefetch weights while
+        # the previous launch's CTAs are still leaving (they leave up to 10 us apart); x is read after it has completed
+        ms = graph_time(torch, lambda _: chain.run(pdl=True), nrep, warm=1, reps=5)
         ach = gbytes / ms / 1e6
         tr, src = ncu_traffic("gemv_chain_kernel", "gemv_chain_32x4096x4096")
         gemv["roofline"] = {"bound": "hbm", "kernel": "gemv_chain_kernel (persistent: TMA stage ring + IMMA m16n8k32, csrc/gemv_chain.cu)",
                             "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                             "traffic": tr, "traffic_source": (src or "") + " (32 x 4096x4096 jobs in one launch: 202,178,560 algorithmic bytes)",
                             "algorithmic_bytes": gbytes, "ms_per_8_layers": ms, "launches": 1,
-                            "note": "independent jobs: the weight-stream rate of one launch over 56 linears"}
+                            "ms_per_8_layers_without_pdl": ms0, "GBps_without_pdl": gbytes / ms0 / 1e6,
+                            "note": "independent jobs: the weight-stream rate of one launch over 56 linears, launches back to back "
+                                    "(4 per graph replay) with programmatic dependent launch; the same without it beside"}
         # the same 56 linears as a DEPENDENT chain: q/k/v <- x, o <- q, gate/up <- o, down <- gate, next layer <- down
         dj, prev, xcur = [], -1, xl[0]["attn"]
         for li, layer in enumerate(packs):

@@ -220,8 +220,16 @@ MXQ_API int mxq_gemv_grouped(const void* x, const mxq_packed_t* w, void* const* 
  *                         from there).  Needs a current CUDA context (cuTensorMapEncodeTiled).
  *   mxq_gemv_chain_run    launches the chain.  sync_ws: device int32[MXQ_GEMV_CHAIN_SYNC_WORDS], zeroed ONCE
  *                         by the caller; the kernel re-arms it at exit (graph replays need no memset).
- *                         Chains with dependencies are launched cooperatively (all CTAs co-resident). */
+ *                         Chains with dependencies are launched cooperatively (all CTAs co-resident).
+ *                         flags: MXQ_GEMV_CHAIN_PDL -- programmatic dependent launch for chains without
+ *                         dependencies: the kernel builds its tile lists and prefetches packed weights while
+ *                         the PREVIOUS kernel of the stream is still draining (its CTAs leave the SMs one by
+ *                         one), and waits for that kernel before it reads an activation vector or writes an
+ *                         output.  Contract: the previous kernel does not write this chain's packed weights
+ *                         or its plan.  A preceding chain launch lets its successor in at once; any other
+ *                         kernel is waited for as usual. */
 #define MXQ_GEMV_CHAIN_MAX_JOBS 64
+#define MXQ_GEMV_CHAIN_PDL 1u
 #define MXQ_GEMV_CHAIN_SYNC_WORDS (MXQ_GEMV_CHAIN_MAX_JOBS + 1)
 typedef struct {
   const void* x;      /* fp16 [IC] */

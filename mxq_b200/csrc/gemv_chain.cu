@@ -97,7 +97,8 @@ struct JobD {                                 // 128 bytes
   int tbase, trem, rot, dep;                   // 16-row tiles per CTA: tbase, +1 on the first trem slices
   int share, dep_target, publish, s2pitch;    // s2pitch: 0 = one copy per row group (pitch kPS2, skewed)
   int oc, ximg_blocks, pw, pwl;               // pw / pwl: row pitch of the weight / weight_last boxes
-  int pad[6];
+  int imgk, imgoff, imgwait;                  // activation image: sequence number, byte offset in the image pool,
+  int pad[3];                                 // image that has to be released before this one is built (-1: none)
 };
 static_assert(sizeof(JobD) == 128, "JobD");
 
@@ -121,9 +122,11 @@ static_assert(sizeof(ChainParams) <= 32000, "kernel parameter space");
 constexpr size_t kMapsOffset = (sizeof(ChainParams) + 127) & ~size_t(127);
 constexpr size_t kPlanBytes = kMapsOffset + (size_t)kMaxJobs * 4 * sizeof(CUtensorMap);
 
+constexpr int kImgBars = 8;                   // activation images in flight (barrier k % 8 belongs to image k)
+
 struct Bars {
   uint64_t full[kMaxStages], empty[kMaxStages];
-  uint64_t imgfull[2], imgempty[2];
+  uint64_t imgfull[kImgBars], imgempty[kImgBars];
 };
 
 // Blocking wait with a suspend-time hint: the warp sleeps in hardware until the phase completes instead of
@@ -387,6 +390,11 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
   const int cta = blockIdx.x;
 
   CTRACE_CTA(0);
+  // Programmatic dependent launch (mxq_gemv_chain_run flag MXQ_GEMV_CHAIN_PDL): the NEXT kernel of the stream may
+  // start as soon as every CTA of this one has got here -- its CTAs take over an SM the moment this kernel's CTA
+  // leaves it (the CTAs of a chain leave up to 10 us apart), build their tile lists and fill their stage rings
+  // with weights, and wait for this grid only where they first read an activation vector (the builders below).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   unsigned char* stages = smem;
   unsigned char* img = stages + (size_t)S * kStageBytes;
   float* red = reinterpret_cast<float*>(img + 2 * (size_t)ximg_max);
@@ -410,25 +418,22 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
   uint4* tiles = reinterpret_cast<uint4*>(jobs + n);
   uint4* recs = tiles + kMaxTiles;
   int* tcount = reinterpret_cast<int*>(recs + kMaxTiles);    // [kMaxJobs] tiles per job, [1] total, [1] images
-  int* tnew = tcount + kMaxJobs + 2;                         // [kMaxJobs] 1 if the job needs a new image here
   __syncthreads();                                           // the shared-memory job table is complete
   if (threadIdx.x < n) {
     const JobD& J = jobs[threadIdx.x];
     const Share sh = cta_share(J, cta, ncta);
     tcount[threadIdx.x] = sh.active ? sh.T : 0;
-    tnew[threadIdx.x] = (sh.active && !J.share) ? 1 : 0;
   }
   __syncthreads();
   if (threadIdx.x < n) {
     const int j = threadIdx.x;
-    int off = 0, imgk = -1, use0 = 0;
+    int off = 0, use0 = 0;
     for (int k = 0; k < j; ++k) {
       off += tcount[k];
       use0 += tcount[k] * jobs[k].nch;
-      imgk += tnew[k];
     }
-    imgk += tnew[j];
     const JobD& J = jobs[j];
+    const int imgk = J.imgk;
     const Share sh = cta_share(J, cta, ncta);
     const int T = tcount[j];
     for (int tile = 0; tile < T; ++tile) {
@@ -455,7 +460,7 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&bars.full[s], 2); mbar_init(&bars.empty[s], kSetW); }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kImgBars; ++b) {
       mbar_init(&bars.imgfull[b], kBW);
       mbar_init(&bars.imgempty[b], kCW);
     }
@@ -506,22 +511,20 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
       while (lastimg < upto) {
         if (lastimg >= 0) {
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bars.imgempty[lastimg & 1]);
+          if (lane == 0) mbar_arrive(&bars.imgempty[lastimg & (kImgBars - 1)]);
         }
         ++lastimg;
-        mbar_wait(&bars.imgfull[lastimg & 1], (lastimg >> 1) & 1);
+        mbar_wait(&bars.imgfull[lastimg & (kImgBars - 1)], (lastimg >> 3) & 1);
       }
     };
     for (int e = set; e < ntile; e += kSets) {
       const uint4 E = recs[e];
       const int j = (int)(E.x & 0xFFu), nrg = (int)((E.x >> 16) & 0xFFu), nch = (int)(E.z & 0xFFu);
       const int rg0 = (int)E.y;
-      if (E.x >> 25) {                                        // new activation image(s) since this set's last tile
-        step_images((int)E.w);
-        ximg = img + (size_t)(lastimg & 1) * ximg_max;
-      }
+      if (E.x >> 25) step_images((int)E.w);                   // new activation image(s) since this set's last tile
       if (E.x & (1u << 24)) {                                 // another job than this set's last tile
         const JobD& J = jobs[j];
+        ximg = img + J.imgoff;
         nbcur = J.ximg_blocks;
         nqb = J.nqb;
         publish = J.publish;
@@ -749,17 +752,24 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
   } else {
     // =========================================== image builders ====================================
     // a thread converts one 64-column block (4 groups) per round
+    // Images live in a pool of 2 * ximg_max bytes; the plan gives every image its offset (ring allocation, an
+    // image is never split) and the last earlier image whose bytes or barrier it reuses.  With the 30 KB
+    // pool half a 11008-column vector needs, three 4096-column images fit beside it: the builders run up to
+    // three images ahead.  (Two fixed buffers let them start the gate/up image only when the last set had
+    // left the q/k/v image, i.e. during the 1-2 tiles of o_proj: 1 us per layer on the 56-linear chain.)
+    // Every CTA builds every image, also those of jobs it has no tile of (numbering is global).
     const int bt = (warp - kBuilder0) * 32 + lane;
-    int imgk = -1;
     const bool tr = (dbg & 8) && cta == 1 && bt == 0;
+    // Everything before this point read kernel parameters, the plan and packed weights only.  The activations
+    // (and the counters, the outputs) may belong to the previous kernel of the stream: wait until it has
+    // completed.  No compute warp gets past its first image, no counter is touched, before the builders have.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int j = 0; j < n; ++j) {
       const JobD& J = jobs[j];
-      const Share sh = cta_share(J, cta, ncta);
-      if (!sh.active || J.share) continue;
-      ++imgk;
-      const int bsel = imgk & 1;
+      if (J.share) continue;
+      const int imgk = J.imgk, bsel = imgk & (kImgBars - 1);
       CTRACE(3, imgk, 0);
-      mbar_wait(&bars.imgempty[bsel], ((imgk >> 1) & 1) ^ 1);
+      if (J.imgwait >= 0) mbar_wait(&bars.imgempty[J.imgwait & (kImgBars - 1)], (uint32_t)(J.imgwait >> 3) & 1u);
       CTRACE(3, imgk, 1);
       if (J.dep >= 0) {
         // (letting all 12 compute warps build a dependent job's image instead -- they are idle until x exists --
@@ -772,7 +782,7 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
           if (clock64() - t0 > 40000000000LL) __trap();
         }
       }
-      unsigned char* xi = img + (size_t)bsel * ximg_max;
+      unsigned char* xi = img + J.imgoff;
       const int nb = J.ximg_blocks, nblk = J.nblk;
       int* tI = reinterpret_cast<int*>(xi + (size_t)nb * 128);
       float* tF = reinterpret_cast<float*>(xi + (size_t)nb * 144);
@@ -848,6 +858,61 @@ static int make_map(EncodeTiledFn enc, CUtensorMap* map, const void* ptr, int64_
   return r == CUDA_SUCCESS ? MXQ_OK : MXQ_E_UNSUPPORTED;
 }
 
+// Where the activation images live.  Two fixed buffers (image k in buffer k % 2) let the builders start image
+// k + 1 when the last compute warp has left image k - 1, i.e. while the CTA works on the jobs of image k: fine
+// as long as those take longer than the conversion.  o_proj between q/k/v and gate/up does not (1-2 tiles per
+// CTA against 1.2-2.3 us for a 4096-column image): the sets waited ~1 us per layer for the gate/up image
+// (161.0 us for bench.py's 56-linear chain).  Such chains get a ring allocation in the same 2 * ximg_max bytes
+// (an image is never split; three 4096-column images fit beside a 11008-column one) with the builders up to
+// two images ahead: 155.2 us.  Chains that do not need it keep the two buffers -- running ahead there cost
+// 1.3 % (151.9 -> 153.8 us with one activation vector per q/k/v/o group), as does running further ahead
+// (three images: 157.0 us).  Images are released in order, so image k waits for the LAST earlier image that
+// overlaps it, and never runs more than `ahead` images in front.  MXQ_CHAIN_IMGPOOL (profiling): 0 = two
+// buffers, n = ring with n images ahead.
+static void place_images(JobD* D, int n, int ncta, int ximg_max) {
+  const int pool = 2 * ximg_max;
+  int first[kMaxJobs], nimg = 0;                      // first job of every image
+  double visits[kMaxJobs];                            // chunk visits per CTA on the jobs of an image
+  for (int j = 0; j < n; ++j) {
+    if (!D[j].share) {
+      first[nimg] = j;
+      visits[nimg++] = 0.0;
+    }
+    visits[nimg - 1] += (double)(D[j].ngrp / 4) * D[j].nch / ncta;
+  }
+  int ahead = 1;
+  for (int k = 0; k + 1 < nimg; ++k)                  // conversion of image k + 1: ~2 visits per 4096 columns
+    if (visits[k] < 2.0 + 1.5 * D[first[k + 1]].nch) ahead = 2;
+  if (const char* e = getenv("MXQ_CHAIN_IMGPOOL")) ahead = atoi(e) > 0 ? atoi(e) : 1;
+  if (ahead > kImgBars - 1) ahead = kImgBars - 1;
+  int off[kMaxJobs], len[kMaxJobs], wait[kMaxJobs];
+  bool ring = ahead > 1;
+  if (ring) {
+    int cursor = 0;
+    for (int k = 0; k < nimg && ring; ++k) {
+      len[k] = D[first[k]].ximg_blocks * 160;
+      if (cursor + len[k] > pool) cursor = 0;
+      off[k] = cursor;
+      cursor += len[k];
+      wait[k] = k - ahead - 1;
+      for (int m = k - 1; m > wait[k] && m >= 0; --m)
+        if (off[m] < off[k] + len[k] && off[k] < off[m] + len[m]) {
+          wait[k] = m;
+          break;
+        }
+      if (k > 0 && wait[k] == k - 1) ring = false;    // fragmented: image k could not be built beside k - 1
+    }
+  }
+  for (int k = 0; k < nimg && !ring; ++k) {
+    off[k] = (k & 1) * ximg_max;
+    wait[k] = k - 2;
+  }
+  for (int j = 0; j < n; ++j) {
+    D[j].imgoff = off[D[j].imgk];
+    D[j].imgwait = wait[D[j].imgk] < 0 ? -1 : wait[D[j].imgk];
+  }
+}
+
 }  // namespace g3
 }  // namespace mxq
 
@@ -866,7 +931,7 @@ extern "C" int mxq_gemv_chain_plan(const mxq_gemv_job_t* jobs, int n, void* plan
   g3::PlanH& H = P->H;
   g3::JobD* D = P->jobs;
   const int ncta = kNumSMs;
-  int ximg_max = 0, coop = 0, next = 0;
+  int ximg_max = 0, coop = 0, next = 0, nimg = 0;
   for (int j = 0; j < n; ++j) {
     const mxq_gemv_job_t& a = jobs[j];
     const mxq_packed_t& w = a.w;
@@ -917,6 +982,7 @@ extern "C" int mxq_gemv_chain_plan(const mxq_gemv_job_t* jobs, int n, void* plan
     }
     const int ximg = d.ximg_blocks * 160;
     if (ximg > ximg_max) ximg_max = ximg;
+    d.imgk = d.share ? D[j - 1].imgk : nimg++;         // images are numbered over the chain, not per CTA
     if (!enc) {
       enc = g3::get_encode();
       if (!enc) return MXQ_E_UNSUPPORTED;             // no driver (CPU-only host): cuTensorMapEncodeTiled is unavailable
@@ -927,6 +993,7 @@ extern "C" int mxq_gemv_chain_plan(const mxq_gemv_job_t* jobs, int n, void* plan
     if (!rc) rc = g3::make_map(enc, maps + j * 4 + 3, w.zeros_2nd, a.OC / 4, (int64_t)d.nch * 32, 4, 32);
     if (rc) return rc;
   }
+  g3::place_images(D, n, ncta, ximg_max);
   const size_t fixed = 2 * (size_t)ximg_max + g3::kRedBytes + ((sizeof(g3::Bars) + 127) & ~size_t(127)) +
                        (size_t)n * sizeof(g3::JobD) + (size_t)g3::kMaxTiles * 32 + (2 * g3::kMaxJobs + 2) * 4 + 128;
   int tiles_max = 0;                                  // 16-row tiles of a CTA with a full share of every job
@@ -948,7 +1015,6 @@ extern "C" int mxq_gemv_chain_plan(const mxq_gemv_job_t* jobs, int n, void* plan
 
 extern "C" int mxq_gemv_chain_run(const void* plan_host, const void* plan_dev, int32_t* sync_ws, unsigned flags,
                                   void* stream) {
-  (void)flags;
   if (!plan_host || !plan_dev || !sync_ws) return MXQ_E_NULL;
   if (reinterpret_cast<uintptr_t>(plan_dev) & 63) return MXQ_E_ALIGN;
   const g3::ChainParams& P = *reinterpret_cast<const g3::ChainParams*>(plan_host);
@@ -970,10 +1036,16 @@ extern "C" int mxq_gemv_chain_run(const void* plan_host, const void* plan_dev, i
   cfg.dynamicSmemBytes = (size_t)H.smem;
   cfg.stream = as_stream(stream);
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = H.coop ? 1 : 0;
+  if (H.coop) {                                     // all CTAs co-resident; no overlap with the previous kernel
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.numAttrs = 1;
+  } else if (flags & MXQ_GEMV_CHAIN_PDL) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 1;
+  }
   const CUtensorMap* maps =
       reinterpret_cast<const CUtensorMap*>(reinterpret_cast<const unsigned char*>(plan_dev) + g3::kMapsOffset);
   e = cudaLaunchKernelEx(&cfg, g3::gemv_chain_kernel, P, maps, reinterpret_cast<int*>(sync_ws), 4, 16, 64, 256);

@@ -462,11 +462,14 @@ class GemvChain:
         self.device = dev
         self.n = len(jobs)
 
-    def run(self):
+    def run(self, pdl: bool = False):
+        """pdl=True (MXQ_GEMV_CHAIN_PDL, chains without dependencies): the launch overlaps the tail of the
+        previous kernel of the stream with its own set-up and weight prefetch; only for callers whose previous
+        kernel does not write this chain's packed weights (a decode loop: the previous step's chain)."""
         lib = L.lib()
         with L.on(self._launches[0][2]) as st:
             for host, plan_dev, sync in self._launches:
-                rc = lib.mxq_gemv_chain_run(host.data_ptr(), plan_dev.data_ptr(), sync.data_ptr(), 0, st)
+                rc = lib.mxq_gemv_chain_run(host.data_ptr(), plan_dev.data_ptr(), sync.data_ptr(), 1 if pdl else 0, st)
                 L.check(rc, "mxq_gemv_chain_run")
 
 

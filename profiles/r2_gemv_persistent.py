@@ -68,8 +68,30 @@ def main():
     jobs = [(xin[ic], p, y, -1) for layer, yl in zip(packs, ys) for (oc, ic), p, y in zip(shapes, layer, yl)]
     chain = ops.GemvChain(jobs, validate=False)
     report("persistent chain, 56 independent jobs (1 launch)", graph_time(chain.run))
+    for pdl in (False, True):                           # back-to-back launches: MXQ_GEMV_CHAIN_PDL overlaps tail and set-up
+        report(f"  4 launches per graph, pdl={pdl} (per launch)", graph_time(lambda: [chain.run(pdl=pdl) for _ in range(4)]) / 4)
+    # bench.py's layout: four activation vectors per layer (q/k/v | o | gate/up | down), distinct per layer
+    xl = [[torch.randn(ic, device=dev).half() for ic in (4096, 4096, 4096, 11008)] for _ in range(nl)]
+    xk = [0, 0, 0, 1, 2, 2, 3]
+    jobs4 = [(xl[li][xk[i]], p, y, -1) for li, (layer, yl) in enumerate(zip(packs, ys)) for i, (p, y) in enumerate(zip(layer, yl))]
+    chain4 = ops.GemvChain(jobs4, validate=False)
+    for pdl in (False, True):
+        report(f"  32 activation vectors, 4 launches per graph, pdl={pdl}", graph_time(lambda: [chain4.run(pdl=pdl) for _ in range(4)]) / 4)
+    del chain4
+    # A/B on the same box: images in two fixed buffers (the plan before the image pool)
+    for mode in ("0", "2", "3"):
+        os.environ["MXQ_CHAIN_IMGPOOL"] = mode
+        c3, c4 = ops.GemvChain(jobs, validate=False), ops.GemvChain(jobs4, validate=False)
+        os.environ.pop("MXQ_CHAIN_IMGPOOL")
+        for name, c in (("3 vectors per layer", c3), ("32 activation vectors", c4)):
+            report(f"  IMGPOOL={mode} (0 = two buffers, n = n images ahead), {name}, pdl=True", graph_time(lambda: [c.run(pdl=True) for _ in range(4)]) / 4)
+        del c3, c4
     for k in (1, 2, 4):
         sub = ops.GemvChain(jobs[:7 * k], validate=False)
+        if k == 1:
+            for pdl in (False, True):
+                report(f"  7 jobs, 8 launches per graph, pdl={pdl} (per launch)",
+                       graph_time(lambda: [sub.run(pdl=pdl) for _ in range(8)]) / 8, gbytes // nl)
         report(f"persistent chain, {7 * k} jobs ({k} layer(s))", graph_time(sub.run), gbytes * k // nl)
 
     # a real decoder dependency structure: q/k/v <- x; o <- q; gate/up <- o; down <- gate; next layer <- down

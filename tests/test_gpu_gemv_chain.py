@@ -210,3 +210,53 @@ def test_chain_rejects_unsupported_shapes(cuda):
     ps, pd = _mk(cuda, [(40, 256)])                       # OC % 32 != 0
     with pytest.raises(RuntimeError):
         ops.GemvChain([(x[:256], pd[0], torch.zeros(40, dtype=torch.float16, device=cuda), -1)])
+
+
+def test_chain_pdl_waits_for_the_previous_kernel(cuda):
+    """MXQ_GEMV_CHAIN_PDL: a launch may start while the previous kernel of the stream is still running, but
+    it must not read an activation vector before that kernel has completed.  Chain B reads what chain A
+    writes (two launches, no in-chain dependency), chain A reads a vector that a copy kernel has just
+    rewritten; eager back-to-back launches and a captured graph replayed with new inputs must both equal
+    the unoverlapped result bit for bit."""
+    from mxq_b200 import ops
+    ic, mid, oc = 4096, 4096, 11008
+    ps, pd = _mk(cuda, [(mid, ic), (mid, ic), (oc, mid), (oc, mid)], seed=11)
+    x = torch.zeros(ic, dtype=torch.float16, device=cuda)
+    xs = [torch.from_numpy(_outlier_x(1, ic, seed=40 + i)[0] * 0.05).to(cuda) for i in range(3)]
+    h = [torch.zeros(mid, dtype=torch.float16, device=cuda) for _ in range(2)]
+    y = [torch.zeros(oc, dtype=torch.float16, device=cuda) for _ in range(2)]
+    A = ops.GemvChain([(x, pd[0], h[0], -1), (x, pd[1], h[1], -1)])
+    B = ops.GemvChain([(h[0], pd[2], y[0], -1), (h[1], pd[3], y[1], -1)])
+
+    def step(xi, pdl):
+        x.copy_(xi)
+        A.run(pdl=pdl)
+        B.run(pdl=pdl)
+
+    want = []
+    for xi in xs:
+        step(xi, False)
+        torch.cuda.synchronize()
+        want.append([t.clone() for t in h + y])
+    for xi, w in zip(xs, want):                       # eager, overlapped
+        step(xi, True)
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(h + y, w))
+    xin = torch.zeros_like(x)
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        step(xin, True)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(3):                        # chain -> chain -> copy -> chain ... programmatic edges
+                step(xin, True)
+    for xi, w in zip(xs, want):
+        xin.copy_(xi)
+        for t in h + y:
+            t.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(h + y, w))
+    _check(want[0][2].cpu().numpy(), want[0][0].cpu().numpy()[None], ps[2], "B[0] on A[0]'s output")
