@@ -46,6 +46,7 @@ class GemvJobC(C.Structure):
 
 GEMV_CHAIN_MAX_JOBS = 64
 GEMV_CHAIN_SYNC_WORDS = GEMV_CHAIN_MAX_JOBS + 1
+GEMV_CHAIN_PDL = 1                 # mxq_gemv_chain_run flag (MXQ_GEMV_CHAIN_PDL)
 
 _lib = None
 

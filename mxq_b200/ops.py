@@ -469,7 +469,7 @@ class GemvChain:
         lib = L.lib()
         with L.on(self._launches[0][2]) as st:
             for host, plan_dev, sync in self._launches:
-                rc = lib.mxq_gemv_chain_run(host.data_ptr(), plan_dev.data_ptr(), sync.data_ptr(), 1 if pdl else 0, st)
+                rc = lib.mxq_gemv_chain_run(host.data_ptr(), plan_dev.data_ptr(), sync.data_ptr(), L.GEMV_CHAIN_PDL if pdl else 0, st)
                 L.check(rc, "mxq_gemv_chain_run")
 
 
