@@ -587,7 +587,7 @@ def run_components(ctx, pk, with_cpu=True):
         ych = [[torch.empty(oc, device=dev, dtype=torch.float16) for oc, _ in shapes] for _ in range(nl)]
         jobs = [(xl[li][xkey[i]], layer[i], ych[li][i], -1) for li, layer in enumerate(packs) for i in range(len(shapes))]
         chain = ops.GemvChain(jobs, validate=False)
-        nrep = 4        # several chain launches per graph: one launch per graph would time the replay overhead (~8 us)
+        nrep = 8        # several chain launches per graph: one launch per graph would time the replay overhead (~8 us)
         ms0 = graph_time(torch, lambda _: chain.run(), nrep, warm=1, reps=5)
         # back-to-back decode steps: MXQ_GEMV_CHAIN_PDL lets a launch build its tile lists and prefetch weights while
         # the previous launch's CTAs are still leaving (they leave up to 10 us apart); x is read after it has completed
@@ -600,7 +600,7 @@ def run_components(ctx, pk, with_cpu=True):
                             "algorithmic_bytes": gbytes, "ms_per_8_layers": ms, "launches": 1,
                             "ms_per_8_layers_without_pdl": ms0, "GBps_without_pdl": gbytes / ms0 / 1e6,
                             "note": "independent jobs: the weight-stream rate of one launch over 56 linears, launches back to back "
-                                    "(4 per graph replay) with programmatic dependent launch; the same without it beside"}
+                                    "(8 per graph replay) with programmatic dependent launch; the same without it beside"}
         # the same 56 linears as a DEPENDENT chain: q/k/v <- x, o <- q, gate/up <- o, down <- gate, next layer <- down
         dj, prev, xcur = [], -1, xl[0]["attn"]
         for li, layer in enumerate(packs):

@@ -84,6 +84,9 @@ constexpr int kMaxStages = 8;
 #define MXQ_CHAIN_BACKOFF 0
 #endif
 constexpr bool kWaitBackoff = MXQ_CHAIN_BACKOFF != 0;
+#ifndef MXQ_CHAIN_XPREFETCH
+#define MXQ_CHAIN_XPREFETCH 1
+#endif
 constexpr int kMaxTiles = 256;                // 16-row tiles of one CTA over the whole chain
 constexpr size_t kSmemMax = 227 * 1024 - 1024;
 
@@ -768,6 +771,15 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
       const JobD& J = jobs[j];
       if (J.share) continue;
       const int imgk = J.imgk, bsel = imgk & (kImgBars - 1);
+      // x of a job without an in-chain producer is complete: load this thread's first block BEFORE waiting for
+      // the image bytes to be released (an L2 hit takes 1-2 us next to the weight stream, most of a conversion)
+      const bool pre = MXQ_CHAIN_XPREFETCH && J.dep < 0 && bt < J.nblk;
+      uint4 a0 = make_uint4(0u, 0u, 0u, 0u), a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0, a7 = a0;
+      if (pre) {
+        const __half* xa = J.x + (size_t)bt * 64;
+        a0 = ld_cg16(xa), a1 = ld_cg16(xa + 8), a2 = ld_cg16(xa + 16), a3 = ld_cg16(xa + 24);
+        a4 = ld_cg16(xa + 32), a5 = ld_cg16(xa + 40), a6 = ld_cg16(xa + 48), a7 = ld_cg16(xa + 56);
+      }
       CTRACE(3, imgk, 0);
       if (J.imgwait >= 0) mbar_wait(&bars.imgempty[J.imgwait & (kImgBars - 1)], (uint32_t)(J.imgwait >> 3) & 1u);
       CTRACE(3, imgk, 1);
@@ -793,9 +805,11 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
           unsigned char* dst = xi + (size_t)Q * 2048 + iq * 512 + tq * 32;       // + k * 128 + h * 16
           const int ts = (Q * 16 + iq * 4 + tq) * 4;
           if (b < nblk) {
-            const __half* xa = J.x + (size_t)b * 64;
-            const uint4 a0 = ld_cg16(xa), a1 = ld_cg16(xa + 8), a2 = ld_cg16(xa + 16), a3 = ld_cg16(xa + 24);
-            const uint4 a4 = ld_cg16(xa + 32), a5 = ld_cg16(xa + 40), a6 = ld_cg16(xa + 48), a7 = ld_cg16(xa + 56);
+            if (!(pre && b == bt)) {
+              const __half* xa = J.x + (size_t)b * 64;
+              a0 = ld_cg16(xa), a1 = ld_cg16(xa + 8), a2 = ld_cg16(xa + 16), a3 = ld_cg16(xa + 24);
+              a4 = ld_cg16(xa + 32), a5 = ld_cg16(xa + 40), a6 = ld_cg16(xa + 48), a7 = ld_cg16(xa + 56);
+            }
             stage_group<0>(a0, a1, dst, tI + ts + 0, tF + ts + 0);
             stage_group<1>(a2, a3, dst + 128, tI + ts + 1, tF + ts + 1);
             stage_group<2>(a4, a5, dst + 256, tI + ts + 2, tF + ts + 2);
