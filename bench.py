@@ -593,10 +593,10 @@ def run_components(ctx, pk, with_cpu=True):
         # the previous launch's CTAs are still leaving (they leave up to 10 us apart); x is read after it has completed
         ms = graph_time(torch, lambda _: chain.run(pdl=True), nrep, warm=1, reps=5)
         ach = gbytes / ms / 1e6
-        tr, src = ncu_traffic("gemv_chain_kernel", "gemv_chain_32x4096x4096")
+        tr, src = ncu_traffic("gemv_chain_kernel", "gemv_chain_56linear")
         gemv["roofline"] = {"bound": "hbm", "kernel": "gemv_chain_kernel (persistent: TMA stage ring + IMMA m16n8k32, csrc/gemv_chain.cu)",
                             "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                            "traffic": tr, "traffic_source": (src or "") + " (32 x 4096x4096 jobs in one launch: 202,178,560 algorithmic bytes)",
+                            "traffic": tr, "traffic_source": (src or "") + " (this workload, one launch; profiles/r2j_ncu_full_gemv_chain56.csv)",
                             "algorithmic_bytes": gbytes, "ms_per_8_layers": ms, "launches": 1,
                             "ms_per_8_layers_without_pdl": ms0, "GBps_without_pdl": gbytes / ms0 / 1e6,
                             "note": "independent jobs: the weight-stream rate of one launch over 56 linears, launches back to back "

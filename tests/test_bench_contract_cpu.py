@@ -50,6 +50,11 @@ def test_ncu_traffic_lookup_reads_the_committed_capture():
     # the persistent decode chain: 32 x 4096^2 jobs of 6,318,080 packed + activation bytes each, read once
     t, src = bench.ncu_traffic("gemv_chain_kernel", "gemv_chain_32x4096x4096")
     assert t is not None and 0.99 < t / (32 * 6318080) < 1.06
+    # bench.py's own chain: the 56 linears of 8 layers (packed tensors + activations + outputs), read once
+    from mxq_b200.prune import packed_nbytes
+    algo = 8 * sum(packed_nbytes(oc, ic) + 2 * (oc + ic) for oc, ic in [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)])
+    t, src = bench.ncu_traffic("gemv_chain_kernel", "gemv_chain_56linear")
+    assert t is not None and 0.99 < t / algo < 1.06
     assert bench.ncu_traffic("no_such_kernel")[0] is None
     pk = bench.peaks()
     assert pk["hbm"] > 1000 and pk["tf_burst"] > 100 and pk["src"] in ("measured", "fallback")
