@@ -499,7 +499,10 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
     int kown = 0;                                             // stages this set has consumed
     const bool tr = (dbg & 8) && cta == 1 && warp == 0 && lane == 0;
     int ev = 0;
-    const int ntile = tcount[kMaxJobs], nimg = tcount[kMaxJobs + 1];
+    // the loop bound is re-read from shared memory once per tile: kept in a register it was spilled (128 registers
+    // are live in the loop body), and the local-memory reload -- an L2 round trip beside 227 KB of shared memory --
+    // held every compute warp ~5 % of its time at the loop's compare (ncu source view, stall_long_sb)
+    const volatile int* counts = tcount + kMaxJobs;          // [0] tiles of this CTA, [1] images
     // per-job state, reloaded when the job changes between two tiles of this set
     const unsigned char* ximg = img;
     const unsigned char* tabI = img;
@@ -520,7 +523,7 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
         mbar_wait(&bars.imgfull[lastimg & (kImgBars - 1)], (lastimg >> 3) & 1);
       }
     };
-    for (int e = set; e < ntile; e += kSets) {
+    for (int e = set; e < counts[0]; e += kSets) {
       const uint4 E = recs[e];
       const int j = (int)(E.x & 0xFFu), nrg = (int)((E.x >> 16) & 0xFFu), nch = (int)(E.z & 0xFFu);
       const int rg0 = (int)E.y;
@@ -645,7 +648,7 @@ gemv_chain_kernel(const __grid_constant__ ChainParams P, const CUtensorMap* __re
         ++ev;
       }
     }
-    step_images(nimg - 1);                                    // images that only other sets used
+    step_images(counts[1] - 1);                               // images that only other sets used
   } else if (warp == kProdA || warp == kProdB) {
     // =========================================== producers =========================================
     // A: the four tensor-map boxes (weight, weight_last, zeros_and_scales, zeros_2nd).  B: the 1-D bulk copies with
