@@ -37,10 +37,15 @@
 //   * the 4 K-partials of a tile meet in shared memory behind a named barrier of the set; one of the four
 //     warps adds them in a fixed order (deterministic), stores y and, if a later job depends on this one,
 //     counts the tile in the job's global counter with a release increment;
-//   * the builders convert x_j into the block-floating image of job j+1 while job j computes.  A job
-//     may name an earlier job `dep` whose y it reads as x (a real dependent chain): the builders then
-//     wait for the counter of `dep` (acquire) -- the weight stream of the waiting job is already in
-//     shared memory by then.  Launched cooperatively when a chain has dependencies (all CTAs co-resident).
+//   * the builders convert x_j into the block-floating image of job j+1 while job j computes (two image
+//     buffers, or a ring allocation with the builders two images ahead when a chain has jobs shorter than a
+//     conversion: place_images).  A job may name an earlier job `dep` whose y it reads as x (a real dependent
+//     chain): the builders then wait for the counter of `dep` (acquire) -- the weight stream of the waiting
+//     job is already in shared memory by then.  Launched cooperatively when a chain has dependencies (all
+//     CTAs co-resident);
+//   * chains without dependencies can be launched with programmatic dependent launch
+//     (MXQ_GEMV_CHAIN_PDL): set-up and weight prefetch overlap the tail of the previous kernel of the
+//     stream, activations are read after it has completed.
 //
 // Shapes: IC % 256 == 0, OC % 32 == 0, batch 1.  Other calls stay on gemv.cu / gemv_mma.cu.
 #include <cuda.h>
